@@ -1,0 +1,157 @@
+"""Generate the golden fixtures that pin ``oracle/``.  Run in the BUILD container only:
+
+    python tests/golden/make_golden.py
+
+Part 1 imports the reference's own torch-only source files straight from /root/reference
+(read-only; nothing is copied) and records their outputs on seeded inputs:
+``ref_*.npz``.  Part 2 records outputs of the independent in-container implementations of the
+third-party towers (``transformers`` Hubert / CLIP) on weights produced by
+``speechclip_b200.init.seeded_init_``: ``hf_*.npz``.  /root/reference does not exist on the GPU
+box, so tests only ever read the committed ``.npz`` files.
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference/avssl"
+
+
+def load_ref(rel, name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def save(name, **arrs):
+    out = {}
+    for k, v in arrs.items():
+        out[k] = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print("wrote", name, {k: out[k].shape for k in out})
+
+
+def part1_reference():
+    g = torch.Generator().manual_seed(7122)
+    # ---- MaskedContrastiveLoss (losses.py:129-245) incl. autograd grads
+    losses = load_ref("module/losses.py", "ref_losses")
+    for tag, B, D in (("small", 16, 32), ("mid", 64, 128)):
+        a = torch.nn.functional.normalize(torch.randn(B, D, generator=g), dim=-1).requires_grad_()
+        b = torch.nn.functional.normalize(torch.randn(B, D, generator=g), dim=-1).requires_grad_()
+        ids = torch.randperm(B, generator=g) // 3            # same-id groups exercise the negative mask
+        crit = losses.MaskedContrastiveLoss(temperature=0.07)
+        loss = crit(feat_A=a, feat_B=b, index=ids)
+        loss.backward()
+        crit_t = losses.MaskedContrastiveLoss(temperature=0.07, temperature_trainable=True)
+        a2, b2 = a.detach().clone().requires_grad_(), b.detach().clone().requires_grad_()
+        loss_t = crit_t(feat_A=a2, feat_B=b2, index=ids)
+        loss_t.backward()
+        loss_noid = crit(feat_A=a.detach(), feat_B=b.detach(), index=None)
+        save(f"ref_loss_{tag}.npz", a=a, b=b, ids=ids, loss=loss, da=a.grad, db=b.grad,
+             loss_t=loss_t, da_t=a2.grad, db_t=b2.grad, dtemp=crit_t.temperature.grad,
+             temp_param=crit_t.temperature, loss_noid=loss_noid)
+    try:
+        losses.MaskedContrastiveLoss()(torch.randn(300, 8), torch.randn(300, 8), torch.arange(300))
+        raised = False
+    except IndexError:
+        raised = True
+    print("reference loss raises IndexError for B>256 (MAX_EYE):", raised)
+
+    # ---- WeightedSumLayer (weighted_sum.py:26-45)
+    ws = load_ref("module/weighted_sum.py", "ref_ws")
+    hidden = [torch.randn(2, 7, 16, generator=g) for _ in range(5)]
+    w = torch.randn(5, generator=g)
+    outs = {}
+    for norm in (False, True):
+        layer = ws.WeightedSumLayer(5, normalize_features=norm)
+        layer.weights.data.copy_(w)
+        outs[f"out_norm{int(norm)}"] = layer(hidden)
+    save("ref_weighted_sum.npz", hidden=torch.stack(hidden), weights=w, **outs)
+
+    # ---- get_keypadding_mask (data_utils.py:4-20)
+    du = load_ref("util/data_utils.py", "ref_du")
+    lens = torch.tensor([1, 5, 9, 12, 3])
+    save("ref_keypad.npz", lens=lens, mask=du.get_keypadding_mask(12, lens))
+
+    # ---- TransformerEncoder branch (TransformerModels.py:48-96), eval mode
+    tm = load_ref("module/kw_modules/TransformerModels.py", "ref_tm")
+    for tag, norm_first in (("postln", False), ("preln", True)):
+        torch.manual_seed(11)
+        enc = tm.TransformerEncoder(n_layers=1, d_model=64, nhead=8, dim_feedforward=128, dropout=0.1,
+                                    activation="gelu", layer_norm_eps=1e-5, batch_first=True, norm_first=norm_first)
+        for p in enc.parameters():
+            p.data.add_(0.05 * torch.randn(p.shape, generator=g))
+        enc.eval()
+        src = torch.randn(3, 11, 64, generator=g)
+        kpm = du.get_keypadding_mask(11, torch.tensor([11, 4, 8]))
+        with torch.no_grad():
+            out = enc(src, kpm)
+            hs = enc.extract_hidden_states(src, kpm)
+        sd = {"sd." + k: v for k, v in enc.state_dict().items()}
+        save(f"ref_branch_{tag}.npz", src=src, kpm=kpm, out=out, h0=hs[0], h1=hs[1], **sd)
+
+    # ---- mutualRetrieval (retrieval.py:6-121)
+    rt = load_ref("module/retrieval.py", "ref_rt")
+    nA, nB = 40, 8
+    score = torch.randn(nA, nB, generator=g)
+    ab = torch.arange(nA) // 5
+    ba = torch.arange(nB)
+    rAB, rBA, rM = rt.mutualRetrieval(score, score.T.contiguous(), ab, ba, [1, 5, 10])
+    save("ref_retrieval.npz", score=score, ab=ab, ba=ba,
+         rAB=[rAB[f"recall@{k}"] for k in (1, 5, 10)], rBA=[rBA[f"recall@{k}"] for k in (1, 5, 10)],
+         rM=[rM[f"recall@{k}"] for k in (1, 5, 10)])
+
+    # ---- linear_warmup_decay (scheduler.py:22-38)
+    sch = load_ref("optim/scheduler.py", "ref_sch")
+    opt = torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))], lr=1e-4)
+    s = sch.get_scheduler("linear_warmup_decay", opt, warmup=5, max_step=20, final_lr=1e-8)
+    lrs = []
+    for _ in range(20):
+        lrs.append(opt.param_groups[0]["lr"])
+        opt.step()
+        s.step()
+    save("ref_scheduler.npz", lrs=np.array(lrs, dtype=np.float64))
+
+    # ---- random_crop_max_length semantics (audio_transforms.py:5-23): shapes only (np.random offset)
+    at = load_ref("data/audio_transforms.py", "ref_at")
+    assert at.random_crop_max_length(torch.arange(10), 4, 10).shape == (4,)
+    assert at.random_crop_max_length(torch.arange(10), 20, 10).shape == (10,)
+    assert at.random_crop_max_length(torch.arange(10), -1, 10).shape == (10,)
+
+
+def part2_hf():
+    import transformers
+    from oracle import clip as oc
+    from oracle import hubert as oh
+    from speechclip_b200.init import seeded_init_
+    from tests.hf_map import hf_clip_from_oracle, hf_hubert_from_oracle
+
+    g = torch.Generator().manual_seed(7122)
+    for name in ("tiny", "tiny_large"):
+        cfg = oh.HubertCfg.named(name)
+        om = seeded_init_(oh.HubertModel(cfg), 7122).eval()
+        hf = hf_hubert_from_oracle(om)
+        wav = 0.1 * torch.randn(2, 4000, generator=g)
+        with torch.no_grad():
+            o = hf(wav, output_hidden_states=True)
+        save(f"hf_hubert_{name}.npz", wav=wav, **{f"h{i}": h for i, h in enumerate(o.hidden_states)})
+    ccfg = oc.ClipCfg.named("tiny")
+    om = seeded_init_(oc.CLIP(ccfg), 7122).eval()
+    hv, ht = hf_clip_from_oracle(om)
+    img = torch.randn(3, 3, ccfg.image_size, ccfg.image_size, generator=g)
+    tok = torch.randint(1, ccfg.vocab - 1, (3, ccfg.context), generator=g)
+    tok[:, 9] = ccfg.vocab - 1  # EOT = largest id, as in CLIP's tokenizer
+    with torch.no_grad():
+        save("hf_clip_tiny.npz", img=img, tok=tok, image_embeds=hv(pixel_values=img).image_embeds,
+             text_embeds=ht(input_ids=tok).text_embeds)
+
+
+if __name__ == "__main__":
+    part1_reference()
+    part2_hf()
