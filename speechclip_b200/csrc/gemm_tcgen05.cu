@@ -1,0 +1,340 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   warp 0 (1 thread)  TMA producer : cp.async.bulk.tensor A/B tiles -> 128B-swizzled smem ring
+//   warp 1 (1 thread)  MMA issuer   : tcgen05.mma 128 x N x 16, fp32 accumulators in TMEM (2 buffers)
+//   warp 2             TMEM allocator
+//   warps 4..11        epilogue     : tcgen05.ld -> alpha/bias/activation/residual -> global stores
+//
+// The two TMEM accumulator buffers let the epilogue of tile i overlap the MMAs of tile i+1.
+// See include/speechclip_b200.h (scb_gemm) for the operand model (plain / strided-conv / grouped tap walk).
+#include "common.cuh"
+#include "ops.cuh"
+
+namespace scb {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = (4 + kEpiWarps) * 32;
+
+struct GemmParams {
+  int batch, m_tiles_per_batch, n_tiles, groups, num_tiles;
+  int m_per_batch, n, k_blocks;
+  int kb_per_tap, tap_row_shift, a_col0, a_group_cols;
+  int umma_n;
+  uint32_t tx_bytes;
+  void* out;
+  void* out2;
+  const float* bias;
+  const void* residual;
+  int out_dtype, out2_dtype, residual_dtype, act, ab_bf16;
+  float alpha;
+  long long ldc, out_batch_stride;
+  int out_group_cols;
+};
+
+struct TileCoord {
+  int g, b, m0, n0;
+};
+
+template <int BN>
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) {
+  TileCoord t;
+  const int nt = tile % p.n_tiles;
+  int rest = tile / p.n_tiles;
+  const int mt = rest % p.m_tiles_per_batch;
+  rest /= p.m_tiles_per_batch;
+  t.b = rest % p.batch;
+  t.g = rest / p.batch;
+  t.m0 = mt * BM;
+  t.n0 = nt * BN;
+  return t;
+}
+
+__device__ __forceinline__ void store8(void* base, int dtype, long long off, const float (&x)[8]) {
+  if (dtype == SCB_F32) {
+    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off);
+    o[0] = make_float4(x[0], x[1], x[2], x[3]);
+    o[1] = make_float4(x[4], x[5], x[6], x[7]);
+  } else {
+    uint4 u;
+    u.x = pack16(dtype, x[0], x[1]);
+    u.y = pack16(dtype, x[2], x[3]);
+    u.z = pack16(dtype, x[4], x[5]);
+    u.w = pack16(dtype, x[6], x[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(base) + off) = u;
+  }
+}
+
+__device__ __forceinline__ void load8(const void* base, int dtype, long long off, float (&x)[8]) {
+  if (dtype == SCB_F32) {
+    const float4* r = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+    const float4 a = __ldg(r), b = __ldg(r + 1);
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
+    x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+  } else {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(base) + off));
+    float2 f;
+    f = unpack16(dtype, u.x); x[0] = f.x; x[1] = f.y;
+    f = unpack16(dtype, u.y); x[2] = f.x; x[3] = f.y;
+    f = unpack16(dtype, u.z); x[4] = f.x; x[5] = f.y;
+    f = unpack16(dtype, u.w); x[6] = f.x; x[7] = f.y;
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  constexpr int A_BYTES = BM * BK * 2;
+  constexpr int B_BYTES = BN * BK * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], kEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile<BN>(p, tile);
+      const int a_c0 = p.a_col0 + t.g * p.a_group_cols;
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1u);
+        mbar_expect_tx(&full[stage], p.tx_bytes);
+        const int tap = kb / p.kb_per_tap;
+        const int kin = kb - tap * p.kb_per_tap;
+        tma_load_3d(sA + stage * A_BYTES, &tmA, &full[stage], a_c0 + kin * BK, t.m0 + tap * p.tap_row_shift, t.b);
+        tma_load_3d(sB + stage * B_BYTES, &tmB, &full[stage], kb * BK, t.n0, t.g);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = umma_idesc_f16(BM, p.umma_n, p.ab_bf16);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(sA + stage * A_BYTES));
+        const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(sB + stage * B_BYTES));
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 elements (32 B) inside the 128 B swizzle row: +2 in the (addr >> 4) field
+          tc_mma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+        }
+        tc_commit(&empty[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      tc_commit(&tfull[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;            // TMEM lane quarter this warp may touch
+    const int half = (warp - 4) >> 2;  // which half of the tile's columns
+    constexpr int COLS_PER_WARP = BN / 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile<BN>(p, tile);
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int m = t.m0 + q * 32 + lane;
+      const bool row_ok = m < p.m_per_batch;
+      const long long row_off = (long long)t.b * p.out_batch_stride + (long long)m * p.ldc + (long long)t.g * p.out_group_cols;
+      const int col_base = t.n0 + half * COLS_PER_WARP;
+      int nchunks = 0;
+      if (col_base < p.n) nchunks = min(COLS_PER_WARP / 32, (p.n - col_base + 31) / 32);
+      if (nchunks == 0) {
+        tc_fence_before();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+      }
+      for (int ch = 0; ch < nchunks; ++ch) {
+        uint32_t v[32];
+        const int c0 = col_base + ch * 32;
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * COLS_PER_WARP + ch * 32), v);
+        tmem_ld_wait();
+        if (ch == nchunks - 1) {  // accumulator fully read by this warp: hand the buffer back to the MMA warp
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col = c0 + j * 8;
+            if (col < p.n) {
+              float x[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x[i] = p.alpha * __uint_as_float(v[j * 8 + i]);
+              if (p.bias) {
+                const float4* bp = reinterpret_cast<const float4*>(p.bias + t.g * p.out_group_cols + col);
+                const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
+                x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+                x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+              }
+              if (p.act == SCB_ACT_GELU_ERF) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = gelu_erf(x[i]);
+              } else if (p.act == SCB_ACT_QUICK_GELU) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = quick_gelu(x[i]);
+              }
+              const long long off = row_off + col;
+              if (p.residual) {
+                float r[8];
+                load8(p.residual, p.residual_dtype, off, r);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] += r[i];
+              }
+              store8(p.out, p.out_dtype, off, x);
+              if (p.out2) store8(p.out2, p.out2_dtype, off, x);
+            }
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<2 * BN>(tmem_base);
+  }
+}
+
+template <int BN, int STAGES>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  constexpr int smem_bytes = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    SCB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured = true;
+  }
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  gemm_tcgen05_kernel<BN, STAGES><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
+  note_launch();
+  SCB_LAUNCH_OK("gemm_tcgen05");
+  return SCB_OK;
+}
+
+}  // namespace
+
+int gemm(const scb_gemm_args& a, cudaStream_t stream) {
+  SCB_CHECK(a.a && a.b && a.out, SCB_EINVAL, "scb_gemm: null operand");
+  SCB_CHECK(a.ab_format == SCB_F16 || a.ab_format == SCB_BF16, SCB_EINVAL, "scb_gemm: ab_format must be F16 or BF16");
+  SCB_CHECK(a.n > 0 && a.k > 0 && a.batch > 0 && a.m_per_batch > 0 && a.groups > 0, SCB_EINVAL, "scb_gemm: empty problem");
+  SCB_CHECK(a.n % 8 == 0, SCB_EINVAL, "scb_gemm: n (%d) must be a multiple of 8", a.n);
+  SCB_CHECK(a.ldc % 8 == 0 && a.out_group_cols % 8 == 0 && a.out_batch_stride % 8 == 0, SCB_EINVAL,
+            "scb_gemm: output strides must be multiples of 8 elements");
+  SCB_CHECK(a.a_row_stride % 8 == 0 && a.b_row_stride % 8 == 0 && a.a_batch_stride % 8 == 0 && a.b_group_stride % 8 == 0,
+            SCB_EINVAL, "scb_gemm: operand strides must be multiples of 8 elements (16 bytes)");
+  SCB_CHECK((reinterpret_cast<uintptr_t>(a.a) | reinterpret_cast<uintptr_t>(a.b) | reinterpret_cast<uintptr_t>(a.out) |
+             reinterpret_cast<uintptr_t>(a.out2) | reinterpret_cast<uintptr_t>(a.residual) |
+             reinterpret_cast<uintptr_t>(a.bias)) % 16 == 0,
+            SCB_EINVAL, "scb_gemm: pointers must be 16-byte aligned");
+  SCB_CHECK(a.kb_per_tap > 0, SCB_EINVAL, "scb_gemm: kb_per_tap must be positive");
+  SCB_CHECK(a.groups == 1 || a.out_group_cols >= a.n, SCB_EINVAL, "scb_gemm: out_group_cols < n");
+
+  const int bn = a.n > 128 ? 256 : (a.n > 64 ? 128 : 64);
+  GemmParams p{};
+  p.batch = a.batch;
+  p.m_tiles_per_batch = (a.m_per_batch + BM - 1) / BM;
+  p.n_tiles = (a.n + bn - 1) / bn;
+  p.groups = a.groups;
+  p.num_tiles = p.groups * p.batch * p.m_tiles_per_batch * p.n_tiles;
+  p.m_per_batch = a.m_per_batch;
+  p.n = a.n;
+  p.k_blocks = (a.k + BK - 1) / BK;
+  p.kb_per_tap = a.kb_per_tap;
+  p.tap_row_shift = a.tap_row_shift;
+  p.a_col0 = a.a_col0;
+  p.a_group_cols = a.a_group_cols;
+  p.umma_n = ((a.n < bn ? a.n : bn) + 15) / 16 * 16;
+  p.tx_bytes = (uint32_t)(BM * BK * 2 + p.umma_n * BK * 2);
+  p.out = a.out;
+  p.out2 = a.out2;
+  p.bias = a.bias;
+  p.residual = a.residual;
+  p.out_dtype = a.out_dtype;
+  p.out2_dtype = a.out2_dtype;
+  p.residual_dtype = a.residual_dtype;
+  p.act = a.act;
+  p.ab_bf16 = a.ab_format == SCB_BF16;
+  p.alpha = a.alpha;
+  p.ldc = a.ldc;
+  p.out_batch_stride = a.out_batch_stride;
+  p.out_group_cols = a.out_group_cols;
+
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t rows = (uint64_t)a.a_rows;
+    const uint64_t bstride = a.a_batch_stride ? (uint64_t)a.a_batch_stride : rows * (uint64_t)a.a_row_stride;
+    const uint64_t dims[3] = {(uint64_t)a.a_inner, rows, (uint64_t)a.batch};
+    const uint64_t strides[2] = {(uint64_t)a.a_row_stride * 2, bstride * 2};
+    const uint32_t box[3] = {BK, BM, 1};
+    int e = make_tmap_16b(&tmA, a.a, 3, dims, strides, box, 1);
+    if (e) return e;
+  }
+  {
+    const uint64_t gstride = a.b_group_stride ? (uint64_t)a.b_group_stride : (uint64_t)a.n * (uint64_t)a.b_row_stride;
+    const uint64_t dims[3] = {(uint64_t)a.k, (uint64_t)a.n, (uint64_t)a.groups};
+    const uint64_t strides[2] = {(uint64_t)a.b_row_stride * 2, gstride * 2};
+    const uint32_t box[3] = {BK, (uint32_t)p.umma_n, 1};
+    int e = make_tmap_16b(&tmB, a.b, 3, dims, strides, box, 1);
+    if (e) return e;
+  }
+  if (bn == 256) return launch<256, 4>(tmA, tmB, p, stream);
+  if (bn == 128) return launch<128, 6>(tmA, tmB, p, stream);
+  return launch<64, 8>(tmA, tmB, p, stream);
+}
+
+}  // namespace scb

@@ -1,0 +1,118 @@
+"""ctypes binding of libspeechclip_b200.so (the C ABI declared in include/speechclip_b200.h).
+
+The product path has no fallback: if the shared library is missing or a call fails, a
+``RuntimeError`` is raised.  ``ensure_built()`` compiles the library in-tree with nvcc when the
+sources are newer than the binary (nvcc cross-compiles sm_100a without a GPU).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+_INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
+LIB_PATH = os.path.join(_HERE, "libspeechclip_b200.so")
+
+F32, F16, BF16 = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_QUICK_GELU = 0, 1, 2
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _sources():
+    return sorted(os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".cu"))
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)] + [os.path.join(_INCLUDE, "speechclip_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def ensure_built(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu into libspeechclip_b200.so for sm_100a (in-tree, so it travels to the GPU box)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs, procs = [], []
+    for src in _sources():  # one nvcc per translation unit, in parallel
+        obj = src[:-3] + ".o"
+        objs.append(obj)
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+               "-Xcompiler", "-fPIC", "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose and out:
+            print(out)
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd) + "\n" + out)
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs + ["-lcudart"]
+    r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed: " + r.stdout)
+    return LIB_PATH
+
+
+class GemmArgs(ctypes.Structure):
+    _fields_ = [
+        ("a", ctypes.c_void_p),
+        ("a_inner", ctypes.c_int64), ("a_rows", ctypes.c_int64), ("a_row_stride", ctypes.c_int64), ("a_batch_stride", ctypes.c_int64),
+        ("batch", ctypes.c_int32), ("m_per_batch", ctypes.c_int32),
+        ("kb_per_tap", ctypes.c_int32), ("tap_row_shift", ctypes.c_int32), ("a_col0", ctypes.c_int32), ("a_group_cols", ctypes.c_int32),
+        ("b", ctypes.c_void_p),
+        ("b_row_stride", ctypes.c_int64), ("b_group_stride", ctypes.c_int64),
+        ("n", ctypes.c_int32), ("k", ctypes.c_int32), ("groups", ctypes.c_int32),
+        ("out", ctypes.c_void_p),
+        ("out_dtype", ctypes.c_int32), ("out_group_cols", ctypes.c_int32),
+        ("ldc", ctypes.c_int64), ("out_batch_stride", ctypes.c_int64),
+        ("out2", ctypes.c_void_p),
+        ("out2_dtype", ctypes.c_int32), ("ab_format", ctypes.c_int32),
+        ("bias", ctypes.c_void_p),
+        ("residual", ctypes.c_void_p),
+        ("residual_dtype", ctypes.c_int32), ("act", ctypes.c_int32),
+        ("alpha", ctypes.c_float),
+    ]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def _declare(lib):
+    vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+    lib.scb_abi_version.restype = i32
+    lib.scb_last_error.restype = ctypes.c_char_p
+    lib.scb_launch_count.restype = i64
+    lib.scb_gemm.argtypes = [ctypes.POINTER(GemmArgs), vp]
+    lib.scb_gemm.restype = i32
+
+
+def load():
+    """Return the loaded library; raise loudly if it is absent (no CPU / eager fallback exists)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing: the CUDA extension is the only implementation of the hot path. "
+                    "Run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc).")
+            lib = ctypes.CDLL(LIB_PATH)
+            _declare(lib)
+            _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed ({rc}): {load().scb_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(load().scb_launch_count())
