@@ -1,0 +1,412 @@
+"""SpeechCLIP model (reference: avssl/model/kwClip.py — KWClipBase :49-695, KW_ParallelBranch :1004-1108,
+KWClip_GeneralTransformer :1111-1496) for the Parallel configuration, B200-native.
+
+Same LightningModule surface: ``forward(batch) -> (losses, log_metrics, others)``, ``training_step`` returns features,
+``training_step_end`` computes the contrastive loss over the GLOBAL batch, ``compute_loss``, ``encode_speech``,
+``feature_extractor_s3prl``, ``validation_*``, ``configure_optimizers``.  The reference gets the global batch from
+Lightning's single-process DataParallel gather (``strategy: dp``); here it is one process per GPU and
+``training_step_end`` all-gathers the pooled embeddings + ids over NCCL (``gather_features``), then every rank evaluates
+the masked InfoNCE on the full matrix and back-propagates its own rows.
+"""
+import logging
+from typing import List, Tuple, Union
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from speechclip_b200 import ops
+from speechclip_b200.functional import GradArena, L2NormFn, ParallelBranchFn
+from speechclip_b200.head import PARAM_ORDER, ParallelHead
+from speechclip_b200.optim import FusedAdam
+
+from ..base import OrderedNamespace
+from ..module import ClipModel, FairseqSpeechEncoder_Hubert, MLPLayers, losses, mutualRetrieval
+from ..module.kw_modules import TransformerModels
+from ..optim import get_scheduler
+from .base_model import BaseLightningModel
+
+logger = logging.getLogger(__name__)
+
+__all__ = ["KWClipBase", "KW_ParallelBranch", "KWClip_GeneralTransformer"]
+
+METRIC_REDUCEFN_MAPPING = {
+    torch.Tensor: lambda x: torch.mean(x),
+    float: lambda x: x,
+    int: lambda x: x,
+    str: lambda x: x,
+}
+
+
+def l2_normalize(x: torch.Tensor) -> torch.Tensor:
+    return L2NormFn.apply(x)
+
+
+def _all_gather_rows(x: torch.Tensor) -> torch.Tensor:
+    x = x.contiguous()
+    out = torch.empty((dist.get_world_size() * x.shape[0],) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
+    dist.all_gather_into_tensor(out, x)
+    return out
+
+
+class _GatherRows(torch.autograd.Function):
+    """all_gather along dim 0 over the default process group (NCCL over NVLink on the GPU box); backward hands every rank
+    the gradient rows of its own slice — each rank evaluates the same global loss, so no reduction is needed here, and the
+    per-rank parameter gradients are summed afterwards (``KWClipBase.allreduce_gradients``)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.rows = x.shape[0]
+        return _all_gather_rows(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        rank = dist.get_rank()
+        return g[rank * ctx.rows:(rank + 1) * ctx.rows]
+
+
+def gather_features(feats: dict) -> dict:
+    """Per-rank ``{id, image_feat, parallel_audio_feat}`` -> the same dict over the global batch (rank-major order).
+    Replaces Lightning's DataParallel gather in front of ``training_step_end`` (kwClip.py:147-167)."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return feats
+    out = {}
+    for k, v in feats.items():
+        if isinstance(v, torch.Tensor) and v.dim() >= 1:
+            out[k] = _GatherRows.apply(v) if v.requires_grad else _all_gather_rows(v)
+        else:
+            out[k] = v
+    return out
+
+
+class KWClipBase(BaseLightningModel):
+    """Base class for SpeechCLIP (kwClip.py:49-695)."""
+
+    def __init__(self, config: OrderedNamespace):
+        super().__init__(config)
+        self.audio_encoder_type = config.audio_encoder.type
+        if self.audio_encoder_type == "FairseqHubert":
+            self.audio_encoder = FairseqSpeechEncoder_Hubert(**config.audio_encoder)
+        elif self.audio_encoder_type in ("s3prl", "s3prl_plus"):
+            raise NotImplementedError("s3prl speech encoders are outside the B200 hot path (no shipped config selects them)")
+        else:
+            logger.warning("No audio encoder loaded")
+        self.clip = ClipModel(**config.clip)
+        if hasattr(self, "audio_encoder"):
+            self.audio_embd_dim = self.audio_encoder.out_dim
+        self.subword_embd_dim = self.clip.model.token_embedding.weight.size(-1)
+        self.recall_at = config.retrieval.recall_at
+        self.criterion = getattr(losses, config.cl_loss.type)(**config.cl_loss.args)
+        self.log_detokenize_results = config.log_setting.get("log_detokenize_results", True)
+        self.keyword_num = self.config.model_settings.cascaded_branch.keyword.number
+        self._arena = None
+
+    # ------------------------------------------------------------------------------------------------- arena
+    def arena(self) -> GradArena:
+        """Flat storage shared by the backward kernels and FusedAdam; rebuilt if ``.to()`` re-homed the parameters."""
+        if self._arena is None or not self._arena.intact():
+            params = [p for p in self.getTrainableParams() if p.requires_grad]
+            if not params or not params[0].is_cuda:
+                return None
+            self._arena = GradArena(params)
+        return self._arena
+
+    def _wire_arena(self):
+        fn = self.arena
+        if hasattr(self, "audio_encoder") and hasattr(self.audio_encoder, "weightedsum_layer"):
+            self.audio_encoder.weightedsum_layer._scb_arena_fn = fn
+        self.criterion._scb_arena_fn = fn
+
+    # ------------------------------------------------------------------------------------------------- towers
+    def forward_audio(self, wav: Union[torch.Tensor, list], wav_len: Union[torch.Tensor, list] = [],
+                      return_hidden_states: bool = False):
+        if self.audio_encoder_type in ["s3prl_plus", "FairseqHubert"]:
+            return self.audio_encoder(wav, wav_len, return_hidden_states=return_hidden_states)
+        raise NotImplementedError("Unknown type:{}".format(self.audio_encoder_type))
+
+    def forward_image(self, images: Union[list, torch.Tensor]) -> torch.Tensor:
+        if isinstance(images, list):
+            image_tensor = self.clip.prep_image(images).to(self.device)
+        elif isinstance(images, torch.Tensor):
+            if images.dim() != 4 or images.shape[1] != 3:
+                raise ValueError(f"Incorrect image tensor shape {images.shape}")
+            image_tensor = images
+        else:
+            raise TypeError(f"Unknown image type {type(images)}")
+        return self.clip.encode_image(image_tensor)
+
+    def forward_text(self, sents: Union[list, torch.Tensor]) -> torch.Tensor:
+        if isinstance(sents, list):
+            text_tensor = self.clip.prep_text(sents).to(self.device)
+        elif isinstance(sents, torch.Tensor):
+            if sents.dim() != 2:
+                raise ValueError(f"Incorrect text tensor shape {sents.shape}")
+            text_tensor = sents
+        else:
+            raise TypeError(f"Unknown text type {type(sents)}")
+        return self.clip.encode_text(text_tensor)
+
+    def forward(self, batch: dict) -> tuple:
+        raise NotImplementedError()
+
+    def compute_loss(self, input_feats):
+        raise NotImplementedError()
+
+    # ------------------------------------------------------------------------------------------------- training hooks
+    def training_step(self, batch: dict, batch_idx=None) -> dict:
+        losses_, log_metrics = self.forward(batch)[:2]
+        return {"loss_feats": losses_, "log_metrics": log_metrics}
+
+    def training_step_end(self, outputs: dict) -> dict:
+        if isinstance(outputs, dict):
+            if "loss" in outputs:
+                return {"loss": torch.mean(outputs["loss"])}
+            elif "loss_feats" in outputs and "log_metrics" in outputs:
+                losses_ = self.compute_loss(gather_features(outputs["loss_feats"]))
+                log_metrics = outputs["log_metrics"]
+                result = {
+                    **{f"train_{k}": losses_[k] for k in losses_},
+                    **{f"train_{k}": METRIC_REDUCEFN_MAPPING[type(log_metrics[k])](log_metrics[k]) for k in log_metrics},
+                }
+                self.log_dict(result, on_step=True, on_epoch=True, prog_bar=True, logger=True, sync_dist=True)
+                return {"loss": losses_["loss"]}
+            raise NotImplementedError()
+        raise NotImplementedError()
+
+    def on_after_backward(self):
+        self.allreduce_gradients()
+
+    def allreduce_gradients(self):
+        """Sum the per-rank gradients of the trainable head (one NCCL all-reduce over the flat gradient buffer)."""
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        arena = self.arena()
+        g0 = arena.params[0].grad
+        for k in (0, 1):
+            if g0 is not None and g0.data_ptr() == arena.flat_g[k].data_ptr() + 4 * arena.offsets[0]:
+                dist.all_reduce(arena.flat_g[k])
+                return
+        for p in arena.params:  # gradients that autograd did not adopt in place
+            if p.grad is not None:
+                dist.all_reduce(p.grad)
+
+    # ------------------------------------------------------------------------------------------------- validation hooks
+    def validation_step(self, batch: dict, batch_idx: int = 0) -> dict:
+        losses_, log_metrics, others = self.forward(batch)
+        audio_feat = (others["cascaded_audio_feat"] if self.config.retrieval.audio_feat_src == "cascaded"
+                      else others["parallel_audio_feat"])
+        return_dict = {"id": others["id"], "audio_feat": audio_feat}
+        if others.get("image_feat") is not None:
+            return_dict["image_feat"] = others["image_feat"]
+        return {"loss_feats": losses_, "log_metrics": log_metrics, "others": return_dict}
+
+    def validation_step_end(self, outputs: dict) -> dict:
+        assert isinstance(outputs, dict)
+        losses_ = self.compute_loss(outputs["loss_feats"])
+        log_metrics = outputs["log_metrics"]
+        result = {
+            **{f"val_{k}": losses_[k] for k in losses_},
+            **{f"val_{k}": METRIC_REDUCEFN_MAPPING[type(log_metrics[k])](log_metrics[k]) for k in log_metrics},
+        }
+        self.log_dict(result, on_step=True, on_epoch=True, prog_bar=True, logger=True, sync_dist=True)
+        return {k: (v.detach() if isinstance(v, torch.Tensor) else v) for k, v in outputs["others"].items()}
+
+    def validation_epoch_end(self, outputs: list):
+        """kwClip.py:468-502: de-duplicate images by id, score = A I^T, recall@k both ways."""
+        dev = self.device
+        all_ids = torch.cat([x["id"] for x in outputs], dim=0).to(dev)
+        all_imgs = torch.cat([x["image_feat"] for x in outputs], dim=0).to(dev)
+        all_audio = torch.cat([x["audio_feat"] for x in outputs], dim=0).to(dev).float().contiguous()
+        # last occurrence of every id wins, first-seen order is kept (the reference's dict comprehension)
+        ids_host = all_ids.cpu().tolist()
+        last = {}
+        for i, _id in enumerate(ids_host):
+            last[_id] = i
+        img_ids = list(last.keys())
+        all_img_feats = all_imgs[torch.tensor([last[i] for i in img_ids], device=dev)].float().contiguous()
+        all_img_ids = torch.tensor(img_ids, dtype=torch.int64, device=dev)
+        print("Total #{} images, #{} audio".format(len(all_img_feats), len(all_audio)))
+        score_per_audio = torch.empty(all_audio.shape[0], all_img_feats.shape[0], device=dev, dtype=torch.float32)
+        ops.sgemm(all_audio, all_img_feats, score_per_audio)
+        score_per_image = torch.empty(all_img_feats.shape[0], all_audio.shape[0], device=dev, dtype=torch.float32)
+        ops.sgemm(all_img_feats, all_audio, score_per_image)
+        return self.reportRetrieval(score_per_A=score_per_audio, score_per_B=score_per_image, AB_answers=all_ids,
+                                    BA_answers=all_img_ids)
+
+    def reportRetrieval(self, score_per_A, score_per_B, AB_answers, BA_answers,
+                        metadata: dict = {"modality_A_title": "audio", "modality_B_title": "image", "modality_A_logAbbr": "A",
+                                          "modality_B_logAbbr": "I"}):
+        rAB, rBA, rMean = mutualRetrieval(score_per_A=score_per_A, score_per_B=score_per_B, AB_answers=AB_answers,
+                                          BA_answers=BA_answers, recall_at=self.recall_at,
+                                          modality_A_title=metadata["modality_A_title"], modality_B_title=metadata["modality_B_title"])
+        ab = "{}{}".format(metadata["modality_A_logAbbr"], metadata["modality_B_logAbbr"])
+        ba = "{}{}".format(metadata["modality_B_logAbbr"], metadata["modality_A_logAbbr"])
+        print(f"val_recall_{ab}", rAB)
+        print(f"val_recall_{ba}", rBA)
+        print("val_recall_mean", rMean)
+        self.log(f"val_recall_{ab}", rAB, sync_dist=True)
+        self.log(f"val_recall_{ba}", rBA, sync_dist=True)
+        self.log("val_recall_mean", rMean, sync_dist=True)
+        if "recall@10" in rMean:
+            self.log("val_recall_mean_10", rMean["recall@10"], sync_dist=True)
+        return rAB, rBA, rMean
+
+    def processWavs(self, wav) -> Tuple[torch.Tensor, list]:
+        return wav, [len(x) for x in wav]
+
+    def feature_extractor_s3prl(self, wav):
+        raise NotImplementedError()
+
+    def getTrainableParams(self) -> list:
+        my_params = []
+        if hasattr(self, "audio_encoder"):
+            my_params += self.audio_encoder.trainable_params()
+            my_params += list(self.criterion.parameters())
+        my_params += self.clip.trainable_params()
+        return my_params
+
+    def configure_optimizers(self) -> Tuple[list, list]:
+        """kwClip.py:666-694.  ``Adam`` maps to the fused clip+Adam kernel (same update rule); the global-norm clip of the
+        Trainer (``trainer.gradient_clip_val``) is applied inside the same pass when ``fuse_grad_clip`` is left on."""
+        my_params = self.getTrainableParams()
+        name = self.config.audio_encoder.optim.name
+        if name != "Adam":
+            raise NotImplementedError(f"optimizer {name}: only Adam (every shipped config) has a fused B200 step")
+        self._wire_arena()
+        clip_val = float(self.config.trainer.get("gradient_clip_val", 0.0) or 0.0) if self.config.get("fuse_grad_clip", True) else 0.0
+        audio_optimizer = FusedAdam(my_params, **self.config.audio_encoder.optim.args, max_grad_norm=clip_val, arena_fn=self.arena)
+        audio_scheduler = get_scheduler(optimizer=audio_optimizer, **self.config.audio_encoder.scheduler)
+        return [audio_optimizer], [{"scheduler": audio_scheduler, "interval": "step"}]
+
+
+class KW_ParallelBranch(nn.Module):
+    """The parallel branch (kwClip.py:1004-1108): [CLS] + transformer encoder + projection."""
+
+    def __init__(self, config: OrderedNamespace, audio_dim: int, out_dim: int) -> None:
+        super().__init__()
+        self.config = config
+        self.audio_dim = audio_dim
+        self.out_dim = out_dim
+        pb = self.config.model_settings.parallel_branch
+        self.need_projection = pb.get("need_projection", True)
+        assert hasattr(TransformerModels, pb.transformer_type)
+        logger.info(f"Using {pb.transformer_type} as KW_ParallelBranch (projection={self.need_projection})")
+        self.self_att = getattr(TransformerModels, pb.transformer_type)(**pb.transformer_args)
+        self.cls = self._create_cls()
+        if self.need_projection:
+            self.linear_proj = nn.Linear(self.audio_dim, self.out_dim)
+        self._scb_arena_fn = None
+
+    def _create_cls(self):
+        return torch.nn.Parameter(torch.randn([1, 1, self.config.model_settings.parallel_branch.transformer_args.d_model]))
+
+    def _head(self) -> Tuple[ParallelHead, dict]:
+        p = self.self_att.head_params()
+        p["cls"] = self.cls
+        if self.need_projection:
+            p["linear_proj.weight"], p["linear_proj.bias"] = self.linear_proj.weight, self.linear_proj.bias
+        else:
+            raise NotImplementedError("need_projection: false is not used by any shipped config")
+        return ParallelHead(self.self_att.d_model, self.self_att.nhead, self.self_att.layer_norm_eps, True), p
+
+    def _kv_len(self, audio_len: torch.Tensor, total_len: int, dev) -> torch.Tensor:
+        # key-padding mask of get_keypadding_mask(max_length=T+1, data_lens=audio_len+1) as valid-key counts
+        kv_len = torch.empty(audio_len.shape[0], device=dev, dtype=torch.int32)
+        ops.lengths_to_i32(audio_len.to(device=dev, dtype=torch.int64).contiguous(), 1, total_len, kv_len)
+        return kv_len
+
+    @torch.no_grad()
+    def extract_hidden_states(self, audio_feat: torch.Tensor, audio_len: torch.Tensor) -> Tuple:
+        from speechclip_b200.functional import workspace
+        head, p = self._head()
+        kv_len = self._kv_len(audio_len, audio_feat.size(1) + 1, audio_feat.device)
+        _, hidden = head.full_forward(workspace(audio_feat.device), p, audio_feat.float().contiguous(), kv_len)
+        return tuple(x[:, 1:, ...] for x in hidden)
+
+    def forward(self, audio_feat: torch.Tensor, audio_len: torch.Tensor) -> torch.Tensor:
+        head, p = self._head()
+        kv_len = self._kv_len(audio_len, audio_feat.size(1) + 1, audio_feat.device)
+        arena = self._scb_arena_fn() if self._scb_arena_fn is not None else None
+        return ParallelBranchFn.apply(audio_feat, kv_len, head, arena, *[p[k] for k in PARAM_ORDER])
+
+
+class KWClip_GeneralTransformer(KWClipBase):
+    """Main class for SpeechCLIP (kwClip.py:1111-1496)."""
+
+    def __init__(self, config: OrderedNamespace) -> None:
+        super().__init__(config)
+        self.cascaded_branch = None
+        self.parallel_branch = None
+        if self.config.model_settings.cascaded_objective_weight > 0:
+            raise NotImplementedError("cascaded branch (keyword VQ + CLIP text tower): SURVEY.md §8 row a9, not built yet")
+        if self.config.model_settings.parallel_objective_weight > 0:
+            logger.info("Create Parallel Branch")
+            self.parallel_branch = KW_ParallelBranch(config=self.config, audio_dim=self.audio_embd_dim, out_dim=self.subword_embd_dim)
+        self.img_enc_proj_net = None
+        self.p_branch_proj_net = None
+        self.c_branch_proj_net = None
+        for key in ("image_encoder_projection", "parallel_branch_projection", "cascaded_branch_projection"):
+            if self.config.model_settings.get(key, None) is not None:
+                MLPLayers()  # raises: projections are not on the shipped path
+        self._wire_arena()
+
+    def _wire_arena(self):
+        super()._wire_arena()
+        if self.parallel_branch is not None:
+            self.parallel_branch._scb_arena_fn = self.arena
+
+    def getTrainableParams(self) -> list:
+        _params = super().getTrainableParams()
+        if self.parallel_branch is not None:
+            _params += list(self.parallel_branch.parameters())
+        return _params
+
+    def feature_extractor_s3prl(self, wav) -> Tuple[torch.Tensor, Tuple]:
+        wav, wav_len = self.processWavs(wav)
+        audio_feat, audio_len, hidden_states = self.forward_audio(wav, wav_len, return_hidden_states=True)
+        assert isinstance(hidden_states, tuple)
+        if self.parallel_branch is not None:
+            parallel_hidden_states = self.parallel_branch.extract_hidden_states(audio_feat, audio_len)
+            assert isinstance(parallel_hidden_states, tuple)
+            hidden_states = hidden_states + tuple(parallel_hidden_states[1:])
+        return hidden_states[-1], hidden_states
+
+    def compute_loss(self, input_feats: dict):
+        assert isinstance(input_feats, dict)
+        assert "id" in input_feats
+        assert "cascaded_audio_feat" in input_feats or "parallel_audio_feat" in input_feats
+        assert "image_feat" in input_feats
+        parallel_audio_feat = input_feats["parallel_audio_feat"].float() if "parallel_audio_feat" in input_feats else None
+        image_feat = input_feats["image_feat"].float()
+        id = input_feats["id"]
+        losses_ = {"loss": 0}
+        w = self.config.model_settings.parallel_objective_weight
+        if w > 0:
+            losses_["p_cl_loss"] = self.criterion(feat_A=parallel_audio_feat, feat_B=image_feat, index=id)
+            # weight 1.0 (every shipped config) adds nothing to the graph; other weights scale through autograd
+            losses_["loss"] = losses_["p_cl_loss"] if w == 1.0 else w * losses_["p_cl_loss"]
+        return losses_
+
+    def encode_speech(self, wav) -> dict:
+        wav, wav_len = self.processWavs(wav)
+        audio_feat, audio_len = self.forward_audio(wav, wav_len)
+        parallel_audio_feat = None
+        if self.parallel_branch is not None:
+            parallel_audio_feat = l2_normalize(self.parallel_branch(audio_feat=audio_feat, audio_len=audio_len))
+        return {"cascaded_audio_feat": None, "parallel_audio_feat": parallel_audio_feat, "vq_results": None, "keywords": None}
+
+    def forward(self, batch) -> tuple:
+        wav, wav_len, image, id = batch["wav"], batch["wav_len"], batch["image"], batch["id"]
+        self.clip.update_device(self.device)
+        audio_feat, audio_len = self.forward_audio(wav, wav_len)
+        image_feat = l2_normalize(self.forward_image(image))
+        losses_ = {"id": id, "image_feat": image_feat}
+        log_metrics = {}
+        parallel_audio_feat = None
+        if self.parallel_branch is not None:
+            parallel_audio_feat = l2_normalize(self.parallel_branch(audio_feat=audio_feat, audio_len=audio_len))
+            losses_["parallel_audio_feat"] = parallel_audio_feat
+        log_metrics.update({"cl_temp": self.criterion.current_temperature})
+        return (losses_, log_metrics,
+                {"cascaded_audio_feat": None, "parallel_audio_feat": parallel_audio_feat, "image_feat": image_feat, "id": id,
+                 "vq_results": None, "keywords": None})

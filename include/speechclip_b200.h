@@ -71,13 +71,158 @@ typedef struct scb_gemm_args {
   int32_t out2_dtype;
   int32_t ab_format;    /* SCB_F16 | SCB_BF16: format of A and B */
   const float* bias;    /* optional, fp32, indexed by output column */
-  const void* residual; /* optional, same layout as out */
+  const void* residual; /* optional; indexed like out unless residual_ld != 0 */
   int32_t residual_dtype;
   int32_t act;
   float alpha;
+  int64_t residual_ld;           /* 0: residual shares out's ldc / batch stride (then the two below are ignored) */
+  int64_t residual_batch_stride; /* may be 0 with residual_ld != 0: one [m_per_batch][n] table broadcast over the batch */
 } scb_gemm_args;
 
 int scb_gemm(const scb_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * fp32 SIMT contraction for the few hundred rows of the trainable head (CLS row of the parallel branch and
+ * its gradients): C[m,n] = alpha * sum_k A(m,k) B(n,k) + beta * C[m,n] with A(m,k) = a[m*a_rs + k*a_cs],
+ * B(n,k) = b[n*b_rs + k*b_cs] (arbitrary strides: no transposed copies for dgrad / wgrad).
+ * Replaces nn.TransformerEncoderLayer's out_proj / linear1 / linear2 on row 0 (TransformerModels.py:64-81),
+ * linear_proj (kwClip.py:1105-1106) and their autograd backward.
+ * ---------------------------------------------------------------------------------------------- */
+int scb_sgemm(const float* a, int64_t a_rs, int64_t a_cs, const float* b, int64_t b_rs, int64_t b_cs, float* c, int64_t ldc,
+              int32_t M, int32_t N, int32_t K, float alpha, float beta, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-head attention forward, softmax(scale * Q K^T + mask) V, fp32 softmax, 16-bit operands.
+ * q/k/v/o: [batch][T][heads*head_dim] views with row stride *_ld and batch stride *_bs (elements); head h lives at
+ * columns h*head_dim.  kv_len (nullable, int32 [batch]) = number of valid keys per batch entry (key-padding mask:
+ * fairseq self_attn_padding_mask, speech_encoder_plus.py:49-53; get_keypadding_mask, data_utils.py:4-20);
+ * causal != 0 adds CLIP's text mask (clip_official.py:257).  head_dim in {16,32,64,96,128}.
+ * ---------------------------------------------------------------------------------------------- */
+int scb_attention_fwd(const void* q, const void* k, const void* v, void* o, int32_t fmt, int64_t q_ld, int64_t k_ld, int64_t v_ld,
+                      int64_t o_ld, int64_t q_bs, int64_t k_bs, int64_t v_bs, int64_t o_bs, const int32_t* kv_len, int32_t batch,
+                      int32_t heads, int32_t head_dim, int32_t Tq, int32_t Tk, float scale, int32_t causal, void* stream);
+
+/* Single-query attention of the parallel branch: only output row 0 ([CLS]) of the branch is consumed
+ * (kwClip.py:1103) and its query is the same learned vector for every utterance, so per (utterance, head) ONE
+ * query attends over all keys.  q fp32 [heads*head_dim] (unscaled; scale applied inside); kv 16-bit [batch][Tk][kv_ld]
+ * with K at column k_off + h*head_dim and V at v_off + h*head_dim.  probs fp32 [batch][heads][Tk] is saved for backward.
+ * bwd writes dkv (16-bit, same layout as kv; rows >= kv_len zero) and ACCUMULATES dq (fp32 [heads*head_dim]). */
+int scb_cls_attention_fwd(const float* q, const void* kv, int32_t kv_fmt, int64_t kv_ld, int64_t kv_bs, int32_t k_off, int32_t v_off,
+                          const int32_t* kv_len, int32_t batch, int32_t heads, int32_t head_dim, int32_t Tk, float scale, float* probs,
+                          float* ctx32, void* ctx16, int32_t ctx16_fmt, void* stream);
+int scb_cls_attention_bwd(const float* q, const void* kv, int32_t kv_fmt, int64_t kv_ld, int64_t kv_bs, int32_t k_off, int32_t v_off,
+                          const int32_t* kv_len, int32_t batch, int32_t heads, int32_t head_dim, int32_t Tk, float scale,
+                          const float* probs, const float* dctx, void* dkv, int32_t dkv_fmt, float* dq, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Waveform front end.
+ * scb_frame_lengths: per-utterance integer bookkeeping done on the device (the reference does it with B host syncs
+ *   and python loops: speech_encoder_plus.py:539-552,602-611; fairseq forward_padding_mask):
+ *     crop_len = min(wav_len, max_audio_len) (max_audio_len <= 0: no crop), crop_off = floor(u * (wav_len - crop_len + 1))
+ *     (u in [0,1): the random-crop draw of audio_transforms.py:5-23; u == NULL -> offset 0),
+ *     valid_frames = min(T, ceil(crop_len / (tw_out / T)))   -- a frame is padding iff ALL its samples are padding,
+ *     feat_len = min(T, round_half_even(crop_len / rate)).
+ * scb_wav_prepare: out[b, i] = i < crop_len[b] ? wav[b, crop_off[b] + i] : 0 for i < tw_out; normalize != 0 applies the
+ *   per-utterance F.layer_norm(wav, wav.shape) of preprocess_input (speech_encoder_plus.py:507-508; eps 1e-5) first
+ *   (stats_scratch: 2*batch floats, only read when normalize != 0).
+ * scb_conv0_groupnorm_gelu: fairseq ConvFeatureExtractionModel layer 0 of HuBERT-base: Conv1d(1,512,k=10,s=5) ->
+ *   GroupNorm(512 groups = per channel over time, eps) -> GELU(erf); out is channel-last 16-bit [batch][n_frames][512].
+ *   scratch >= scb_conv0_scratch_bytes(batch).
+ * scb_conv0_layernorm_gelu: HuBERT-large variant (extractor_mode=layer_norm): conv -> LayerNorm over the 512 channels
+ *   of each frame -> GELU.
+ * ---------------------------------------------------------------------------------------------- */
+int scb_frame_lengths(const int64_t* wav_len, int32_t batch, int64_t tw_out, int32_t max_audio_len, int32_t n_frames, int32_t rate,
+                      const float* u, int32_t* crop_off, int32_t* crop_len, int32_t* valid_frames, int32_t* feat_len,
+                      int64_t* feat_len64, void* stream);
+/* out[i] = clamp(in[i] + add, 0, clamp_max): key-padding lengths of the branch (audio_len + 1 for the [CLS] slot,
+ * kwClip.py:1096-1099; get_keypadding_mask, data_utils.py:4-20) as the int32 valid-key counts the attention kernels take. */
+int scb_lengths_to_i32(const int64_t* in, int32_t n, int32_t add, int32_t clamp_max, int32_t* out, void* stream);
+int scb_wav_prepare(const float* wav, int64_t wav_ld, int32_t batch, const int32_t* crop_off, const int32_t* crop_len, int64_t tw_out,
+                    int32_t normalize, float* stats_scratch, float* out, int64_t out_ld, void* stream);
+int64_t scb_conv0_scratch_bytes(int32_t batch);
+int scb_conv0_groupnorm_gelu(const float* wav, int64_t wav_ld, int32_t batch, int32_t n_samples, const float* w, const float* conv_bias,
+                             const float* gamma, const float* beta, float eps, void* out, int32_t out_fmt, int64_t out_batch_stride,
+                             void* scratch, int64_t scratch_bytes, void* stream);
+int scb_conv0_layernorm_gelu(const float* wav, int64_t wav_ld, int32_t batch, int32_t n_samples, const float* w, const float* conv_bias,
+                             const float* gamma, const float* beta, float eps, void* out, int32_t out_fmt, int64_t out_batch_stride,
+                             void* stream);
+/* Zero padded frames of x in place (speech_encoder_plus.py:32-33) and write the 16-bit, group-padded (channels per group ->
+ * 64), time-padded copy that the positional-conv GEMM walks tap by tap (speech_encoder_plus.py:35). */
+int scb_posconv_pack(float* x, const int32_t* valid_frames, void* xpad, int32_t fmt, int32_t batch, int32_t T, int32_t D, int32_t groups,
+                     int32_t pad_left, int32_t rows_pad, void* stream);
+/* CLIP visual.conv1 input (kernel = stride = P, clip_official.py:209): patches[b*G*G + gy*G + gx][c*P*P + py*P + px]. */
+int scb_patchify(const float* img, void* out, int32_t fmt, int32_t batch, int32_t C, int32_t H, int32_t W, int32_t P, int32_t ldk,
+                 void* stream);
+/* out[b, :] = a[:] + a2[:] for b < nb (class_embedding + positional_embedding[0]; [CLS] prepend of kwClip.py:1093-1094). */
+int scb_broadcast_row(const float* a, const float* a2, void* out, int32_t out_dtype, int64_t out_stride, int32_t nb, int32_t d,
+                      void* stream);
+int scb_cast_rows(const void* in, int32_t in_dtype, int64_t in_ld, void* out, int32_t out_dtype, int64_t out_ld, int64_t rows, int32_t cols,
+                  void* stream);
+int scb_transpose(const void* in, int32_t in_dtype, int64_t in_ld, void* out, int32_t out_dtype, int64_t out_ld, int32_t rows,
+                  int32_t cols, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Row kernels (HBM bound).
+ * scb_layernorm_fwd: torch / fairseq / CLIP LayerNorm over the last dim (fp32 statistics), optional fused activation
+ *   on the result (HuBERT-large conv blocks: LN -> GELU); optional fp32 and 16-bit outputs; stats = [rows][2] (mean, rstd).
+ * scb_layernorm_bwd: dx, and dgamma/dbeta ACCUMULATED (+=).
+ * scb_l2norm_*: x / ||x|| (kwClip.py:1436,1451-1453).
+ * scb_weighted_sum_*: softmax(w)-weighted sum of the L hidden states (weighted_sum.py:26-45; normalize != 0 applies the
+ *   parameter-free LayerNorm of :41-42 first).  h = [L] slabs of [rows][d] fp32 at layer_stride.  The 16-bit output can be
+ *   scattered into the branch source buffer: row r of utterance b goes to out16 + b*out16_batch_stride + (out16_row0 + r)*d.
+ *   bwd reads dout the same way and ACCUMULATES grad_scale * dL/dw into grad_logits.
+ * scb_rows_bias_act: y = act(x + bias + res) on [rows][d] fp32 (res row stride res_ld; 0 = one row broadcast);
+ *   pre (nullable) receives x + bias + res before the activation (saved for backward).
+ * scb_gelu_bwd: dx = dy * gelu'(pre).
+ * scb_column_sum: out[c] (+)= sum_r in[r*ld + c]  (bias gradients; beta 0 or 1).
+ * ---------------------------------------------------------------------------------------------- */
+int scb_layernorm_fwd(const void* x, int32_t x_dtype, const float* gamma, const float* beta, float* y32, void* y16, int32_t y16_fmt,
+                      float* stats, int64_t rows, int32_t d, int64_t x_ld, int64_t y_ld, float eps, int32_t act, void* stream);
+int scb_layernorm_bwd(const float* dy, const float* x, const float* stats, const float* gamma, float* dx, float* dgamma, float* dbeta,
+                      int64_t rows, int32_t d, void* stream);
+int scb_l2norm_fwd(const float* x, float* y, float* norms, int32_t rows, int32_t d, void* stream);
+int scb_l2norm_bwd(const float* dy, const float* y, const float* norms, float* dx, int32_t rows, int32_t d, void* stream);
+int scb_weighted_sum_fwd(const float* h, int64_t layer_stride, const float* w_logits, int32_t L, int32_t normalize, float* out32,
+                         void* out16, int32_t out16_fmt, int64_t rows, int32_t d, int32_t rows_per_batch, int64_t out16_batch_stride,
+                         int64_t out16_row0, void* stream);
+int scb_weighted_sum_bwd(const float* h, int64_t layer_stride, const float* w_logits, int32_t L, int32_t normalize, const float* dout,
+                         int64_t rows, int32_t d, int32_t rows_per_batch, int64_t dout_batch_stride, int64_t dout_row0,
+                         float* scratch_L, float* grad_logits, float grad_scale, void* stream);
+int scb_rows_bias_act(const float* x, int64_t x_ld, const float* bias, const float* res, int64_t res_ld, int32_t act, float* pre, float* y,
+                      int64_t y_ld, int64_t rows, int32_t d, void* stream);
+int scb_gelu_bwd(const float* dy, const float* pre, float* dx, int64_t n, void* stream);
+int scb_column_sum(const void* in, int32_t in_dtype, int64_t ld, int64_t rows, int32_t cols, float* out, float beta, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Masked symmetric InfoNCE, forward + backward (avssl/module/losses.py:185-245; kwClip.py:1248-1297).
+ *   logits = A B^T * mult (mult = exp(*log_mult) if log_mult else fixed_mult), diagonal -= margin;
+ *   neg_ij = (id_i != id_j) | (i == j & !dcl)    (ids NULL: i != j, plus the diagonal unless dcl);
+ *   loss = [a2b] mean_i(-l_ii + log sum_j e^{l_ij} neg_ij) + [b2a] (columns) ; halved when both.
+ * No max-subtraction, exactly like the reference.  B is not capped at MAX_EYE=256 (losses.py:126).
+ * phase 1 = forward (logits, row/column sums and loss; the logits stay in scratch), 2 = backward from the scratch a phase-1
+ * call left (consumes it), 3 = both.  Gradients (each nullable): dA = s * dloss/dA, dB, and dlog_mult (ACCUMULATED), with
+ * s = upstream * (upstream_dev ? *upstream_dev : 1) — upstream_dev is autograd's incoming dloss on the device (no host sync).
+ * logits_out nullable [B][B].
+ * ---------------------------------------------------------------------------------------------- */
+int64_t scb_infonce_scratch_bytes(int32_t B);
+int scb_infonce(const float* feat_a, const float* feat_b, const int64_t* ids, int32_t B, int32_t D, const float* log_mult, float fixed_mult,
+                float margin, int32_t dcl, int32_t a2b, int32_t b2a, int32_t phase, float* loss, float* logits_out, float upstream,
+                const float* upstream_dev, float* dA, float* dB, float* dlog_mult, void* scratch, int64_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer step over ONE flat fp32 buffer: Lightning's gradient_clip_val global-norm clip (spchclp_p.yaml:108) fused with
+ * torch.optim.Adam (kwClip.py:666-694: L2 weight decay folded into the gradient, bias-corrected moments), refreshing the
+ * optional 16-bit weight copies.  step counts from 1; max_norm <= 0 disables clipping; sumsq_scratch = 1 double.
+ * ---------------------------------------------------------------------------------------------- */
+int scb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double* sumsq_scratch, float grad_scale, float max_norm, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int32_t step, void* p_f16, void* p_bf16, void* stream);
+
+/* Retrieval (avssl/module/retrieval.py:45-121 without the argsort + python row loops): for query row i,
+ * best = max_j { score[i][j] : cand_ids[j] == answers[i] }, rank[i] = #{ j : score[i][j] > best } (so the answer is inside
+ * the top k of a descending sort iff rank[i] < k; rank = cols when no candidate matches), top1[i] = argmax_j score[i][j]
+ * (lowest index on ties).  score fp32 [rows][ld]. */
+int scb_retrieval_rank(const float* score, int64_t ld, int32_t rows, int32_t cols, const int64_t* cand_ids, const int64_t* answers,
+                       int32_t* rank, int32_t* top1, void* stream);
 
 #ifdef __cplusplus
 }

@@ -74,6 +74,9 @@ int make_tmap_16b(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 
 extern "C" {
 
+#define ST static_cast<cudaStream_t>(stream)
+typedef long long ll;
+
 int scb_abi_version(void) { return SCB_ABI_VERSION; }
 const char* scb_last_error(void) { return scb::g_err; }
 int64_t scb_launch_count(void) { return scb::g_launches.load(); }
@@ -83,7 +86,131 @@ int scb_gemm(const scb_gemm_args* args, void* stream) {
     scb::set_error("scb_gemm: args is NULL");
     return SCB_EINVAL;
   }
-  return scb::gemm(*args, static_cast<cudaStream_t>(stream));
+  return scb::gemm(*args, ST);
+}
+
+int scb_sgemm(const float* a, int64_t a_rs, int64_t a_cs, const float* b, int64_t b_rs, int64_t b_cs, float* c, int64_t ldc, int32_t M,
+              int32_t N, int32_t K, float alpha, float beta, void* stream) {
+  return scb::sgemm(a, a_rs, a_cs, b, b_rs, b_cs, c, ldc, M, N, K, alpha, beta, ST);
+}
+
+int scb_attention_fwd(const void* q, const void* k, const void* v, void* o, int32_t fmt, int64_t q_ld, int64_t k_ld, int64_t v_ld,
+                      int64_t o_ld, int64_t q_bs, int64_t k_bs, int64_t v_bs, int64_t o_bs, const int32_t* kv_len, int32_t batch,
+                      int32_t heads, int32_t head_dim, int32_t Tq, int32_t Tk, float scale, int32_t causal, void* stream) {
+  return scb::attention_fwd(q, k, v, o, fmt, q_ld, k_ld, v_ld, o_ld, q_bs, k_bs, v_bs, o_bs, kv_len, batch, heads, head_dim, Tq, Tk, scale,
+                            causal, ST);
+}
+int scb_cls_attention_fwd(const float* q, const void* kv, int32_t kv_fmt, int64_t kv_ld, int64_t kv_bs, int32_t k_off, int32_t v_off,
+                          const int32_t* kv_len, int32_t batch, int32_t heads, int32_t head_dim, int32_t Tk, float scale, float* probs,
+                          float* ctx32, void* ctx16, int32_t ctx16_fmt, void* stream) {
+  return scb::cls_attention_fwd(q, kv, kv_fmt, kv_ld, kv_bs, k_off, v_off, kv_len, batch, heads, head_dim, Tk, scale, probs, ctx32, ctx16,
+                                ctx16_fmt, ST);
+}
+int scb_cls_attention_bwd(const float* q, const void* kv, int32_t kv_fmt, int64_t kv_ld, int64_t kv_bs, int32_t k_off, int32_t v_off,
+                          const int32_t* kv_len, int32_t batch, int32_t heads, int32_t head_dim, int32_t Tk, float scale,
+                          const float* probs, const float* dctx, void* dkv, int32_t dkv_fmt, float* dq, void* stream) {
+  return scb::cls_attention_bwd(q, kv, kv_fmt, kv_ld, kv_bs, k_off, v_off, kv_len, batch, heads, head_dim, Tk, scale, probs, dctx, dkv,
+                                dkv_fmt, dq, ST);
+}
+
+int scb_frame_lengths(const int64_t* wav_len, int32_t batch, int64_t tw_out, int32_t max_audio_len, int32_t n_frames, int32_t rate,
+                      const float* u, int32_t* crop_off, int32_t* crop_len, int32_t* valid_frames, int32_t* feat_len,
+                      int64_t* feat_len64, void* stream) {
+  return scb::frame_lengths(reinterpret_cast<const ll*>(wav_len), batch, tw_out, max_audio_len, n_frames, rate, u, crop_off, crop_len,
+                            valid_frames, feat_len, reinterpret_cast<ll*>(feat_len64), ST);
+}
+int scb_lengths_to_i32(const int64_t* in, int32_t n, int32_t add, int32_t clamp_max, int32_t* out, void* stream) {
+  return scb::lengths_to_i32(reinterpret_cast<const ll*>(in), n, add, clamp_max, out, ST);
+}
+int scb_wav_prepare(const float* wav, int64_t wav_ld, int32_t batch, const int32_t* crop_off, const int32_t* crop_len, int64_t tw_out,
+                    int32_t normalize, float* stats_scratch, float* out, int64_t out_ld, void* stream) {
+  return scb::wav_prepare(wav, wav_ld, batch, crop_off, crop_len, tw_out, normalize, stats_scratch, out, out_ld, ST);
+}
+int64_t scb_conv0_scratch_bytes(int32_t batch) { return scb::conv0_scratch_bytes(batch); }
+int scb_conv0_groupnorm_gelu(const float* wav, int64_t wav_ld, int32_t batch, int32_t n_samples, const float* w, const float* conv_bias,
+                             const float* gamma, const float* beta, float eps, void* out, int32_t out_fmt, int64_t out_batch_stride,
+                             void* scratch, int64_t scratch_bytes, void* stream) {
+  return scb::conv0_groupnorm_gelu(wav, wav_ld, batch, n_samples, w, conv_bias, gamma, beta, eps, out, out_fmt, out_batch_stride, scratch,
+                                   scratch_bytes, ST);
+}
+int scb_conv0_layernorm_gelu(const float* wav, int64_t wav_ld, int32_t batch, int32_t n_samples, const float* w, const float* conv_bias,
+                             const float* gamma, const float* beta, float eps, void* out, int32_t out_fmt, int64_t out_batch_stride,
+                             void* stream) {
+  return scb::conv0_layernorm_gelu(wav, wav_ld, batch, n_samples, w, conv_bias, gamma, beta, eps, out, out_fmt, out_batch_stride, ST);
+}
+int scb_posconv_pack(float* x, const int32_t* valid_frames, void* xpad, int32_t fmt, int32_t batch, int32_t T, int32_t D, int32_t groups,
+                     int32_t pad_left, int32_t rows_pad, void* stream) {
+  return scb::posconv_pack(x, valid_frames, xpad, fmt, batch, T, D, groups, pad_left, rows_pad, ST);
+}
+int scb_patchify(const float* img, void* out, int32_t fmt, int32_t batch, int32_t C, int32_t H, int32_t W, int32_t P, int32_t ldk,
+                 void* stream) {
+  return scb::patchify(img, out, fmt, batch, C, H, W, P, ldk, ST);
+}
+int scb_broadcast_row(const float* a, const float* a2, void* out, int32_t out_dtype, int64_t out_stride, int32_t nb, int32_t d,
+                      void* stream) {
+  return scb::broadcast_row(a, a2, out, out_dtype, out_stride, nb, d, ST);
+}
+int scb_cast_rows(const void* in, int32_t in_dtype, int64_t in_ld, void* out, int32_t out_dtype, int64_t out_ld, int64_t rows, int32_t cols,
+                  void* stream) {
+  return scb::cast_rows(in, in_dtype, in_ld, out, out_dtype, out_ld, rows, cols, ST);
+}
+int scb_transpose(const void* in, int32_t in_dtype, int64_t in_ld, void* out, int32_t out_dtype, int64_t out_ld, int32_t rows,
+                  int32_t cols, void* stream) {
+  return scb::transpose(in, in_dtype, in_ld, out, out_dtype, out_ld, rows, cols, ST);
+}
+
+int scb_layernorm_fwd(const void* x, int32_t x_dtype, const float* gamma, const float* beta, float* y32, void* y16, int32_t y16_fmt,
+                      float* stats, int64_t rows, int32_t d, int64_t x_ld, int64_t y_ld, float eps, int32_t act, void* stream) {
+  return scb::layernorm_fwd(x, x_dtype, gamma, beta, y32, y16, y16_fmt, stats, rows, d, x_ld, y_ld, eps, act, ST);
+}
+int scb_layernorm_bwd(const float* dy, const float* x, const float* stats, const float* gamma, float* dx, float* dgamma, float* dbeta,
+                      int64_t rows, int32_t d, void* stream) {
+  return scb::layernorm_bwd(dy, x, stats, gamma, dx, dgamma, dbeta, rows, d, ST);
+}
+int scb_l2norm_fwd(const float* x, float* y, float* norms, int32_t rows, int32_t d, void* stream) {
+  return scb::l2norm_fwd(x, y, norms, rows, d, ST);
+}
+int scb_l2norm_bwd(const float* dy, const float* y, const float* norms, float* dx, int32_t rows, int32_t d, void* stream) {
+  return scb::l2norm_bwd(dy, y, norms, dx, rows, d, ST);
+}
+int scb_weighted_sum_fwd(const float* h, int64_t layer_stride, const float* w_logits, int32_t L, int32_t normalize, float* out32,
+                         void* out16, int32_t out16_fmt, int64_t rows, int32_t d, int32_t rows_per_batch, int64_t out16_batch_stride,
+                         int64_t out16_row0, void* stream) {
+  return scb::weighted_sum_fwd(h, layer_stride, w_logits, L, normalize, out32, out16, out16_fmt, rows, d, rows_per_batch,
+                               out16_batch_stride, out16_row0, ST);
+}
+int scb_weighted_sum_bwd(const float* h, int64_t layer_stride, const float* w_logits, int32_t L, int32_t normalize, const float* dout,
+                         int64_t rows, int32_t d, int32_t rows_per_batch, int64_t dout_batch_stride, int64_t dout_row0,
+                         float* scratch_L, float* grad_logits, float grad_scale, void* stream) {
+  return scb::weighted_sum_bwd(h, layer_stride, w_logits, L, normalize, dout, rows, d, rows_per_batch, dout_batch_stride, dout_row0,
+                               scratch_L, grad_logits, grad_scale, ST);
+}
+int scb_rows_bias_act(const float* x, int64_t x_ld, const float* bias, const float* res, int64_t res_ld, int32_t act, float* pre, float* y,
+                      int64_t y_ld, int64_t rows, int32_t d, void* stream) {
+  return scb::rows_bias_act(x, x_ld, bias, res, res_ld, act, pre, y, y_ld, rows, d, ST);
+}
+int scb_gelu_bwd(const float* dy, const float* pre, float* dx, int64_t n, void* stream) { return scb::gelu_bwd(dy, pre, dx, n, ST); }
+int scb_column_sum(const void* in, int32_t in_dtype, int64_t ld, int64_t rows, int32_t cols, float* out, float beta, void* stream) {
+  return scb::column_sum(in, in_dtype, ld, rows, cols, out, beta, ST);
+}
+
+int64_t scb_infonce_scratch_bytes(int32_t B) { return scb::infonce_scratch_bytes(B); }
+int scb_infonce(const float* feat_a, const float* feat_b, const int64_t* ids, int32_t B, int32_t D, const float* log_mult, float fixed_mult,
+                float margin, int32_t dcl, int32_t a2b, int32_t b2a, int32_t phase, float* loss, float* logits_out, float upstream,
+                const float* upstream_dev, float* dA, float* dB, float* dlog_mult, void* scratch, int64_t scratch_bytes, void* stream) {
+  return scb::infonce(feat_a, feat_b, reinterpret_cast<const ll*>(ids), B, D, log_mult, fixed_mult, margin, dcl, a2b, b2a, phase, loss,
+                      logits_out, upstream, upstream_dev, dA, dB, dlog_mult, scratch, scratch_bytes, ST);
+}
+
+int scb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double* sumsq_scratch, float grad_scale, float max_norm, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int32_t step, void* p_f16, void* p_bf16, void* stream) {
+  return scb::adam_step(p, g, m, v, n, sumsq_scratch, grad_scale, max_norm, lr, beta1, beta2, eps, weight_decay, step, p_f16, p_bf16, ST);
+}
+
+int scb_retrieval_rank(const float* score, int64_t ld, int32_t rows, int32_t cols, const int64_t* cand_ids, const int64_t* answers,
+                       int32_t* rank, int32_t* top1, void* stream) {
+  return scb::retrieval_rank(score, ld, rows, cols, reinterpret_cast<const ll*>(cand_ids), reinterpret_cast<const ll*>(answers), rank, top1,
+                             ST);
 }
 
 }  // extern "C"

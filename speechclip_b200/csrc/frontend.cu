@@ -1,0 +1,404 @@
+// Front-end kernels (HBM / CUDA-core bound):
+//   * HuBERT conv0 (C_in = 1, k = 10, s = 5) + GroupNorm-over-time + GELU   [fairseq ConvFeatureExtractionModel layer 0]
+//       - statistics from the 10x10 windowed autocorrelation of the waveform (no second pass over 512 channels)
+//       - apply pass recomputes the conv and writes channel-last f16 activations for the conv1 GEMM
+//   * pos-conv input packing (zero padded frames, regroup 16 x 48 -> 16 x 64 channels, zero time padding)
+//   * CLIP patchify (im2col for kernel = stride = P) and row broadcast helpers
+#include "common.cuh"
+#include "ops.cuh"
+
+namespace scb {
+namespace {
+
+constexpr int kTaps = 10;
+constexpr int kStride = 5;
+constexpr int kPairs = kTaps * (kTaps + 1) / 2;  // 55 upper-triangular autocorrelation entries
+constexpr int kStatVals = kPairs + kTaps;        // + 10 plain sums
+
+// acc[b][0..54] = sum_t x[5t+k] x[5t+k'] (k<=k'), acc[b][55..64] = sum_t x[5t+k]   over all n_frames of utterance b.
+__global__ void __launch_bounds__(256) conv0_autocorr_kernel(const float* __restrict__ wav, long long wav_ld, int n_frames,
+                                                             double* __restrict__ acc) {
+  const int b = blockIdx.y;
+  const float* x = wav + (long long)b * wav_ld;
+  float part[kStatVals];
+#pragma unroll
+  for (int i = 0; i < kStatVals; ++i) part[i] = 0.f;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_frames; t += gridDim.x * blockDim.x) {
+    float v[kTaps];
+#pragma unroll
+    for (int k = 0; k < kTaps; ++k) v[k] = __ldg(x + (long long)t * kStride + k);
+    int idx = 0;
+#pragma unroll
+    for (int k = 0; k < kTaps; ++k)
+#pragma unroll
+      for (int k2 = k; k2 < kTaps; ++k2) part[idx++] += v[k] * v[k2];
+#pragma unroll
+    for (int k = 0; k < kTaps; ++k) part[kPairs + k] += v[k];
+  }
+  __shared__ double red[8][kStatVals];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < kStatVals; ++i) {
+    const double s = warp_sum_d((double)part[i]);
+    if (lane == 0) red[warp][i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < kStatVals) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w][threadIdx.x];
+    atomicAdd(&acc[(long long)b * kStatVals + threadIdx.x], s);
+  }
+}
+
+// Per (utterance, channel): mean / biased variance of the conv output from the autocorrelation, folded with the
+// GroupNorm affine into y = conv * scale + shift.
+__global__ void conv0_finalize_kernel(const double* __restrict__ acc, const float* __restrict__ w, const float* __restrict__ conv_bias,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta, int n_frames, int channels,
+                                      float eps, float2* __restrict__ scale_shift) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= channels) return;
+  const double* a = acc + (long long)b * kStatVals;
+  double wk[kTaps];
+#pragma unroll
+  for (int k = 0; k < kTaps; ++k) wk[k] = (double)w[c * kTaps + k];
+  double s1 = 0.0, s2 = 0.0;
+  int idx = 0;
+#pragma unroll
+  for (int k = 0; k < kTaps; ++k) {
+    s1 += wk[k] * a[kPairs + k];
+#pragma unroll
+    for (int k2 = k; k2 < kTaps; ++k2) {
+      const double r = a[idx++];
+      s2 += (k == k2 ? 1.0 : 2.0) * wk[k] * wk[k2] * r;
+    }
+  }
+  const double mean_nb = s1 / n_frames;
+  double var = s2 / n_frames - mean_nb * mean_nb;
+  if (var < 0.0) var = 0.0;
+  const double cb = conv_bias ? (double)conv_bias[c] : 0.0;
+  const double mean = mean_nb + cb;
+  const double rstd = 1.0 / sqrt(var + (double)eps);
+  const double g = gamma ? (double)gamma[c] : 1.0, be = beta ? (double)beta[c] : 0.0;
+  // y = ((conv_nb + cb) - mean) * rstd * g + be  with conv_nb the bias-free conv
+  scale_shift[(long long)b * channels + c] = make_float2((float)(rstd * g), (float)(be - mean_nb * rstd * g));
+}
+
+// out[b, t, c] = gelu(conv0(wav)[b, c, t] * scale[b,c] + shift[b,c])   channel-last, 16-bit.
+// Block = 64 frames x 512 channels; thread owns channel pair (2*tid, 2*tid+1).
+constexpr int kFramesPerBlock = 64;
+__global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restrict__ wav, long long wav_ld, const float* __restrict__ w,
+                                                          const float2* __restrict__ scale_shift, void* __restrict__ out, int out_fmt,
+                                                          int n_frames, long long out_batch_stride, int channels) {
+  __shared__ float xs[kFramesPerBlock * kStride + kTaps];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * kFramesPerBlock;
+  const int nt = min(kFramesPerBlock, n_frames - t0);
+  const int nsamp = (nt - 1) * kStride + kTaps;
+  const float* x = wav + (long long)b * wav_ld + (long long)t0 * kStride;
+  for (int i = threadIdx.x; i < nsamp; i += blockDim.x) xs[i] = __ldg(x + i);
+  __syncthreads();
+  for (int cp = threadIdx.x; cp * 2 < channels; cp += blockDim.x) {
+    const int c = cp * 2;
+    float w0[kTaps], w1[kTaps];
+#pragma unroll
+    for (int k = 0; k < kTaps; ++k) {
+      w0[k] = __ldg(w + c * kTaps + k);
+      w1[k] = __ldg(w + (c + 1) * kTaps + k);
+    }
+    const float2 ss0 = scale_shift[(long long)b * channels + c], ss1 = scale_shift[(long long)b * channels + c + 1];
+    uint32_t* o = reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(out) + (long long)b * out_batch_stride + (long long)t0 * channels + c);
+    for (int t = 0; t < nt; ++t) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < kTaps; ++k) {
+        const float xv = xs[t * kStride + k];
+        a0 = fmaf(w0[k], xv, a0);
+        a1 = fmaf(w1[k], xv, a1);
+      }
+      a0 = gelu_erf(fmaf(a0, ss0.x, ss0.y));
+      a1 = gelu_erf(fmaf(a1, ss1.x, ss1.y));
+      o[(long long)t * (channels / 2)] = pack16(out_fmt, a0, a1);
+    }
+  }
+}
+
+
+// HuBERT-large conv0 block: conv (C_in = 1) -> LayerNorm over the 512 channels of each frame (affine, fp32) -> GELU.
+// One warp per frame; lane owns channels {lane*4 + 128*i .. +3}, i < 4 (coalesced 8-byte 16-bit stores).
+__global__ void __launch_bounds__(256) conv0_ln_kernel(const float* __restrict__ wav, long long wav_ld, const float* __restrict__ w,
+                                                       const float* __restrict__ conv_bias, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float eps, void* __restrict__ out, int out_fmt,
+                                                       int n_frames, long long out_batch_stride) {
+  constexpr int C = 512;
+  __shared__ float ws[C * kTaps];
+  for (int i = threadIdx.x; i < C * kTaps; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warps = blockDim.x >> 5;
+  for (int t = blockIdx.x * warps + warp; t < n_frames; t += gridDim.x * warps) {
+    const float* x = wav + (long long)b * wav_ld + (long long)t * kStride;
+    float xv[kTaps];
+#pragma unroll
+    for (int k = 0; k < kTaps; ++k) xv[k] = __ldg(x + k);
+    float v[16];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = lane * 4 + 128 * i + j;
+        float a = conv_bias ? conv_bias[c] : 0.f;
+#pragma unroll
+        for (int k = 0; k < kTaps; ++k) a = fmaf(ws[c * kTaps + k], xv[k], a);
+        v[i * 4 + j] = a;
+        s += a;
+      }
+    const float mean = warp_sum(s) / C;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float d = v[i] - mean;
+      ss += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / C + eps);
+    uint16_t* o = reinterpret_cast<uint16_t*>(out) + (long long)b * out_batch_stride + (long long)t * C;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float y[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = lane * 4 + 128 * i + j;
+        y[j] = gelu_erf((v[i * 4 + j] - mean) * rstd * (gamma ? gamma[c] : 1.f) + (beta ? beta[c] : 0.f));
+      }
+      uint2 u;
+      u.x = pack16(out_fmt, y[0], y[1]);
+      u.y = pack16(out_fmt, y[2], y[3]);
+      *reinterpret_cast<uint2*>(o + lane * 4 + 128 * i) = u;
+    }
+  }
+}
+
+// x fp32 [B, T, D] (post_extract_proj output): zero the frames t >= valid[b] in place (speech_encoder_plus.py:32-33) and
+// write the 16-bit, group-padded, time-padded copy the positional-conv GEMM reads:
+//   xpad[b, pad_left + t, g*64 + c] = x[b, t, g*cpg + c]  (c < cpg);   everything else stays zero (buffer pre-zeroed once).
+__global__ void __launch_bounds__(256) posconv_pack_kernel(float* __restrict__ x, const int* __restrict__ valid, void* __restrict__ xpad,
+                                                           int fmt, long long rows, int T, int D, int groups, int cpg, int pad_left,
+                                                           int rows_pad) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int b = (int)(row / T), t = (int)(row % T);
+  float* xr = x + row * D;
+  const bool keep = valid == nullptr || t < valid[b];
+  uint16_t* pr = reinterpret_cast<uint16_t*>(xpad) + ((long long)b * rows_pad + pad_left + t) * (groups * 64);
+  for (int c2 = lane; c2 * 2 < D; c2 += 32) {
+    const int c = c2 * 2;
+    float2 v = *reinterpret_cast<float2*>(xr + c);
+    if (!keep) {
+      v = make_float2(0.f, 0.f);
+      *reinterpret_cast<float2*>(xr + c) = v;
+    }
+    const int g = c / cpg, ci = c % cpg;  // cpg is even, so the pair stays inside one group
+    *reinterpret_cast<uint32_t*>(pr + g * 64 + ci) = pack16(fmt, v.x, v.y);
+  }
+}
+
+// patches[b*G*G + gy*G + gx, c*P*P + py*P + px] = image[b, c, gy*P+py, gx*P+px]  (K padded with zeros to ldk)
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ img, void* __restrict__ out, int fmt, int C, int H,
+                                                       int W, int P, int G, int ldk) {
+  const long long prow = blockIdx.x;  // patch row index
+  const int b = (int)(prow / (G * G)), gi = (int)(prow % (G * G));
+  const int gy = gi / G, gx = gi % G;
+  const int K = C * P * P;
+  uint16_t* o = reinterpret_cast<uint16_t*>(out) + prow * ldk;
+  for (int i2 = threadIdx.x; i2 * 2 < ldk; i2 += blockDim.x) {
+    float v[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int idx = i2 * 2 + j;
+      if (idx < K) {
+        const int c = idx / (P * P), r = idx % (P * P), py = r / P, px = r % P;
+        v[j] = __ldg(img + (((long long)b * C + c) * H + gy * P + py) * W + gx * P + px);
+      } else {
+        v[j] = 0.f;
+      }
+    }
+    *reinterpret_cast<uint32_t*>(o + i2 * 2) = pack16(fmt, v[0], v[1]);
+  }
+}
+
+// out[b, :] = a[:] + (a2 ? a2[:] : 0)   for b in [0, nb); out row stride given; fp32 or 16-bit output.
+__global__ void broadcast_row_kernel(const float* __restrict__ a, const float* __restrict__ a2, void* __restrict__ out, int out_dtype,
+                                     long long out_stride, int d) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  const float v = a[c] + (a2 ? a2[c] : 0.f);
+  if (out_dtype == SCB_F32)
+    reinterpret_cast<float*>(out)[(long long)b * out_stride + c] = v;
+  else if (out_dtype == SCB_F16)
+    reinterpret_cast<__half*>(out)[(long long)b * out_stride + c] = __float2half_rn(v);
+  else
+    reinterpret_cast<__nv_bfloat16*>(out)[(long long)b * out_stride + c] = __float2bfloat16_rn(v);
+}
+
+// Generic strided 2-D cast/copy: out[r, c] = (T_out) in[r, c]; used for small layout fix-ups (e.g. fp32 -> 16-bit rows).
+__global__ void cast_rows_kernel(const void* __restrict__ in, int in_dtype, long long in_ld, void* __restrict__ out, int out_dtype,
+                                 long long out_ld, long long rows, int cols) {
+  const long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i % cols);
+    float v;
+    if (in_dtype == SCB_F32) v = reinterpret_cast<const float*>(in)[r * in_ld + c];
+    else if (in_dtype == SCB_F16) v = __half2float(reinterpret_cast<const __half*>(in)[r * in_ld + c]);
+    else v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(in)[r * in_ld + c]);
+    if (out_dtype == SCB_F32) reinterpret_cast<float*>(out)[r * out_ld + c] = v;
+    else if (out_dtype == SCB_F16) reinterpret_cast<__half*>(out)[r * out_ld + c] = __float2half_rn(v);
+    else reinterpret_cast<__nv_bfloat16*>(out)[r * out_ld + c] = __float2bfloat16_rn(v);
+  }
+}
+
+// out[c, r] = (T_out) in[r, c] through a padded 32x32 shared tile (coalesced both ways).
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) transpose_kernel(const TI* __restrict__ in, long long in_ld, TO* __restrict__ out, long long out_ld,
+                                                        int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[j][threadIdx.x] = (float)in[(long long)r * in_ld + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[(long long)c * out_ld + r] = (TO)tile[threadIdx.x][j];
+  }
+}
+
+}  // namespace
+
+int conv0_groupnorm_gelu(const float* wav, long long wav_ld, int batch, int n_samples, const float* w, const float* conv_bias,
+                         const float* gamma, const float* beta, float eps, void* out, int out_fmt, long long out_batch_stride,
+                         void* scratch, long long scratch_bytes, cudaStream_t st) {
+  const int channels = 512;
+  SCB_CHECK(wav && w && out && scratch, SCB_EINVAL, "scb_conv0_groupnorm_gelu: null operand");
+  SCB_CHECK(out_fmt == SCB_F16 || out_fmt == SCB_BF16, SCB_EINVAL, "scb_conv0_groupnorm_gelu: 16-bit output required");
+  SCB_CHECK(n_samples >= kTaps, SCB_EINVAL, "scb_conv0_groupnorm_gelu: utterance shorter than the conv kernel");
+  const int n_frames = (n_samples - kTaps) / kStride + 1;
+  const long long need = conv0_scratch_bytes(batch);
+  SCB_CHECK(batch <= 65535, SCB_EUNSUPPORTED, "scb_conv0_groupnorm_gelu: batch exceeds grid limits");
+  SCB_CHECK(scratch_bytes >= need, SCB_EINVAL, "scb_conv0_groupnorm_gelu: scratch too small (%lld < %lld)", scratch_bytes, need);
+  if (batch == 0) return SCB_OK;
+  double* acc = reinterpret_cast<double*>(scratch);
+  float2* ss = reinterpret_cast<float2*>(acc + (long long)batch * kStatVals);
+  SCB_CUDA(cudaMemsetAsync(acc, 0, (size_t)batch * kStatVals * sizeof(double), st));
+  int chunks = (n_frames + 2559) / 2560;
+  if (chunks < 1) chunks = 1;
+  conv0_autocorr_kernel<<<dim3(chunks, batch), 256, 0, st>>>(wav, wav_ld, n_frames, acc);
+  note_launch();
+  SCB_LAUNCH_OK("conv0_autocorr");
+  conv0_finalize_kernel<<<dim3((channels + 127) / 128, batch), 128, 0, st>>>(acc, w, conv_bias, gamma, beta, n_frames, channels, eps, ss);
+  note_launch();
+  SCB_LAUNCH_OK("conv0_finalize");
+  conv0_apply_kernel<<<dim3((n_frames + kFramesPerBlock - 1) / kFramesPerBlock, batch), 256, 0, st>>>(wav, wav_ld, w, ss, out, out_fmt,
+                                                                                                     n_frames, out_batch_stride, channels);
+  note_launch();
+  SCB_LAUNCH_OK("conv0_apply");
+  return SCB_OK;
+}
+
+
+long long conv0_scratch_bytes(int batch) {
+  return (long long)batch * kStatVals * (long long)sizeof(double) + (long long)batch * 512 * (long long)sizeof(float2);
+}
+
+int conv0_layernorm_gelu(const float* wav, long long wav_ld, int batch, int n_samples, const float* w, const float* conv_bias,
+                         const float* gamma, const float* beta, float eps, void* out, int out_fmt, long long out_batch_stride,
+                         cudaStream_t st) {
+  SCB_CHECK(wav && w && out, SCB_EINVAL, "scb_conv0_layernorm_gelu: null operand");
+  SCB_CHECK(out_fmt == SCB_F16 || out_fmt == SCB_BF16, SCB_EINVAL, "scb_conv0_layernorm_gelu: 16-bit output required");
+  SCB_CHECK(n_samples >= kTaps, SCB_EINVAL, "scb_conv0_layernorm_gelu: utterance shorter than the conv kernel");
+  SCB_CHECK(batch <= 65535, SCB_EUNSUPPORTED, "scb_conv0_layernorm_gelu: batch exceeds grid limits");
+  if (batch == 0) return SCB_OK;
+  const int n_frames = (n_samples - kTaps) / kStride + 1;
+  int gx = (n_frames + 63) / 64;  // 8 frames per pass, ~8 passes per block amortise the weight staging
+  if (gx < 1) gx = 1;
+  conv0_ln_kernel<<<dim3(gx, batch), 256, 0, st>>>(wav, wav_ld, w, conv_bias, gamma, beta, eps, out, out_fmt, n_frames, out_batch_stride);
+  note_launch();
+  SCB_LAUNCH_OK("conv0_layernorm_gelu");
+  return SCB_OK;
+}
+
+int posconv_pack(float* x, const int* valid_frames, void* xpad, int fmt, int batch, int T, int D, int groups, int pad_left, int rows_pad,
+                 cudaStream_t st) {
+  SCB_CHECK(x && xpad, SCB_EINVAL, "scb_posconv_pack: null operand");
+  SCB_CHECK(D % groups == 0 && (D / groups) % 2 == 0 && D / groups <= 64, SCB_EUNSUPPORTED,
+            "scb_posconv_pack: channels per group (%d) must be even and <= 64", D / groups);
+  SCB_CHECK(rows_pad >= pad_left + T, SCB_EINVAL, "scb_posconv_pack: rows_pad too small");
+  const long long rows = (long long)batch * T;
+  if (rows == 0) return SCB_OK;
+  posconv_pack_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, valid_frames, xpad, fmt, rows, T, D, groups, D / groups, pad_left,
+                                                                 rows_pad);
+  note_launch();
+  SCB_LAUNCH_OK("posconv_pack");
+  return SCB_OK;
+}
+
+int patchify(const float* img, void* out, int fmt, int batch, int C, int H, int W, int P, int ldk, cudaStream_t st) {
+  SCB_CHECK(img && out, SCB_EINVAL, "scb_patchify: null operand");
+  SCB_CHECK(H % P == 0 && W % P == 0 && H == W, SCB_EINVAL, "scb_patchify: image %dx%d not divisible by patch %d", H, W, P);
+  SCB_CHECK(ldk >= C * P * P && ldk % 8 == 0, SCB_EINVAL, "scb_patchify: ldk must be >= C*P*P and a multiple of 8");
+  const int G = H / P;
+  if (batch == 0) return SCB_OK;
+  patchify_kernel<<<(unsigned)((long long)batch * G * G), 256, 0, st>>>(img, out, fmt, C, H, W, P, G, ldk);
+  note_launch();
+  SCB_LAUNCH_OK("patchify");
+  return SCB_OK;
+}
+
+int broadcast_row(const float* a, const float* a2, void* out, int out_dtype, long long out_stride, int nb, int d, cudaStream_t st) {
+  SCB_CHECK(a && out, SCB_EINVAL, "scb_broadcast_row: null operand");
+  if (nb == 0 || d == 0) return SCB_OK;
+  broadcast_row_kernel<<<dim3((d + 255) / 256, nb), 256, 0, st>>>(a, a2, out, out_dtype, out_stride, d);
+  note_launch();
+  SCB_LAUNCH_OK("broadcast_row");
+  return SCB_OK;
+}
+
+int cast_rows(const void* in, int in_dtype, long long in_ld, void* out, int out_dtype, long long out_ld, long long rows, int cols,
+              cudaStream_t st) {
+  SCB_CHECK(in && out, SCB_EINVAL, "scb_cast_rows: null operand");
+  if (rows == 0 || cols == 0) return SCB_OK;
+  long long blocks = (rows * cols + 255) / 256;
+  if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
+  cast_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, in_dtype, in_ld, out, out_dtype, out_ld, rows, cols);
+  note_launch();
+  SCB_LAUNCH_OK("cast_rows");
+  return SCB_OK;
+}
+
+template <typename TI>
+static int transpose_out(const TI* in, long long in_ld, void* out, int out_dtype, long long out_ld, int rows, int cols, cudaStream_t st) {
+  const dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  if (out_dtype == SCB_F32) transpose_kernel<TI, float><<<grid, block, 0, st>>>(in, in_ld, (float*)out, out_ld, rows, cols);
+  else if (out_dtype == SCB_F16) transpose_kernel<TI, __half><<<grid, block, 0, st>>>(in, in_ld, (__half*)out, out_ld, rows, cols);
+  else transpose_kernel<TI, __nv_bfloat16><<<grid, block, 0, st>>>(in, in_ld, (__nv_bfloat16*)out, out_ld, rows, cols);
+  note_launch();
+  SCB_LAUNCH_OK("transpose");
+  return SCB_OK;
+}
+
+int transpose(const void* in, int in_dtype, long long in_ld, void* out, int out_dtype, long long out_ld, int rows, int cols,
+              cudaStream_t st) {
+  SCB_CHECK(in && out, SCB_EINVAL, "scb_transpose: null operand");
+  if (rows == 0 || cols == 0) return SCB_OK;
+  SCB_CHECK((rows + 31) / 32 <= 65535, SCB_EUNSUPPORTED, "scb_transpose: too many rows (%d)", rows);
+  if (in_dtype == SCB_F32) return transpose_out((const float*)in, in_ld, out, out_dtype, out_ld, rows, cols, st);
+  if (in_dtype == SCB_F16) return transpose_out((const __half*)in, in_ld, out, out_dtype, out_ld, rows, cols, st);
+  return transpose_out((const __nv_bfloat16*)in, in_ld, out, out_dtype, out_ld, rows, cols, st);
+}
+
+}  // namespace scb

@@ -32,6 +32,7 @@ struct GemmParams {
   int out_dtype, out2_dtype, residual_dtype, act, ab_bf16;
   float alpha;
   long long ldc, out_batch_stride;
+  long long res_ld, res_batch_stride;
   int out_group_cols;
 };
 
@@ -188,6 +189,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int m = t.m0 + q * 32 + lane;
       const bool row_ok = m < p.m_per_batch;
       const long long row_off = (long long)t.b * p.out_batch_stride + (long long)m * p.ldc + (long long)t.g * p.out_group_cols;
+      const long long res_row_off = (long long)t.b * p.res_batch_stride + (long long)m * p.res_ld + (long long)t.g * p.out_group_cols;
       const int col_base = t.n0 + half * COLS_PER_WARP;
       int nchunks = 0;
       if (col_base < p.n) nchunks = min(COLS_PER_WARP / 32, (p.n - col_base + 31) / 32);
@@ -228,7 +230,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               const long long off = row_off + col;
               if (p.residual) {
                 float r[8];
-                load8(p.residual, p.residual_dtype, off, r);
+                load8(p.residual, p.residual_dtype, res_row_off + col, r);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) x[i] += r[i];
               }
@@ -313,6 +315,9 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
   p.ldc = a.ldc;
   p.out_batch_stride = a.out_batch_stride;
   p.out_group_cols = a.out_group_cols;
+  p.res_ld = a.residual_ld ? a.residual_ld : a.ldc;
+  p.res_batch_stride = a.residual_ld ? a.residual_batch_stride : a.out_batch_stride;
+  SCB_CHECK(p.res_ld % 8 == 0 && p.res_batch_stride % 8 == 0, SCB_EINVAL, "scb_gemm: residual strides must be multiples of 8 elements");
 
   CUtensorMap tmA, tmB;
   {

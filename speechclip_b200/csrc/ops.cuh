@@ -3,5 +3,67 @@
 #include "common.cuh"
 
 namespace scb {
+// gemm_tcgen05.cu
 int gemm(const scb_gemm_args& a, cudaStream_t stream);
+// loss.cu
+int sgemm(const float* a, long long a_rs, long long a_cs, const float* b, long long b_rs, long long b_cs, float* c, long long ldc, int M, int N,
+          int K, float alpha, float beta, cudaStream_t st);
+long long infonce_scratch_bytes(int B);
+int infonce(const float* feat_a, const float* feat_b, const long long* ids, int B, int D, const float* log_mult, float fixed_mult,
+            float margin, int dcl, int a2b, int b2a, int phase, float* loss, float* logits_out, float upstream, const float* upstream_dev,
+            float* dA, float* dB, float* dlog_mult, void* scratch, long long scratch_bytes, cudaStream_t st);
+// attention.cu
+int attention_fwd(const void* q, const void* k, const void* v, void* o, int fmt, long long q_ld, long long k_ld, long long v_ld,
+                  long long o_ld, long long q_bs, long long k_bs, long long v_bs, long long o_bs, const int* kv_len, int batch, int heads,
+                  int head_dim, int Tq, int Tk, float scale, int causal, cudaStream_t st);
+int cls_attention_fwd(const float* q, const void* kv, int kv_fmt, long long kv_ld, long long kv_bs, int k_off, int v_off,
+                      const int* kv_len, int batch, int heads, int head_dim, int Tk, float scale, float* probs, float* ctx32, void* ctx16,
+                      int ctx16_fmt, cudaStream_t st);
+int cls_attention_bwd(const float* q, const void* kv, int kv_fmt, long long kv_ld, long long kv_bs, int k_off, int v_off,
+                      const int* kv_len, int batch, int heads, int head_dim, int Tk, float scale, const float* probs, const float* dctx,
+                      void* dkv, int dkv_fmt, float* dq, cudaStream_t st);
+// frontend.cu
+long long conv0_scratch_bytes(int batch);
+int conv0_groupnorm_gelu(const float* wav, long long wav_ld, int batch, int n_samples, const float* w, const float* conv_bias,
+                         const float* gamma, const float* beta, float eps, void* out, int out_fmt, long long out_batch_stride,
+                         void* scratch, long long scratch_bytes, cudaStream_t st);
+int conv0_layernorm_gelu(const float* wav, long long wav_ld, int batch, int n_samples, const float* w, const float* conv_bias,
+                         const float* gamma, const float* beta, float eps, void* out, int out_fmt, long long out_batch_stride,
+                         cudaStream_t st);
+int posconv_pack(float* x, const int* valid_frames, void* xpad, int fmt, int batch, int T, int D, int groups, int pad_left, int rows_pad,
+                 cudaStream_t st);
+int patchify(const float* img, void* out, int fmt, int batch, int C, int H, int W, int P, int ldk, cudaStream_t st);
+int broadcast_row(const float* a, const float* a2, void* out, int out_dtype, long long out_stride, int nb, int d, cudaStream_t st);
+int cast_rows(const void* in, int in_dtype, long long in_ld, void* out, int out_dtype, long long out_ld, long long rows, int cols,
+              cudaStream_t st);
+int transpose(const void* in, int in_dtype, long long in_ld, void* out, int out_dtype, long long out_ld, int rows, int cols,
+              cudaStream_t st);
+// norm.cu
+int layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, float* y32, void* y16, int y16_fmt,
+                  float* stats, long long rows, int d, long long x_ld, long long y_ld, float eps, int act, cudaStream_t st);
+int layernorm_bwd(const float* dy, const float* x, const float* stats, const float* gamma, float* dx, float* dgamma, float* dbeta,
+                  long long rows, int d, cudaStream_t st);
+int l2norm_fwd(const float* x, float* y, float* norms, int rows, int d, cudaStream_t st);
+int l2norm_bwd(const float* dy, const float* y, const float* norms, float* dx, int rows, int d, cudaStream_t st);
+int weighted_sum_fwd(const float* h, long long layer_stride, const float* w_logits, int L, int normalize, float* out32, void* out16,
+                     int out16_fmt, long long rows, int d, int rows_per_batch, long long out16_batch_stride, long long out16_row0,
+                     cudaStream_t st);
+int weighted_sum_bwd(const float* h, long long layer_stride, const float* w_logits, int L, int normalize, const float* dout,
+                     long long rows, int d, int rows_per_batch, long long dout_batch_stride, long long dout_row0, float* scratch_L,
+                     float* grad_logits, float grad_scale, cudaStream_t st);
+// optim.cu
+int adam_step(float* p, const float* g, float* m, float* v, long long n, double* sumsq_scratch, float grad_scale, float max_norm, float lr,
+              float beta1, float beta2, float eps, float weight_decay, int step, void* p_f16, void* p_bf16, cudaStream_t st);
+// misc.cu
+int frame_lengths(const long long* wav_len, int batch, long long tw_out, int max_audio_len, int n_frames, int rate, const float* u,
+                  int* crop_off, int* crop_len, int* valid_frames, int* feat_len, long long* feat_len64, cudaStream_t st);
+int lengths_to_i32(const long long* in, int n, int add, int clamp_max, int* out, cudaStream_t st);
+int wav_prepare(const float* wav, long long wav_ld, int batch, const int* crop_off, const int* crop_len, long long tw_out, int normalize,
+                float* stats_scratch, float* out, long long out_ld, cudaStream_t st);
+int rows_bias_act(const float* x, long long x_ld, const float* bias, const float* res, long long res_ld, int act, float* pre, float* y,
+                  long long y_ld, long long rows, int d, cudaStream_t st);
+int gelu_bwd(const float* dy, const float* pre, float* dx, long long n, cudaStream_t st);
+int column_sum(const void* in, int in_dtype, long long ld, long long rows, int cols, float* out, float beta, cudaStream_t st);
+int retrieval_rank(const float* score, long long ld, int rows, int cols, const long long* cand_ids, const long long* answers, int* rank,
+                   int* top1, cudaStream_t st);
 }  // namespace scb

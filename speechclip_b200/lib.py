@@ -78,6 +78,7 @@ class GemmArgs(ctypes.Structure):
         ("residual", ctypes.c_void_p),
         ("residual_dtype", ctypes.c_int32), ("act", ctypes.c_int32),
         ("alpha", ctypes.c_float),
+        ("residual_ld", ctypes.c_int64), ("residual_batch_stride", ctypes.c_int64),
     ]
 
 
@@ -90,8 +91,51 @@ def _declare(lib):
     lib.scb_abi_version.restype = i32
     lib.scb_last_error.restype = ctypes.c_char_p
     lib.scb_launch_count.restype = i64
-    lib.scb_gemm.argtypes = [ctypes.POINTER(GemmArgs), vp]
-    lib.scb_gemm.restype = i32
+    lib.scb_conv0_scratch_bytes.restype = i64
+    lib.scb_conv0_scratch_bytes.argtypes = [i32]
+    lib.scb_infonce_scratch_bytes.restype = i64
+    lib.scb_infonce_scratch_bytes.argtypes = [i32]
+    sig = {
+        "scb_gemm": [ctypes.POINTER(GemmArgs), vp],
+        "scb_sgemm": [vp, i64, i64, vp, i64, i64, vp, i64, i32, i32, i32, f32, f32, vp],
+        "scb_attention_fwd": [vp, vp, vp, vp, i32] + [i64] * 8 + [vp, i32, i32, i32, i32, i32, f32, i32, vp],
+        "scb_cls_attention_fwd": [vp, vp, i32, i64, i64, i32, i32, vp, i32, i32, i32, i32, f32, vp, vp, vp, i32, vp],
+        "scb_cls_attention_bwd": [vp, vp, i32, i64, i64, i32, i32, vp, i32, i32, i32, i32, f32, vp, vp, vp, i32, vp, vp],
+        "scb_frame_lengths": [vp, i32, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp],
+        "scb_lengths_to_i32": [vp, i32, i32, i32, vp, vp],
+        "scb_wav_prepare": [vp, i64, i32, vp, vp, i64, i32, vp, vp, i64, vp],
+        "scb_conv0_groupnorm_gelu": [vp, i64, i32, i32, vp, vp, vp, vp, f32, vp, i32, i64, vp, i64, vp],
+        "scb_conv0_layernorm_gelu": [vp, i64, i32, i32, vp, vp, vp, vp, f32, vp, i32, i64, vp],
+        "scb_posconv_pack": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+        "scb_patchify": [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+        "scb_broadcast_row": [vp, vp, vp, i32, i64, i32, i32, vp],
+        "scb_cast_rows": [vp, i32, i64, vp, i32, i64, i64, i32, vp],
+        "scb_transpose": [vp, i32, i64, vp, i32, i64, i32, i32, vp],
+        "scb_layernorm_fwd": [vp, i32, vp, vp, vp, vp, i32, vp, i64, i32, i64, i64, f32, i32, vp],
+        "scb_layernorm_bwd": [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
+        "scb_l2norm_fwd": [vp, vp, vp, i32, i32, vp],
+        "scb_l2norm_bwd": [vp, vp, vp, vp, i32, i32, vp],
+        "scb_weighted_sum_fwd": [vp, i64, vp, i32, i32, vp, vp, i32, i64, i32, i32, i64, i64, vp],
+        "scb_weighted_sum_bwd": [vp, i64, vp, i32, i32, vp, i64, i32, i32, i64, i64, vp, vp, f32, vp],
+        "scb_rows_bias_act": [vp, i64, vp, vp, i64, i32, vp, vp, i64, i64, i32, vp],
+        "scb_gelu_bwd": [vp, vp, vp, i64, vp],
+        "scb_column_sum": [vp, i32, i64, i64, i32, vp, f32, vp],
+        "scb_infonce": [vp, vp, vp, i32, i32, vp, f32, f32, i32, i32, i32, i32, vp, vp, f32, vp, vp, vp, vp, vp, i64, vp],
+        "scb_adam_step": [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, f32, f32, i32, vp, vp, vp],
+        "scb_retrieval_rank": [vp, i64, i32, i32, vp, vp, vp, vp, vp],
+    }
+    for name, argtypes in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = i32
+
+
+EXPORTS = ["scb_abi_version", "scb_last_error", "scb_launch_count", "scb_conv0_scratch_bytes", "scb_infonce_scratch_bytes",
+           "scb_gemm", "scb_sgemm", "scb_attention_fwd", "scb_cls_attention_fwd", "scb_cls_attention_bwd", "scb_frame_lengths",
+           "scb_lengths_to_i32", "scb_wav_prepare", "scb_conv0_groupnorm_gelu", "scb_conv0_layernorm_gelu", "scb_posconv_pack", "scb_patchify",
+           "scb_broadcast_row", "scb_cast_rows", "scb_transpose", "scb_layernorm_fwd", "scb_layernorm_bwd", "scb_l2norm_fwd",
+           "scb_l2norm_bwd", "scb_weighted_sum_fwd", "scb_weighted_sum_bwd", "scb_rows_bias_act", "scb_gelu_bwd", "scb_column_sum",
+           "scb_infonce", "scb_adam_step", "scb_retrieval_rank"]
 
 
 def load():

@@ -1,7 +1,7 @@
 """Thin tensor-level wrappers over the C ABI: take torch CUDA tensors, pass raw pointers + sizes.
 
 torch is used for device memory and the current stream only; every arithmetic op below runs in
-libspeechclip_b200.so.
+libspeechclip_b200.so (include/speechclip_b200.h).  There is no CPU path: CPU tensors assert.
 """
 from __future__ import annotations
 
@@ -13,50 +13,263 @@ import torch
 from . import lib as _l
 
 _DT = {torch.float32: _l.F32, torch.float16: _l.F16, torch.bfloat16: _l.BF16}
+F32, F16, BF16 = _l.F32, _l.F16, _l.BF16
+ACT_NONE, ACT_GELU, ACT_QUICK_GELU = _l.ACT_NONE, _l.ACT_GELU, _l.ACT_QUICK_GELU
 
 
-def _stream() -> ctypes.c_void_p:
+def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _ptr(t: Optional[torch.Tensor]):
-    return None if t is None else ctypes.c_void_p(t.data_ptr())
-
-
-def _need(t: torch.Tensor, *dtypes):
+def _p(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
     assert t.is_cuda, "CUDA tensor required (there is no CPU path)"
-    assert t.dtype in dtypes, (t.dtype, dtypes)
-    return t
+    return ctypes.c_void_p(t.data_ptr())
 
 
-def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act: int = _l.ACT_NONE,
+def _call(name: str, *args):
+    rc = getattr(_l.load(), name)(*args, _stream())
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {_l.load().scb_last_error().decode()}")
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core GEMM
+def gemm_raw(*, a: torch.Tensor, a_inner: int, a_rows: int, a_row_stride: int, a_batch_stride: int = 0, batch: int = 1,
+             m_per_batch: int, w: torch.Tensor, n: int, k: int, b_row_stride: Optional[int] = None, groups: int = 1,
+             b_group_stride: int = 0, kb_per_tap: Optional[int] = None, tap_row_shift: int = 0, a_col0: int = 0,
+             a_group_cols: int = 0, out: torch.Tensor, ldc: int, out_batch_stride: int = 0, out_group_cols: int = 0,
+             out2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+             residual: Optional[torch.Tensor] = None, residual_ld: int = 0, residual_batch_stride: int = 0,
+             act: int = ACT_NONE, alpha: float = 1.0, a_offset: int = 0, out_offset: int = 0, residual_offset: int = 0):
+    """Full operand model of scb_gemm (plain / strided-conv / grouped tap walk); offsets are in elements."""
+    assert a.dtype in (torch.float16, torch.bfloat16) and w.dtype == a.dtype
+    g = _l.GemmArgs()
+    g.a = a.data_ptr() + a_offset * 2
+    g.a_inner, g.a_rows, g.a_row_stride, g.a_batch_stride = a_inner, a_rows, a_row_stride, a_batch_stride
+    g.batch, g.m_per_batch = batch, m_per_batch
+    g.kb_per_tap = kb_per_tap if kb_per_tap is not None else (k + 63) // 64
+    g.tap_row_shift, g.a_col0, g.a_group_cols = tap_row_shift, a_col0, a_group_cols
+    g.b = w.data_ptr()
+    g.b_row_stride = b_row_stride if b_row_stride is not None else k
+    g.b_group_stride, g.n, g.k, g.groups = b_group_stride, n, k, groups
+    g.out = out.data_ptr() + out_offset * out.element_size()
+    g.out_dtype, g.out_group_cols, g.ldc, g.out_batch_stride = _DT[out.dtype], out_group_cols, ldc, out_batch_stride
+    if out2 is not None:
+        g.out2, g.out2_dtype = out2.data_ptr() + out_offset * out2.element_size(), _DT[out2.dtype]
+    g.ab_format = _DT[a.dtype]
+    if bias is not None:
+        assert bias.dtype == torch.float32
+        g.bias = bias.data_ptr()
+    if residual is not None:
+        g.residual = residual.data_ptr() + residual_offset * residual.element_size()
+        g.residual_dtype = _DT[residual.dtype]
+        g.residual_ld, g.residual_batch_stride = residual_ld, residual_batch_stride
+    g.act, g.alpha = act, alpha
+    _call("scb_gemm", ctypes.byref(g))
+    return out
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
          residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
          out_dtype: torch.dtype = torch.float16, out2: Optional[torch.Tensor] = None, alpha: float = 1.0) -> torch.Tensor:
     """out[M,N] = act(alpha * a[M,K] @ w[N,K]^T + bias) + residual   (a, w 16-bit; fp32 accumulate on tcgen05)."""
-    _need(a, torch.float16, torch.bfloat16)
-    assert w.dtype == a.dtype and a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1]
-    assert a.stride(1) == 1 and w.stride(1) == 1
+    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1] and a.stride(1) == 1 and w.stride(1) == 1
     M, K = a.shape
     N = w.shape[0]
     if out is None:
         out = torch.empty(M, N, device=a.device, dtype=out_dtype)
     assert out.shape == (M, N) and out.stride(1) == 1
-    g = _l.GemmArgs()
-    g.a, g.a_inner, g.a_rows, g.a_row_stride, g.a_batch_stride = a.data_ptr(), K, M, a.stride(0), 0
-    g.batch, g.m_per_batch = 1, M
-    g.kb_per_tap, g.tap_row_shift, g.a_col0, g.a_group_cols = (K + 63) // 64, 0, 0, 0
-    g.b, g.b_row_stride, g.b_group_stride, g.n, g.k, g.groups = w.data_ptr(), w.stride(0), 0, N, K, 1
-    g.out, g.out_dtype, g.out_group_cols, g.ldc, g.out_batch_stride = out.data_ptr(), _DT[out.dtype], 0, out.stride(0), 0
     if out2 is not None:
         assert out2.shape == out.shape and out2.stride(0) == out.stride(0)
-        g.out2, g.out2_dtype = out2.data_ptr(), _DT[out2.dtype]
-    g.ab_format = _DT[a.dtype]
-    if bias is not None:
-        _need(bias, torch.float32)
-        g.bias = bias.data_ptr()
+    res_ld = 0
     if residual is not None:
-        assert residual.shape == out.shape and residual.stride(0) == out.stride(0)
-        g.residual, g.residual_dtype = residual.data_ptr(), _DT[residual.dtype]
-    g.act, g.alpha = act, alpha
-    _l.check(_l.load().scb_gemm(ctypes.byref(g), _stream()), "scb_gemm")
+        assert residual.shape == out.shape and residual.stride(1) == 1
+        res_ld = residual.stride(0)
+    return gemm_raw(a=a, a_inner=K, a_rows=M, a_row_stride=a.stride(0), m_per_batch=M, w=w, n=N, k=K, b_row_stride=w.stride(0),
+                    out=out, ldc=out.stride(0), out2=out2, bias=bias, residual=residual, residual_ld=res_ld, act=act, alpha=alpha)
+
+
+def sgemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, alpha: float = 1.0, beta: float = 0.0):
+    """c[M,N] = alpha * sum_k a[m,k] b[n,k] + beta * c  — a, b arbitrary-strided 2-D fp32 views (pass .t() for transposes)."""
+    assert a.dtype == b.dtype == c.dtype == torch.float32 and a.dim() == b.dim() == c.dim() == 2
+    M, K = a.shape
+    N = b.shape[0]
+    assert b.shape[1] == K and c.shape == (M, N) and c.stride(1) == 1
+    _call("scb_sgemm", _p(a), a.stride(0), a.stride(1), _p(b), b.stride(0), b.stride(1), _p(c), c.stride(0), M, N, K, alpha, beta)
+    return c
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, heads: int, scale: float,
+              kv_len: Optional[torch.Tensor] = None, causal: bool = False):
+    """q/k/v/out: [B, T, heads*hd] 16-bit views (last dim contiguous; typically slices of one fused QKV buffer)."""
+    B, Tq, D = q.shape
+    Tk = k.shape[1]
+    hd = D // heads
+    for t in (q, k, v, out):
+        assert t.stride(2) == 1 and t.dtype == q.dtype
+    if kv_len is not None:
+        assert kv_len.dtype == torch.int32
+    _call("scb_attention_fwd", _p(q), _p(k), _p(v), _p(out), _DT[q.dtype], q.stride(1), k.stride(1), v.stride(1), out.stride(1),
+          q.stride(0), k.stride(0), v.stride(0), out.stride(0), _p(kv_len), B, heads, hd, Tq, Tk, scale, int(causal))
     return out
+
+
+def cls_attention_fwd(q, kv, k_off, v_off, kv_len, heads, hd, scale, probs, ctx32):
+    B, Tk = kv.shape[0], kv.shape[1]
+    _call("scb_cls_attention_fwd", _p(q), _p(kv), _DT[kv.dtype], kv.stride(1), kv.stride(0), k_off, v_off, _p(kv_len), B, heads, hd,
+          Tk, scale, _p(probs), _p(ctx32), None, 0)
+
+
+def cls_attention_bwd(q, kv, k_off, v_off, kv_len, heads, hd, scale, probs, dctx, dkv, dq):
+    B, Tk = kv.shape[0], kv.shape[1]
+    assert dkv.shape == kv.shape and dkv.stride() == kv.stride()
+    _call("scb_cls_attention_bwd", _p(q), _p(kv), _DT[kv.dtype], kv.stride(1), kv.stride(0), k_off, v_off, _p(kv_len), B, heads, hd,
+          Tk, scale, _p(probs), _p(dctx), _p(dkv), _DT[dkv.dtype], _p(dq))
+
+
+# ------------------------------------------------------------------------------------------------ front end
+def frame_lengths(wav_len, batch, tw_out, max_audio_len, n_frames, rate, u, crop_off, crop_len, valid_frames, feat_len, feat_len64):
+    _call("scb_frame_lengths", _p(wav_len), batch, tw_out, max_audio_len, n_frames, rate, _p(u), _p(crop_off), _p(crop_len),
+          _p(valid_frames), _p(feat_len), _p(feat_len64))
+
+
+def lengths_to_i32(src, add, clamp_max, out):
+    assert src.dtype == torch.int64 and out.dtype == torch.int32
+    _call("scb_lengths_to_i32", _p(src), src.numel(), add, clamp_max, _p(out))
+    return out
+
+
+def wav_prepare(wav, crop_off, crop_len, tw_out, normalize, stats_scratch, out):
+    assert wav.dtype == torch.float32 and wav.stride(1) == 1 and out.stride(1) == 1
+    _call("scb_wav_prepare", _p(wav), wav.stride(0), wav.shape[0], _p(crop_off), _p(crop_len), tw_out, int(normalize),
+          _p(stats_scratch), _p(out), out.stride(0))
+
+
+def conv0_scratch_bytes(batch: int) -> int:
+    return int(_l.load().scb_conv0_scratch_bytes(batch))
+
+
+def conv0_groupnorm_gelu(wav, n_samples, w, conv_bias, gamma, beta, eps, out, out_batch_stride, scratch):
+    _call("scb_conv0_groupnorm_gelu", _p(wav), wav.stride(0), wav.shape[0], n_samples, _p(w), _p(conv_bias), _p(gamma), _p(beta), eps,
+          _p(out), _DT[out.dtype], out_batch_stride, _p(scratch), scratch.numel() * scratch.element_size())
+
+
+def conv0_layernorm_gelu(wav, n_samples, w, conv_bias, gamma, beta, eps, out, out_batch_stride):
+    _call("scb_conv0_layernorm_gelu", _p(wav), wav.stride(0), wav.shape[0], n_samples, _p(w), _p(conv_bias), _p(gamma), _p(beta), eps,
+          _p(out), _DT[out.dtype], out_batch_stride)
+
+
+def posconv_pack(x, valid_frames, xpad, batch, T, D, groups, pad_left, rows_pad):
+    _call("scb_posconv_pack", _p(x), _p(valid_frames), _p(xpad), _DT[xpad.dtype], batch, T, D, groups, pad_left, rows_pad)
+
+
+def patchify(img, out, P, ldk):
+    B, C, H, W = img.shape
+    assert img.is_contiguous() and img.dtype == torch.float32
+    _call("scb_patchify", _p(img), _p(out), _DT[out.dtype], B, C, H, W, P, ldk)
+
+
+def broadcast_row(a, a2, out, out_stride, nb, d, out_offset=0):
+    o = ctypes.c_void_p(out.data_ptr() + out_offset * out.element_size())
+    _call("scb_broadcast_row", _p(a), _p(a2), o, _DT[out.dtype], out_stride, nb, d)
+
+
+def cast_rows(src, dst, rows=None, cols=None, src_ld=None, dst_ld=None):
+    """dst[r, c] = src[r, c] with dtype conversion; 2-D views with contiguous last dim (or explicit rows/cols/ld)."""
+    if rows is None:
+        rows, cols = src.shape
+        src_ld, dst_ld = src.stride(0), dst.stride(0)
+    _call("scb_cast_rows", _p(src), _DT[src.dtype], src_ld, _p(dst), _DT[dst.dtype], dst_ld, rows, cols)
+    return dst
+
+
+def transpose(src, dst):
+    """dst[c, r] = src[r, c] (2-D, last dim contiguous), converting dtype."""
+    rows, cols = src.shape
+    assert dst.shape == (cols, rows) and src.stride(1) == 1 and dst.stride(1) == 1
+    _call("scb_transpose", _p(src), _DT[src.dtype], src.stride(0), _p(dst), _DT[dst.dtype], dst.stride(0), rows, cols)
+    return dst
+
+
+# ------------------------------------------------------------------------------------------------ row kernels
+def layernorm(x, gamma, beta, *, y32=None, y16=None, stats=None, rows=None, d=None, x_ld=None, y_ld=None, eps=1e-5, act=ACT_NONE):
+    if rows is None:
+        d = x.shape[-1]
+        rows = x.numel() // d
+    x_ld = d if x_ld is None else x_ld
+    y_ld = d if y_ld is None else y_ld
+    _call("scb_layernorm_fwd", _p(x), _DT[x.dtype], _p(gamma), _p(beta), _p(y32), _p(y16), _DT[y16.dtype] if y16 is not None else 0,
+          _p(stats), rows, d, x_ld, y_ld, eps, act)
+
+
+def layernorm_bwd(dy, x, stats, gamma, dx, dgamma, dbeta):
+    d = x.shape[-1]
+    _call("scb_layernorm_bwd", _p(dy), _p(x), _p(stats), _p(gamma), _p(dx), _p(dgamma), _p(dbeta), x.numel() // d, d)
+
+
+def l2norm(x, y, norms):
+    _call("scb_l2norm_fwd", _p(x), _p(y), _p(norms), x.shape[0], x.shape[1])
+
+
+def l2norm_bwd(dy, y, norms, dx):
+    _call("scb_l2norm_bwd", _p(dy), _p(y), _p(norms), _p(dx), y.shape[0], y.shape[1])
+
+
+def weighted_sum(h, w_logits, normalize, *, out32=None, out16=None, rows_per_batch=0, out16_batch_stride=0, out16_row0=0):
+    """h: [L, rows, d] fp32 (contiguous)."""
+    L, rows, d = h.shape
+    _call("scb_weighted_sum_fwd", _p(h), h.stride(0), _p(w_logits), L, int(normalize), _p(out32), _p(out16),
+          _DT[out16.dtype] if out16 is not None else 0, rows, d, rows_per_batch, out16_batch_stride, out16_row0)
+
+
+def weighted_sum_bwd(h, w_logits, normalize, dout, rows_per_batch, dout_batch_stride, dout_row0, scratch_L, grad_logits, grad_scale=1.0):
+    L, rows, d = h.shape
+    _call("scb_weighted_sum_bwd", _p(h), h.stride(0), _p(w_logits), L, int(normalize), _p(dout), rows, d, rows_per_batch,
+          dout_batch_stride, dout_row0, _p(scratch_L), _p(grad_logits), grad_scale)
+
+
+def rows_bias_act(x, bias, res, res_ld, act, pre, y, rows=None, d=None, x_ld=None, y_ld=None):
+    if rows is None:
+        rows, d = x.shape
+        x_ld, y_ld = x.stride(0), y.stride(0)
+    _call("scb_rows_bias_act", _p(x), x_ld, _p(bias), _p(res), res_ld, act, _p(pre), _p(y), y_ld, rows, d)
+
+
+def gelu_bwd(dy, pre, dx):
+    _call("scb_gelu_bwd", _p(dy), _p(pre), _p(dx), pre.numel())
+
+
+def column_sum(x, out, beta=0.0, rows=None, cols=None, ld=None):
+    if rows is None:
+        rows, cols = x.shape
+        ld = x.stride(0)
+    _call("scb_column_sum", _p(x), _DT[x.dtype], ld, rows, cols, _p(out), beta)
+
+
+# ------------------------------------------------------------------------------------------------ loss / optimiser / retrieval
+def infonce_scratch_bytes(B: int) -> int:
+    return int(_l.load().scb_infonce_scratch_bytes(B))
+
+
+def infonce(a, b, ids, log_mult, fixed_mult, margin, dcl, a2b, b2a, scratch, *, phase=3, loss=None, logits_out=None, upstream=1.0,
+            upstream_dev=None, dA=None, dB=None, dlog_mult=None):
+    B, D = a.shape
+    assert a.dtype == b.dtype == torch.float32 and a.is_contiguous() and b.is_contiguous()
+    if ids is not None:
+        assert ids.dtype == torch.int64 and ids.is_contiguous()
+    _call("scb_infonce", _p(a), _p(b), _p(ids), B, D, _p(log_mult), fixed_mult, margin, int(dcl), int(a2b), int(b2a), phase, _p(loss),
+          _p(logits_out), upstream, _p(upstream_dev), _p(dA), _p(dB), _p(dlog_mult), _p(scratch),
+          scratch.numel() * scratch.element_size())
+
+
+def adam_step(p, g, m, v, sumsq, grad_scale, max_norm, lr, beta1, beta2, eps, weight_decay, step, p_f16=None, p_bf16=None):
+    _call("scb_adam_step", _p(p), _p(g), _p(m), _p(v), p.numel(), _p(sumsq), grad_scale, max_norm, lr, beta1, beta2, eps, weight_decay,
+          step, _p(p_f16), _p(p_bf16))
+
+
+def retrieval_rank(score, cand_ids, answers, rank, top1):
+    rows, cols = score.shape
+    assert score.dtype == torch.float32 and score.stride(1) == 1
+    _call("scb_retrieval_rank", _p(score), score.stride(0), rows, cols, _p(cand_ids), _p(answers), _p(rank), _p(top1))

@@ -1,0 +1,148 @@
+"""Host-side logic that runs without a GPU: config container, schedules, model construction / state-dict layout,
+loud failure on CPU tensors, and the world_size-2 (gloo) feature gather + gradient routing."""
+import os
+import pickle
+from argparse import Namespace
+from collections import OrderedDict
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from avssl.base import OrderedNamespace
+from avssl.optim import get_scheduler
+from avssl.util import get_keypadding_mask
+from speechclip_b200.configs import parallel_config
+
+
+def test_ordered_namespace_semantics():
+    # mirrors the reference's own test (test/test_dict.py:7-67)
+    d_1 = {"a": 1, "b": [2, {"c": 3}], "d": {"e": 4, "f": "g"}, "h": SimpleNamespace(i=5, j={"k": 6})}
+    ons_1, ons_2 = OrderedNamespace(d_1), OrderedNamespace(**d_1)
+    assert ons_1.a == ons_1["a"] and ons_1.b == ons_1["b"] and ons_1.b[0] == 2 and ons_1.b[1].c == 3
+    assert ons_1.d.e == ons_1["d"]["e"] == ons_1.d["e"] == 4
+    assert ons_1.h.i == 5 and ons_1.h.j.k == 6 and ons_1 == ons_2 and len(ons_1) == 4 and len(ons_1.keys()) == 4 and "a" in ons_1
+    d_2, od_1 = ons_1.pydict, ons_1.odict
+    assert ons_1.keys() == d_2.keys() == od_1.keys() and d_2 == ons_1.to_dict() and od_1 == ons_1.to_odict()
+    assert isinstance(d_2, dict) and isinstance(od_1, OrderedDict)
+    assert OrderedNamespace({"a": 1, "b": 2}) == OrderedNamespace(SimpleNamespace(a=1, b=2)) == OrderedNamespace(Namespace(a=1, b=2))
+    ons_6 = OrderedNamespace([{"a": 1, "b": 2, "c": {"d": 3}}, Namespace(e=4, f=SimpleNamespace(g=5))])
+    assert (ons_6.a, ons_6.c.d, ons_6.e, ons_6.f.g, ons_6.f["g"]) == (1, 3, 4, 5, 5)
+    # checkpoint format: the pickle round-trips through __getstate__/__setstate__ (base_model.py:15)
+    back = pickle.loads(pickle.dumps(ons_1))
+    assert back == ons_1 and back.h.j.k == 6
+    assert ons_1.get("zz", 7) == 7 and not hasattr(ons_1, "zz")
+    assert dict(**ons_1.d) == {"e": 4, "f": "g"}
+
+
+def test_scheduler_matches_reference_fixture(golden):
+    lrs = golden("ref_scheduler.npz")["lrs"]
+    opt = torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))], lr=1e-4)
+    s = get_scheduler("linear_warmup_decay", opt, warmup=5, max_step=20, final_lr=1e-8)
+    mine = []
+    for _ in range(20):
+        mine.append(opt.param_groups[0]["lr"])
+        opt.step()
+        s.step()
+    assert np.allclose(mine, lrs, rtol=1e-12, atol=0)
+    with pytest.raises(NotImplementedError):
+        get_scheduler("cosine", opt)
+
+
+def test_keypadding_mask_matches_reference_fixture(golden):
+    z = golden("ref_keypad.npz")
+    assert torch.equal(get_keypadding_mask(12, torch.from_numpy(z["lens"])), torch.from_numpy(z["mask"]))
+
+
+def test_model_builds_with_reference_state_dict_layout():
+    from avssl.model import KWClip_GeneralTransformer
+    m = KWClip_GeneralTransformer(OrderedNamespace(parallel_config("base")))
+    keys = set(m.state_dict().keys())
+    for k in ("audio_encoder.encoder.feature_extractor.conv_layers.0.0.weight", "audio_encoder.encoder.feature_extractor.conv_layers.0.2.weight",
+              "audio_encoder.encoder.post_extract_proj.weight", "audio_encoder.encoder.encoder.pos_conv.0.weight_g",
+              "audio_encoder.encoder.encoder.layers.11.self_attn.q_proj.weight", "audio_encoder.encoder.encoder.layers.0.final_layer_norm.bias",
+              "audio_encoder.encoder.mask_emb", "audio_encoder.encoder.label_embs_concat", "audio_encoder.weightedsum_layer.weights",
+              "clip.model.visual.conv1.weight", "clip.model.visual.transformer.resblocks.11.attn.in_proj_weight", "clip.model.visual.proj",
+              "clip.model.token_embedding.weight", "clip.model.text_projection", "clip.model.logit_scale",
+              "criterion.eye_mat", "criterion.neg_eye_mat", "criterion.eye_mat_fl", "parallel_branch.cls",
+              "parallel_branch.self_att.model.layers.0.self_attn.in_proj_weight", "parallel_branch.self_att.model.layers.0.linear2.bias",
+              "parallel_branch.self_att.model.norm.weight", "parallel_branch.linear_proj.weight"):
+        assert k in keys, k
+    trainable = sum(p.numel() for p in m.getTrainableParams())
+    assert trainable == 7089408 + 768 + 768 * 512 + 512 + 13  # encoder layer + norm, cls, linear_proj, layer weights
+    assert all(not p.requires_grad for p in m.audio_encoder.encoder.parameters())
+    assert all(not p.requires_grad for p in m.clip.parameters())
+    assert m.audio_encoder.out_dim == 768 and m.audio_encoder.downsample_rate == 320 and m.audio_encoder.upstream_model_hiddenstates_len == 13
+    assert m.subword_embd_dim == 512 and m.recall_at == [1, 5, 10]
+    large = KWClip_GeneralTransformer(OrderedNamespace(parallel_config("tiny_large")))
+    assert "criterion.temperature" in large.state_dict() and large.criterion.temperature.requires_grad
+
+
+def test_unsupported_configs_fail_loudly():
+    from avssl.model import KWClip_GeneralTransformer
+    cfg = parallel_config("tiny")
+    cfg["model_settings"]["cascaded_objective_weight"] = 1.0
+    with pytest.raises(NotImplementedError):
+        KWClip_GeneralTransformer(OrderedNamespace(cfg))
+    cfg = parallel_config("tiny")
+    cfg["audio_encoder"]["trainable"] = True
+    with pytest.raises(NotImplementedError):
+        KWClip_GeneralTransformer(OrderedNamespace(cfg))
+    cfg = parallel_config("tiny")
+    cfg["audio_encoder"]["pretrained"] = True
+    with pytest.raises(FileNotFoundError):
+        KWClip_GeneralTransformer(OrderedNamespace(cfg))
+
+
+def test_product_path_has_no_cpu_fallback():
+    from avssl.model import KWClip_GeneralTransformer
+    from avssl.module import MaskedContrastiveLoss, mutualRetrieval
+    m = KWClip_GeneralTransformer(OrderedNamespace(parallel_config("tiny")))
+    b = {"wav": torch.randn(2, 4000), "wav_len": torch.tensor([4000, 3000]), "image": torch.randn(2, 3, 32, 32), "id": torch.arange(2)}
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.training_step(b)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        MaskedContrastiveLoss()(torch.randn(4, 8), torch.randn(4, 8), torch.arange(4))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mutualRetrieval(torch.randn(4, 2), torch.randn(2, 4), torch.arange(4) // 2, torch.arange(2), [1])
+
+
+def test_product_does_not_import_oracle():
+    import subprocess
+    import sys
+    code = ("import sys; import avssl.model, speechclip_b200.engine, speechclip_b200.head, speechclip_b200.optim; "
+            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported by the product'")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=root)
+
+
+def _gather_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from avssl.model.kwClip import gather_features
+    torch.manual_seed(rank)
+    a = torch.randn(3, 4, requires_grad=True)
+    feats = gather_features({"id": torch.arange(3) + 10 * rank, "image_feat": torch.randn(3, 4), "parallel_audio_feat": a, "tag": 1.0})
+    assert feats["parallel_audio_feat"].shape == (3 * world, 4) and feats["id"].tolist() == [0, 1, 2, 10, 11, 12]
+    w = torch.arange(3 * world * 4, dtype=torch.float32).view(3 * world, 4)
+    (feats["parallel_audio_feat"] * w).sum().backward()  # every rank evaluates the same global objective
+    assert torch.equal(a.grad, w[rank * 3:(rank + 1) * 3])  # ... and receives exactly the gradient rows of its own slice
+    q.put((rank, feats["parallel_audio_feat"].detach().clone()))
+    dist.destroy_process_group()
+
+
+def test_gather_features_world_size_2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert torch.equal(got[0], got[1])  # identical global feature matrix on both ranks
