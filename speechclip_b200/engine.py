@@ -214,7 +214,7 @@ class HubertPlan:
         ops.gemm_raw(a=xpad, a_inner=G * 64, a_rows=rows_pad, a_row_stride=G * 64, a_batch_stride=rows_pad * G * 64, batch=B,
                      m_per_batch=T, w=self.pos_w, n=cpg, k=K * 64, groups=G, b_group_stride=cpg * K * 64, kb_per_tap=1,
                      tap_row_shift=1, a_group_cols=64, out=tgt, ldc=d, out_batch_stride=T * d, out_group_cols=cpg,
-                     bias=self.pos_b, act=ops.ACT_GELU, residual=x)
+                     bias=self.pos_b, act=ops.ACT_GELU, residual=x, algo_k=K * cpg)
         if not self.pre_ln:
             x16 = ws.view("h16", (M, d), H)
             ops.layernorm(x, *self.enc_ln, y32=hidden[0], y16=x16, rows=M, d=d, eps=1e-5)
@@ -265,7 +265,7 @@ class VitPlan:
         xb = ws.view("vit_x1", (B * L, Wd), torch.float32)
         ops.gemm_raw(a=patches, a_inner=self.ldk, a_rows=G2, a_row_stride=self.ldk, a_batch_stride=G2 * self.ldk, batch=B,
                      m_per_batch=G2, w=self.conv_w, n=Wd, k=self.ldk, out=xa, out_offset=Wd, ldc=Wd, out_batch_stride=L * Wd,
-                     residual=self.pos, residual_offset=Wd, residual_ld=Wd, residual_batch_stride=0)
+                     residual=self.pos, residual_offset=Wd, residual_ld=Wd, residual_batch_stride=0, algo_k=self.kk)
         ops.broadcast_row(self.cls, self.pos, xa, L * Wd, B, Wd)
         ops.layernorm(xa, *self.ln_pre, y32=xa, rows=B * L, d=Wd, eps=1e-5)
         cur, nxt = xa, xb

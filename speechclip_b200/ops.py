@@ -28,8 +28,24 @@ def _p(t: Optional[torch.Tensor]):
     return ctypes.c_void_p(t.data_ptr())
 
 
+# bench.py's live per-entry-point timing: when PROFILE is a list every C-ABI call is bracketed by CUDA events on the
+# launching stream and (name, algorithmic flops, ev0, ev1) is appended.  None (the default) adds no work.
+PROFILE = None
+_FLOPS = 0.0
+_SHAPE = ""
+
+
 def _call(name: str, *args):
+    global _FLOPS, _SHAPE
+    prof = PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(_l.load(), name)(*args, _stream())
+    if prof is not None:
+        e1.record()
+        prof.append((name, _FLOPS, e0, e1, _SHAPE))
+        _FLOPS, _SHAPE = 0.0, ""
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {_l.load().scb_last_error().decode()}")
 
@@ -41,8 +57,14 @@ def gemm_raw(*, a: torch.Tensor, a_inner: int, a_rows: int, a_row_stride: int, a
              a_group_cols: int = 0, out: torch.Tensor, ldc: int, out_batch_stride: int = 0, out_group_cols: int = 0,
              out2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
              residual: Optional[torch.Tensor] = None, residual_ld: int = 0, residual_batch_stride: int = 0,
-             act: int = ACT_NONE, alpha: float = 1.0, a_offset: int = 0, out_offset: int = 0, residual_offset: int = 0):
-    """Full operand model of scb_gemm (plain / strided-conv / grouped tap walk); offsets are in elements."""
+             act: int = ACT_NONE, alpha: float = 1.0, a_offset: int = 0, out_offset: int = 0, residual_offset: int = 0,
+             algo_k: Optional[int] = None):
+    """Full operand model of scb_gemm (plain / strided-conv / grouped tap walk); offsets are in elements.
+    algo_k: the ALGORITHMIC contraction length when k carries zero padding (pos-conv groups padded 48 -> 64 channels)."""
+    global _FLOPS, _SHAPE
+    if PROFILE is not None:
+        _FLOPS = 2.0 * batch * groups * m_per_batch * n * (algo_k if algo_k is not None else k)
+        _SHAPE = f"b{batch} g{groups} m{m_per_batch} n{n} k{k} {str(a.dtype)[6:]}->{str(out.dtype)[6:]} act{act}{' bias' if bias is not None else ''}{' res' if residual is not None else ''}"
     assert a.dtype in (torch.float16, torch.bfloat16) and w.dtype == a.dtype
     g = _l.GemmArgs()
     g.a = a.data_ptr() + a_offset * 2

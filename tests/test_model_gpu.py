@@ -147,6 +147,12 @@ def test_training_steps_follow_torch_adam_on_the_oracle():
     for n, p in model.named_parameters():
         if p.requires_grad:
             mine, ref = p.detach().cpu() - start[n], od[n].detach() - start[n]
+            if n.endswith("in_proj_bias"):
+                # d loss / d b_k is exactly zero (a key bias shifts every score of a row equally): both sides apply
+                # sign(noise) * lr there, so leave the K third out of the comparison
+                d3 = mine.numel() // 3
+                keep = torch.cat([torch.arange(0, d3), torch.arange(2 * d3, 3 * d3)])
+                mine, ref = mine[keep], ref[keep]
             # Adam's early steps are sign-like (|update| ~ lr per element): elements whose gradient is at noise level may
             # differ, so compare the update in the mean, relative to the mean update size
             assert ref.abs().mean() > 1e-5, n
