@@ -116,8 +116,8 @@ __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restric
         a0 = fmaf(w0[k], xv, a0);
         a1 = fmaf(w1[k], xv, a1);
       }
-      a0 = gelu_erf(fmaf(a0, ss0.x, ss0.y));
-      a1 = gelu_erf(fmaf(a1, ss1.x, ss1.y));
+      a0 = gelu_fast(fmaf(a0, ss0.x, ss0.y));
+      a1 = gelu_fast(fmaf(a1, ss1.x, ss1.y));
       o[(long long)t * (channels / 2)] = pack16(out_fmt, a0, a1);
     }
   }

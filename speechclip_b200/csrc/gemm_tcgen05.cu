@@ -3,7 +3,7 @@
 //   warp 0 (1 thread)  TMA producer : cp.async.bulk.tensor A/B tiles -> 128B-swizzled smem ring
 //   warp 1 (1 thread)  MMA issuer   : tcgen05.mma 128 x N x 16, fp32 accumulators in TMEM (2 buffers)
 //   warp 2             TMEM allocator
-//   warps 4..11        epilogue     : tcgen05.ld -> alpha/bias/activation/residual -> global stores
+//   warps 4..          epilogue     : tcgen05.ld -> alpha/bias/activation/residual -> global stores (16 warps for BN >= 128)
 //
 // The two TMEM accumulator buffers let the epilogue of tile i overlap the MMAs of tile i+1.
 // See include/speechclip_b200.h (scb_gemm) for the operand model (plain / strided-conv / grouped tap walk).
@@ -16,8 +16,11 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = (4 + kEpiWarps) * 32;
+template <int BN> struct EpiCfg {
+  static constexpr int WARPS = BN >= 128 ? 16 : 8;          // 4 (or 2) warps per TMEM lane quarter
+  static constexpr int COLS = BN / (WARPS / 4);              // accumulator columns per warp: 64 / 32 / 32
+  static constexpr int THREADS = (4 + WARPS) * 32;
+};
 
 struct GemmParams {
   int batch, m_tiles_per_batch, n_tiles, groups, num_tiles;
@@ -54,44 +57,22 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) 
   return t;
 }
 
-__device__ __forceinline__ void store8(void* base, int dtype, long long off, const float (&x)[8]) {
+// 4 consecutive output elements of one row (8 B for 16-bit, 16 B for fp32).
+__device__ __forceinline__ void store4(void* base, int dtype, long long off, const float (&x)[4]) {
   if (dtype == SCB_F32) {
-    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off);
-    o[0] = make_float4(x[0], x[1], x[2], x[3]);
-    o[1] = make_float4(x[4], x[5], x[6], x[7]);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off) = make_float4(x[0], x[1], x[2], x[3]);
   } else {
-    uint4 u;
-    u.x = pack16(dtype, x[0], x[1]);
-    u.y = pack16(dtype, x[2], x[3]);
-    u.z = pack16(dtype, x[4], x[5]);
-    u.w = pack16(dtype, x[6], x[7]);
-    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(base) + off) = u;
-  }
-}
-
-__device__ __forceinline__ void load8(const void* base, int dtype, long long off, float (&x)[8]) {
-  if (dtype == SCB_F32) {
-    const float4* r = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
-    const float4 a = __ldg(r), b = __ldg(r + 1);
-    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
-    x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-  } else {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(base) + off));
-    float2 f;
-    f = unpack16(dtype, u.x); x[0] = f.x; x[1] = f.y;
-    f = unpack16(dtype, u.y); x[2] = f.x; x[3] = f.y;
-    f = unpack16(dtype, u.z); x[4] = f.x; x[5] = f.y;
-    f = unpack16(dtype, u.w); x[6] = f.x; x[7] = f.y;
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(base) + off) = make_uint2(pack16(dtype, x[0], x[1]), pack16(dtype, x[2], x[3]));
   }
 }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(EpiCfg<BN>::THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int B_BYTES = BN * BK * 2;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset arithmetic keeps the shared address space
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
@@ -99,6 +80,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* stage = reinterpret_cast<float*>(sB + STAGES * B_BYTES + 256);  // [epilogue warp][32 rows x 16 cols] transpose patches
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -114,7 +96,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], kEpiWarps);
+      mbar_init(&tempty[s], EpiCfg<BN>::WARPS);
     }
     mbar_fence_init();
   }
@@ -177,65 +159,97 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
+    // tcgen05.ld (32x32b) hands each lane one ROW of the accumulator.  Writing global memory in that layout costs one LSU
+    // wavefront per lane per instruction (32 different cache lines): measured 20 us per 128x256 fp32+residual tile against
+    // 3.5 us of MMA.  So every 32x16 chunk is transposed through a private, XOR-swizzled (bank-conflict-free) 2 KB shared
+    // patch: afterwards 4 lanes cover one 64-byte row segment and a warp instruction touches 8 rows instead of 32.  The
+    // residual loads of a chunk are issued before the TMEM load (out may alias residual, so the compiler cannot hoist them).
+    constexpr int COLS = EpiCfg<BN>::COLS;
     const int q = warp & 3;            // TMEM lane quarter this warp may touch
-    const int half = (warp - 4) >> 2;  // which half of the tile's columns
-    constexpr int COLS_PER_WARP = BN / 2;
+    const int part = (warp - 4) >> 2;  // which slice of the tile's columns
+    float4* stg = reinterpret_cast<float4*>(stage + (warp - 4) * (32 * 16));
+    const int prow = lane >> 2, u = lane & 3;  // after the transpose: row (within a pass of 8) and 4-column unit of this lane
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile<BN>(p, tile);
+      const int m_base = t.m0 + q * 32;
+      const int col_base = t.n0 + part * COLS;
+      const long long gcol = (long long)t.g * p.out_group_cols;
+      const long long out_base = (long long)t.b * p.out_batch_stride + (long long)m_base * p.ldc + gcol;
+      const long long res_base = (long long)t.b * p.res_batch_stride + (long long)m_base * p.res_ld + gcol;
+      int nchunks = 0;
+      if (col_base < p.n && m_base < p.m_per_batch) nchunks = min(COLS / 16, (p.n - col_base + 15) / 16);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const int m = t.m0 + q * 32 + lane;
-      const bool row_ok = m < p.m_per_batch;
-      const long long row_off = (long long)t.b * p.out_batch_stride + (long long)m * p.ldc + (long long)t.g * p.out_group_cols;
-      const long long res_row_off = (long long)t.b * p.res_batch_stride + (long long)m * p.res_ld + (long long)t.g * p.out_group_cols;
-      const int col_base = t.n0 + half * COLS_PER_WARP;
-      int nchunks = 0;
-      if (col_base < p.n) nchunks = min(COLS_PER_WARP / 32, (p.n - col_base + 31) / 32);
       if (nchunks == 0) {
         tc_fence_before();
         if (lane == 0) mbar_arrive(&tempty[acc]);
       }
       for (int ch = 0; ch < nchunks; ++ch) {
-        uint32_t v[32];
-        const int c0 = col_base + ch * 32;
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * COLS_PER_WARP + ch * 32), v);
+        const int col = col_base + ch * 16 + u * 4;  // first of this lane's 4 columns
+        const bool col_ok = col < p.n;               // n % 8 == 0: a 4-column unit is entirely inside or outside
+        // ---- residual + bias: everything this chunk needs from global memory, in flight at once
+        uint4 rr[4];
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok) {
+          if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol + col));
+          if (p.residual) {
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+              const int r = ps * 8 + prow;
+              if (m_base + r < p.m_per_batch) {
+                const long long off = res_base + (long long)r * p.res_ld + col;
+                if (p.residual_dtype == SCB_F32) {
+                  rr[ps] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.residual) + off));
+                } else {
+                  const uint2 h2 = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.residual) + off));
+                  rr[ps] = make_uint4(h2.x, h2.y, 0u, 0u);
+                }
+              }
+            }
+          }
+        }
+        uint32_t v[16];
+        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + part * COLS + ch * 16), v);
         tmem_ld_wait();
         if (ch == nchunks - 1) {  // accumulator fully read by this warp: hand the buffer back to the MMA warp
           tc_fence_before();
           if (lane == 0) mbar_arrive(&tempty[acc]);
         }
-        if (row_ok) {
+        __syncwarp();  // the previous chunk's reads of the patch are done
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int col = c0 + j * 8;
-            if (col < p.n) {
-              float x[8];
+        for (int k = 0; k < 4; ++k)  // row = lane; 16-byte unit k lands at k ^ ((lane >> 1) & 3): conflict-free both ways
+          stg[lane * 4 + (k ^ ((lane >> 1) & 3))] = make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]),
+                                                               __uint_as_float(v[4 * k + 2]), __uint_as_float(v[4 * k + 3]));
+        __syncwarp();
+        if (col_ok) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) x[i] = p.alpha * __uint_as_float(v[j * 8 + i]);
-              if (p.bias) {
-                const float4* bp = reinterpret_cast<const float4*>(p.bias + t.g * p.out_group_cols + col);
-                const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
-                x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-                x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-              }
+          for (int ps = 0; ps < 4; ++ps) {
+            const int r = ps * 8 + prow;
+            if (m_base + r < p.m_per_batch) {
+              const float4 a = stg[r * 4 + (u ^ ((r >> 1) & 3))];
+              float x[4] = {fmaf(p.alpha, a.x, bias4.x), fmaf(p.alpha, a.y, bias4.y), fmaf(p.alpha, a.z, bias4.z),
+                            fmaf(p.alpha, a.w, bias4.w)};
               if (p.act == SCB_ACT_GELU_ERF) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = gelu_erf(x[i]);
+                for (int i = 0; i < 4; ++i) x[i] = gelu_fast(x[i]);
               } else if (p.act == SCB_ACT_QUICK_GELU) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = quick_gelu(x[i]);
+                for (int i = 0; i < 4; ++i) x[i] = quick_gelu(x[i]);
               }
-              const long long off = row_off + col;
               if (p.residual) {
-                float r[8];
-                load8(p.residual, p.residual_dtype, res_row_off + col, r);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] += r[i];
+                if (p.residual_dtype == SCB_F32) {
+                  x[0] += __uint_as_float(rr[ps].x); x[1] += __uint_as_float(rr[ps].y);
+                  x[2] += __uint_as_float(rr[ps].z); x[3] += __uint_as_float(rr[ps].w);
+                } else {
+                  const float2 f0 = unpack16(p.residual_dtype, rr[ps].x), f1 = unpack16(p.residual_dtype, rr[ps].y);
+                  x[0] += f0.x; x[1] += f0.y; x[2] += f1.x; x[3] += f1.y;
+                }
               }
-              store8(p.out, p.out_dtype, off, x);
-              if (p.out2) store8(p.out2, p.out2_dtype, off, x);
+              const long long off = out_base + (long long)r * p.ldc + col;
+              store4(p.out, p.out_dtype, off, x);
+              if (p.out2) store4(p.out2, p.out2_dtype, off, x);
             }
           }
         }
@@ -255,14 +269,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 template <int BN, int STAGES>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  constexpr int smem_bytes = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + 256;
+  constexpr int smem_bytes = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + 256 + EpiCfg<BN>::WARPS * 32 * 16 * 4;
+  static_assert(smem_bytes <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
   static bool configured = false;
   if (!configured) {
     SCB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  gemm_tcgen05_kernel<BN, STAGES><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
+  gemm_tcgen05_kernel<BN, STAGES><<<grid, EpiCfg<BN>::THREADS, smem_bytes, stream>>>(tmA, tmB, p);
   note_launch();
   SCB_LAUNCH_OK("gemm_tcgen05");
   return SCB_OK;
