@@ -47,8 +47,8 @@ int64_t scb_launch_count(void);
  *   c_fc / c_proj / proj (clip_official.py:209), nn.TransformerEncoderLayer linears
  *   (kw_modules/TransformerModels.py:64-75), linear_proj (kwClip.py:1105-1106), and their dgrad/wgrad.
  *
- * A is a 16-bit tensor viewed as [batch][a_rows][a_inner] (strides in elements, a_inner contiguous).
- * K is walked in 64-element blocks; block kb reads A columns
+ * A is a 16-bit (or fp32, see ab_format) tensor viewed as [batch][a_rows][a_inner] (strides in elements, a_inner contiguous).
+ * K is walked in 128-byte blocks (64 16-bit elements; 32 for fp32); block kb reads A columns
  *   a_col0 + g*a_group_cols + (kb % kb_per_tap)*64 ... +63   of row   m + (kb / kb_per_tap) * tap_row_shift
  * which expresses a plain GEMM (kb_per_tap = K/64, shift 0), a strided Conv1d over channel-last
  * activations (pairs of input frames viewed as one row) and the grouped positional conv (one tap per
@@ -69,7 +69,7 @@ typedef struct scb_gemm_args {
   int64_t ldc, out_batch_stride;
   void* out2;           /* optional second copy of the result (same layout), may be NULL */
   int32_t out2_dtype;
-  int32_t ab_format;    /* SCB_F16 | SCB_BF16: format of A and B */
+  int32_t ab_format;    /* SCB_F16 | SCB_BF16 | SCB_F32: format of A and B (SCB_F32 operands are multiplied as TF32) */
   const float* bias;    /* optional, fp32, indexed by output column */
   const void* residual; /* optional; indexed like out unless residual_ld != 0 */
   int32_t residual_dtype;

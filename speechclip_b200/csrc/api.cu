@@ -40,8 +40,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_tmap_16b(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box, int swizzle128) {
+int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, int swizzle128) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -59,8 +59,8 @@ int make_tmap_16b(CUtensorMap* out, const void* base, int rank, const uint64_t* 
     es[i] = 1;
   }
   for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
-  // The element type only matters for OOB fill / arithmetic; both 16-bit formats move as raw 2-byte words.
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, es,
+  // The element type only matters for OOB fill / arithmetic: 16-bit formats move as raw 2-byte words, fp32/tf32 as 4-byte words.
+  CUresult r = fn(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SCB_CHECK(r == CUDA_SUCCESS, SCB_ECUDA,

@@ -32,9 +32,9 @@ int check_cuda(cudaError_t e, const char* what);
 int num_sms();
 void note_launch();  // bumps the per-process kernel-launch counter (scb_launch_count)
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency).
-// dims/strides innermost first; strides in BYTES for dims 1..rank-1; 16-bit elements.
-int make_tmap_16b(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box, int swizzle128);
+// dims/strides innermost first; strides in BYTES for dims 1..rank-1; 2- or 4-byte elements.
+int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, int swizzle128);
 
 // ---------------------------------------------------------------- 16-bit formats
 // SCB_F16 = IEEE half (forward activations / weights), SCB_BF16 = bfloat16 (gradient operands).
@@ -193,6 +193,15 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with fp32 operands read as TF32 (K = 8 per instruction): the fp32 rows of the trainable head need no 16-bit copies.
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane base + t).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -230,11 +239,12 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   return d;
 }
 // kind::f16 instruction descriptor: fp32 accumulator, A/B both K-major, format 0 = f16 / 1 = bf16.
-__device__ __forceinline__ uint32_t umma_idesc_f16(int m, int n, int fmt_bf16) {
+// (kind::tf32 uses the same layout with format 2 = tf32.)
+__device__ __forceinline__ uint32_t umma_idesc_f16(int m, int n, int fmt) {
   uint32_t d = 0;
-  d |= 1u << 4;                            // c_format = F32
-  d |= (uint32_t)(fmt_bf16 ? 1 : 0) << 7;  // a_format
-  d |= (uint32_t)(fmt_bf16 ? 1 : 0) << 10; // b_format
+  d |= 1u << 4;                 // c_format = F32
+  d |= (uint32_t)fmt << 7;      // a_format
+  d |= (uint32_t)fmt << 10;     // b_format
   d |= (uint32_t)(n >> 3) << 17;
   d |= (uint32_t)(m >> 4) << 24;
   return d;

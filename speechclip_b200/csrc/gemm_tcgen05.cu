@@ -15,7 +15,7 @@ namespace scb {
 namespace {
 
 constexpr int BM = 128;
-constexpr int BK = 64;
+constexpr int BK = 64;  // 16-bit elements per k-block (one 128-byte swizzle row); fp32/tf32 operands use 32
 template <int BN> struct EpiCfg {
   static constexpr int WARPS = BN >= 128 ? 16 : 8;          // 4 (or 2) warps per TMEM lane quarter
   static constexpr int COLS = BN / (WARPS / 4);              // accumulator columns per warp: 64 / 32 / 32
@@ -27,12 +27,13 @@ struct GemmParams {
   int m_per_batch, n, k_blocks;
   int kb_per_tap, tap_row_shift, a_col0, a_group_cols;
   int umma_n;
+  int bk;  // elements per k-block: 64 (16-bit) or 32 (tf32)
   uint32_t tx_bytes;
   void* out;
   void* out2;
   const float* bias;
   const void* residual;
-  int out_dtype, out2_dtype, residual_dtype, act, ab_bf16;
+  int out_dtype, out2_dtype, residual_dtype, act, ab_fmt;  // ab_fmt: 0 f16, 1 bf16, 2 tf32 (UMMA format codes)
   float alpha;
   long long ldc, out_batch_stride;
   long long res_ld, res_batch_stride;
@@ -118,8 +119,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_expect_tx(&full[stage], p.tx_bytes);
         const int tap = kb / p.kb_per_tap;
         const int kin = kb - tap * p.kb_per_tap;
-        tma_load_3d(sA + stage * A_BYTES, &tmA, &full[stage], a_c0 + kin * BK, t.m0 + tap * p.tap_row_shift, t.b);
-        tma_load_3d(sB + stage * B_BYTES, &tmB, &full[stage], kb * BK, t.n0, t.g);
+        tma_load_3d(sA + stage * A_BYTES, &tmA, &full[stage], a_c0 + kin * p.bk, t.m0 + tap * p.tap_row_shift, t.b);
+        tma_load_3d(sB + stage * B_BYTES, &tmB, &full[stage], kb * p.bk, t.n0, t.g);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1u;
@@ -128,7 +129,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1 && lane == 0) {
     // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = umma_idesc_f16(BM, p.umma_n, p.ab_bf16);
+    const uint32_t idesc = umma_idesc_f16(BM, p.umma_n, p.ab_fmt);
+    const bool tf32 = p.ab_fmt == 2;
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -145,7 +147,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           // advance 16 elements (32 B) inside the 128 B swizzle row: +2 in the (addr >> 4) field
-          tc_mma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          if (tf32) tc_mma_tf32(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          else tc_mma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
         }
         tc_commit(&empty[stage]);
         if (++stage == STAGES) {
@@ -287,13 +290,16 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, 
 
 int gemm(const scb_gemm_args& a, cudaStream_t stream) {
   SCB_CHECK(a.a && a.b && a.out, SCB_EINVAL, "scb_gemm: null operand");
-  SCB_CHECK(a.ab_format == SCB_F16 || a.ab_format == SCB_BF16, SCB_EINVAL, "scb_gemm: ab_format must be F16 or BF16");
+  SCB_CHECK(a.ab_format == SCB_F16 || a.ab_format == SCB_BF16 || a.ab_format == SCB_F32, SCB_EINVAL,
+            "scb_gemm: ab_format must be F16, BF16 or F32 (fp32 operands run as TF32)");
+  const int eb = a.ab_format == SCB_F32 ? 4 : 2;  // operand element bytes
+  const int al = 16 / eb;                          // elements per 16 bytes
   SCB_CHECK(a.n > 0 && a.k > 0 && a.batch > 0 && a.m_per_batch > 0 && a.groups > 0, SCB_EINVAL, "scb_gemm: empty problem");
   SCB_CHECK(a.n % 8 == 0, SCB_EINVAL, "scb_gemm: n (%d) must be a multiple of 8", a.n);
   SCB_CHECK(a.ldc % 8 == 0 && a.out_group_cols % 8 == 0 && a.out_batch_stride % 8 == 0, SCB_EINVAL,
             "scb_gemm: output strides must be multiples of 8 elements");
-  SCB_CHECK(a.a_row_stride % 8 == 0 && a.b_row_stride % 8 == 0 && a.a_batch_stride % 8 == 0 && a.b_group_stride % 8 == 0,
-            SCB_EINVAL, "scb_gemm: operand strides must be multiples of 8 elements (16 bytes)");
+  SCB_CHECK(a.a_row_stride % al == 0 && a.b_row_stride % al == 0 && a.a_batch_stride % al == 0 && a.b_group_stride % al == 0,
+            SCB_EINVAL, "scb_gemm: operand strides must be multiples of 16 bytes");
   SCB_CHECK((reinterpret_cast<uintptr_t>(a.a) | reinterpret_cast<uintptr_t>(a.b) | reinterpret_cast<uintptr_t>(a.out) |
              reinterpret_cast<uintptr_t>(a.out2) | reinterpret_cast<uintptr_t>(a.residual) |
              reinterpret_cast<uintptr_t>(a.bias)) % 16 == 0,
@@ -310,7 +316,8 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
   p.num_tiles = p.groups * p.batch * p.m_tiles_per_batch * p.n_tiles;
   p.m_per_batch = a.m_per_batch;
   p.n = a.n;
-  p.k_blocks = (a.k + BK - 1) / BK;
+  p.bk = BK * 2 / eb;
+  p.k_blocks = (a.k + p.bk - 1) / p.bk;
   p.kb_per_tap = a.kb_per_tap;
   p.tap_row_shift = a.tap_row_shift;
   p.a_col0 = a.a_col0;
@@ -325,7 +332,7 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
   p.out2_dtype = a.out2_dtype;
   p.residual_dtype = a.residual_dtype;
   p.act = a.act;
-  p.ab_bf16 = a.ab_format == SCB_BF16;
+  p.ab_fmt = a.ab_format == SCB_F32 ? 2 : (a.ab_format == SCB_BF16 ? 1 : 0);
   p.alpha = a.alpha;
   p.ldc = a.ldc;
   p.out_batch_stride = a.out_batch_stride;
@@ -339,17 +346,17 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
     const uint64_t rows = (uint64_t)a.a_rows;
     const uint64_t bstride = a.a_batch_stride ? (uint64_t)a.a_batch_stride : rows * (uint64_t)a.a_row_stride;
     const uint64_t dims[3] = {(uint64_t)a.a_inner, rows, (uint64_t)a.batch};
-    const uint64_t strides[2] = {(uint64_t)a.a_row_stride * 2, bstride * 2};
-    const uint32_t box[3] = {BK, BM, 1};
-    int e = make_tmap_16b(&tmA, a.a, 3, dims, strides, box, 1);
+    const uint64_t strides[2] = {(uint64_t)a.a_row_stride * eb, bstride * eb};
+    const uint32_t box[3] = {(uint32_t)p.bk, BM, 1};
+    int e = make_tmap(&tmA, a.a, eb, 3, dims, strides, box, 1);
     if (e) return e;
   }
   {
     const uint64_t gstride = a.b_group_stride ? (uint64_t)a.b_group_stride : (uint64_t)a.n * (uint64_t)a.b_row_stride;
     const uint64_t dims[3] = {(uint64_t)a.k, (uint64_t)a.n, (uint64_t)a.groups};
-    const uint64_t strides[2] = {(uint64_t)a.b_row_stride * 2, gstride * 2};
-    const uint32_t box[3] = {BK, (uint32_t)p.umma_n, 1};
-    int e = make_tmap_16b(&tmB, a.b, 3, dims, strides, box, 1);
+    const uint64_t strides[2] = {(uint64_t)a.b_row_stride * eb, gstride * eb};
+    const uint32_t box[3] = {(uint32_t)p.bk, (uint32_t)p.umma_n, 1};
+    int e = make_tmap(&tmB, a.b, eb, 3, dims, strides, box, 1);
     if (e) return e;
   }
   if (bn == 256) return launch<256, 4>(tmA, tmB, p, stream);

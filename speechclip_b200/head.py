@@ -39,6 +39,50 @@ def _ceil8(n: int) -> int:
     return (n + 7) // 8 * 8
 
 
+def _ceil4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+def _tc_ok(*ts) -> bool:
+    """fp32 2-D operands the tcgen05 GEMM can read as TF32: unit inner stride, 16-byte aligned rows and base."""
+    return all(t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in ts)
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias=None, residual=None):
+    """out[M,N] = x[M,K] @ w[N,K]^T (+ bias) (+ residual) on fp32 rows: TF32 tensor cores when the layout allows, else SIMT."""
+    N = w.shape[0]
+    if N % 8 == 0 and _tc_ok(x, w, out) and (residual is None or _tc_ok(residual)):
+        return ops.gemm(x, w, bias=bias, residual=residual, out=out)
+    ops.sgemm(x, w, out)
+    if bias is not None or residual is not None:
+        ops.rows_bias_act(out, bias, residual, residual.stride(0) if residual is not None else 0, ops.ACT_NONE, None, out)
+    return out
+
+
+def transposed(ws: Workspace, name: str, x: torch.Tensor) -> torch.Tensor:
+    """fp32 [R, C] -> fp32 view [C, R] of a workspace buffer whose row stride is padded to 16 bytes."""
+    R, C = x.shape
+    buf = ws.view(name, (C, _ceil4(R)), torch.float32)
+    ops.transpose(x, buf[:, :R])
+    return buf[:, :R]
+
+
+def wgrad(ws: Workspace, tag: str, dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor):
+    """out[N,K] = dy[M,N]^T @ x[M,K]  (contraction over the M rows)."""
+    if out.shape[1] % 8 == 0 and _tc_ok(out):
+        return ops.gemm(transposed(ws, tag + "_dyT", dy), transposed(ws, tag + "_xT", x), out=out)
+    return ops.sgemm(dy.t(), x.t(), out)
+
+
+def dgrad(ws: Workspace, tag: str, dy: torch.Tensor, w: torch.Tensor, out: torch.Tensor, residual=None):
+    """out[M,K] = dy[M,N] @ w[N,K] (+ residual; residual may be out itself)."""
+    if w.shape[1] % 8 == 0 and _tc_ok(dy, out) and (residual is None or _tc_ok(residual)):
+        return ops.gemm(dy, transposed(ws, tag + "_wT", w), residual=residual, out=out)
+    if residual is not None and residual.data_ptr() != out.data_ptr():
+        ops.rows_bias_act(residual, None, None, 0, ops.ACT_NONE, None, out)  # out = residual
+    return ops.sgemm(dy, w.t(), out, beta=0.0 if residual is None else 1.0)
+
+
 class ParallelHead:
     """Stateless executor; ``p`` maps the names in PARAM_ORDER to live fp32 CUDA tensors."""
 
@@ -75,25 +119,23 @@ class ParallelHead:
         ctx = _new((B, d), dev)
         ops.cls_attention_fwd(q, kv, 0, d, kv_len, heads, hd, hd ** -0.5, probs, ctx)
         t1 = _new((B, d), dev)
-        ops.sgemm(ctx, p[L0 + "self_attn.out_proj.weight"], t1)
-        ops.rows_bias_act(t1, p[L0 + "self_attn.out_proj.bias"], cls, 0, ops.ACT_NONE, None, t1)
+        linear(ctx, p[L0 + "self_attn.out_proj.weight"], t1, bias=p[L0 + "self_attn.out_proj.bias"])
+        ops.rows_bias_act(t1, None, cls, 0, ops.ACT_NONE, None, t1)  # + [CLS] residual (one row, broadcast)
         x1, st1 = _new((B, d), dev), _new((B, 2), dev)
         ops.layernorm(t1, p[L0 + "norm1.weight"], p[L0 + "norm1.bias"], y32=x1, stats=st1, eps=self.eps)
         ffn = p[L0 + "linear1.weight"].shape[0]
         h_pre, h = _new((B, ffn), dev), _new((B, ffn), dev)
-        ops.sgemm(x1, p[L0 + "linear1.weight"], h)
-        ops.rows_bias_act(h, p[L0 + "linear1.bias"], None, 0, ops.ACT_GELU, h_pre, h)
+        linear(x1, p[L0 + "linear1.weight"], h_pre, bias=p[L0 + "linear1.bias"])
+        ops.rows_bias_act(h_pre, None, None, 0, ops.ACT_GELU, None, h)
         t2 = _new((B, d), dev)
-        ops.sgemm(h, p[L0 + "linear2.weight"], t2)
-        ops.rows_bias_act(t2, p[L0 + "linear2.bias"], x1, d, ops.ACT_NONE, None, t2)
+        linear(h, p[L0 + "linear2.weight"], t2, bias=p[L0 + "linear2.bias"], residual=x1)
         x2, st2 = _new((B, d), dev), _new((B, 2), dev)
         ops.layernorm(t2, p[L0 + "norm2.weight"], p[L0 + "norm2.bias"], y32=x2, stats=st2, eps=self.eps)
         x3, st3 = _new((B, d), dev), _new((B, 2), dev)
         ops.layernorm(x2, p["self_att.model.norm.weight"], p["self_att.model.norm.bias"], y32=x3, stats=st3, eps=1e-5)
         if self.need_projection:
             out = _new((B, p["linear_proj.weight"].shape[0]), dev)
-            ops.sgemm(x3, p["linear_proj.weight"], out)
-            ops.rows_bias_act(out, p["linear_proj.bias"], None, 0, ops.ACT_NONE, None, out)
+            linear(x3, p["linear_proj.weight"], out, bias=p["linear_proj.bias"])
         else:
             out = x3
         saved = dict(B=B, T=T, src=src, kv=kv, q=q, probs=probs, ctx=ctx, t1=t1, x1=x1, st1=st1, h_pre=h_pre, h=h, t2=t2, x2=x2,
@@ -114,10 +156,10 @@ class ParallelHead:
         dcls = g["cls"].view(1, d)
         if self.need_projection:
             wp = p["linear_proj.weight"]
-            ops.sgemm(dout.t(), s["x3"].t(), g["linear_proj.weight"])
+            wgrad(ws, "hp", dout, s["x3"], g["linear_proj.weight"])
             ops.column_sum(dout, g["linear_proj.bias"])
             dx3 = _new((B, d), dev)
-            ops.sgemm(dout, wp.t(), dx3)
+            dgrad(ws, "hp", dout, wp, dx3)
         else:
             dx3 = dout.contiguous()
         # final norm, norm2
@@ -130,22 +172,22 @@ class ParallelHead:
         dt2 = _new((B, d), dev)
         ops.layernorm_bwd(dx2, s["t2"], s["st2"], p[L0 + "norm2.weight"], dt2, g[L0 + "norm2.weight"], g[L0 + "norm2.bias"])
         # MLP
-        ops.sgemm(dt2.t(), s["h"].t(), g[L0 + "linear2.weight"])
+        wgrad(ws, "h2", dt2, s["h"], g[L0 + "linear2.weight"])
         ops.column_sum(dt2, g[L0 + "linear2.bias"])
         dh = _new(s["h"].shape, dev)
-        ops.sgemm(dt2, p[L0 + "linear2.weight"].t(), dh)
+        dgrad(ws, "h2", dt2, p[L0 + "linear2.weight"], dh)
         ops.gelu_bwd(dh, s["h_pre"], dh)
-        ops.sgemm(dh.t(), s["x1"].t(), g[L0 + "linear1.weight"])
+        wgrad(ws, "h1", dh, s["x1"], g[L0 + "linear1.weight"])
         ops.column_sum(dh, g[L0 + "linear1.bias"])
-        ops.sgemm(dh, p[L0 + "linear1.weight"].t(), dt2, beta=1.0)  # dx1 = dt2 (residual) + dh W1
+        dgrad(ws, "h1", dh, p[L0 + "linear1.weight"], dt2, residual=dt2)  # dx1 = dt2 (residual path) + dh W1
         dt1 = _new((B, d), dev)
         ops.layernorm_bwd(dt2, s["t1"], s["st1"], p[L0 + "norm1.weight"], dt1, g[L0 + "norm1.weight"], g[L0 + "norm1.bias"])
         # attention out-proj (+ residual = [CLS])
-        ops.sgemm(dt1.t(), s["ctx"].t(), g[L0 + "self_attn.out_proj.weight"])
+        wgrad(ws, "ho", dt1, s["ctx"], g[L0 + "self_attn.out_proj.weight"])
         ops.column_sum(dt1, g[L0 + "self_attn.out_proj.bias"])
         ops.column_sum(dt1, dcls)
         dctx = _new((B, d), dev)
-        ops.sgemm(dt1, p[L0 + "self_attn.out_proj.weight"].t(), dctx)
+        dgrad(ws, "ho", dt1, p[L0 + "self_attn.out_proj.weight"], dctx)
         # single-query attention
         kv = s["kv"]
         dkv = ws.view("head_dkv", (B, Tk, 2 * d), BF)

@@ -65,12 +65,13 @@ def gemm_raw(*, a: torch.Tensor, a_inner: int, a_rows: int, a_row_stride: int, a
     if PROFILE is not None:
         _FLOPS = 2.0 * batch * groups * m_per_batch * n * (algo_k if algo_k is not None else k)
         _SHAPE = f"b{batch} g{groups} m{m_per_batch} n{n} k{k} {str(a.dtype)[6:]}->{str(out.dtype)[6:]} act{act}{' bias' if bias is not None else ''}{' res' if residual is not None else ''}"
-    assert a.dtype in (torch.float16, torch.bfloat16) and w.dtype == a.dtype
+    assert a.dtype in (torch.float16, torch.bfloat16, torch.float32) and w.dtype == a.dtype
     g = _l.GemmArgs()
-    g.a = a.data_ptr() + a_offset * 2
+    g.a = a.data_ptr() + a_offset * a.element_size()
     g.a_inner, g.a_rows, g.a_row_stride, g.a_batch_stride = a_inner, a_rows, a_row_stride, a_batch_stride
     g.batch, g.m_per_batch = batch, m_per_batch
-    g.kb_per_tap = kb_per_tap if kb_per_tap is not None else (k + 63) // 64
+    bk = 128 // a.element_size()
+    g.kb_per_tap = kb_per_tap if kb_per_tap is not None else (k + bk - 1) // bk
     g.tap_row_shift, g.a_col0, g.a_group_cols = tap_row_shift, a_col0, a_group_cols
     g.b = w.data_ptr()
     g.b_row_stride = b_row_stride if b_row_stride is not None else k
