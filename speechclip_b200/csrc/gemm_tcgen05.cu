@@ -15,6 +15,7 @@ namespace scb {
 namespace {
 
 constexpr int BM = 128;
+constexpr int kSlabTaps = 4;  // slab mode: taps (k-blocks) per pipeline stage — amortises the single-thread barrier/issue latency
 constexpr int BK = 64;  // 16-bit elements per k-block (one 128-byte swizzle row); fp32/tf32 operands use 32
 template <int BN> struct EpiCfg {
   static constexpr int WARPS = BN >= 128 ? 16 : 8;          // 4 (or 2) warps per TMEM lane quarter
@@ -28,6 +29,8 @@ struct GemmParams {
   int kb_per_tap, tap_row_shift, a_col0, a_group_cols;
   int umma_n;
   int bk;  // elements per k-block: 64 (16-bit) or 32 (tf32)
+  int slab;       // 1: one-tap-per-k-block walk with row shift 1 (positional conv): A is loaded ONCE per tile as a 256-row slab
+  int slab_stages, slab_sub_bytes;  // slab mode: B ring of slab_stages stages, each kSlabTaps sub-tiles of slab_sub_bytes
   uint32_t tx_bytes;
   void* out;
   void* out2;
@@ -80,7 +83,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* sfull = tempty + 2;   // slab mode: A slab landed / A slab free (2 slabs carved out of the unused A ring)
+  uint64_t* sempty = sfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + 2);
+  constexpr int SLAB_BYTES = 256 * BK * 2;  // 256 rows x 128 B
+  static_assert(BN > 64 || STAGES * A_BYTES >= 2 * SLAB_BYTES, "the A ring must hold two slabs");
   float* stage = reinterpret_cast<float*>(sB + STAGES * B_BYTES + 256);  // [epilogue warp][32 rows x 16 cols] transpose patches
 
   const int warp = threadIdx.x >> 5;
@@ -98,6 +105,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
       mbar_init(&tempty[s], EpiCfg<BN>::WARPS);
+      mbar_init(&sfull[s], 1);
+      mbar_init(&sempty[s], 1);
     }
     mbar_fence_init();
   }
@@ -111,9 +120,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
+    int sl = 0;
+    uint32_t sl_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile<BN>(p, tile);
       const int a_c0 = p.a_col0 + t.g * p.a_group_cols;
+      if (p.slab) {  // rows m0 .. m0+255 of this group's 64 columns: every tap's A tile is a row-shifted window of it
+        mbar_wait(&sempty[sl], sl_phase ^ 1u);
+        mbar_expect_tx(&sfull[sl], (uint32_t)SLAB_BYTES);
+        tma_load_3d(sA + sl * SLAB_BYTES, &tmA, &sfull[sl], a_c0, t.m0, t.b);
+        sl ^= 1;
+        if (sl == 0) sl_phase ^= 1u;
+      }
+      if (p.slab) {
+        // B ring for the slab walk: kSlabTaps consecutive taps per stage, carved out of [sA + 2 slabs, end of the B ring)
+        uint8_t* sBs = sA + 2 * SLAB_BYTES;
+        for (int kb0 = 0; kb0 < p.k_blocks; kb0 += kSlabTaps) {
+          const int ntap = min(kSlabTaps, p.k_blocks - kb0);
+          mbar_wait(&empty[stage], phase ^ 1u);
+          mbar_expect_tx(&full[stage], (uint32_t)(ntap * p.slab_sub_bytes));
+          for (int tp = 0; tp < ntap; ++tp)
+            tma_load_3d(sBs + stage * (kSlabTaps * p.slab_sub_bytes) + tp * p.slab_sub_bytes, &tmB, &full[stage], (kb0 + tp) * p.bk, t.n0, t.g);
+          if (++stage == p.slab_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        continue;
+      }
       for (int kb = 0; kb < p.k_blocks; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1u);
         mbar_expect_tx(&full[stage], p.tx_bytes);
@@ -135,11 +169,40 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int sl = 0;
+    uint32_t sl_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       mbar_wait(&tempty[acc], acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-      for (int kb = 0; kb < p.k_blocks; ++kb) {
+      if (p.slab) {
+        mbar_wait(&sfull[sl], sl_phase);
+        tc_fence_after();
+        // Tap kb reads rows kb .. kb+127 of the slab: the A descriptor's start address advances by kb rows (128 B each).
+        // The 128B swizzle XORs the 16-byte chunk index with ABSOLUTE shared-address bits [7:9] (in TMA and in the MMA's
+        // operand fetch alike), so a row-shifted window of a 1024-aligned slab needs no descriptor base offset (measured:
+        // base offset (kb & 7) gives wrong results, 0 is bit-identical to reloading every tap).
+        const uint32_t slab_addr = smem_u32(sA + sl * SLAB_BYTES);
+        const uint32_t bs_addr = smem_u32(sA + 2 * SLAB_BYTES);
+        for (int kb0 = 0; kb0 < p.k_blocks; kb0 += kSlabTaps) {
+          const int ntap = min(kSlabTaps, p.k_blocks - kb0);
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          for (int tp = 0; tp < ntap; ++tp) {
+            const uint64_t a_desc = umma_desc_kmajor_sw128(slab_addr + (uint32_t)(kb0 + tp) * 128u);
+            const uint64_t b_desc = umma_desc_kmajor_sw128(bs_addr + (uint32_t)(stage * kSlabTaps + tp) * (uint32_t)p.slab_sub_bytes);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              tc_mma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)((kb0 | tp | k) != 0));
+          }
+          tc_commit(&empty[stage]);
+          if (++stage == p.slab_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+      for (int kb = 0; kb < (p.slab ? 0 : p.k_blocks); ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(sA + stage * A_BYTES));
@@ -155,6 +218,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           stage = 0;
           phase ^= 1u;
         }
+      }
+      if (p.slab) {
+        tc_commit(&sempty[sl]);  // every MMA that read this slab has retired
+        sl ^= 1;
+        if (sl == 0) sl_phase ^= 1u;
       }
       tc_commit(&tfull[acc]);
       acc ^= 1;
@@ -323,6 +391,11 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
   p.a_col0 = a.a_col0;
   p.a_group_cols = a.a_group_cols;
   p.umma_n = ((a.n < bn ? a.n : bn) + 15) / 16 * 16;
+  p.slab = (eb == 2 && bn == 64 && a.kb_per_tap == 1 && a.tap_row_shift == 1 && p.k_blocks + BM - 1 <= 256) ? 1 : 0;
+  p.slab_sub_bytes = p.umma_n * BK * 2;  // 48 x 128 B = 6 KB (base) / 8 KB (large): multiples of the 1024-byte swizzle atom
+  if (p.slab && p.slab_sub_bytes % 1024 != 0) p.slab = 0;
+  p.slab_stages = 8;
+  while (p.slab && p.slab_stages * kSlabTaps * p.slab_sub_bytes > 8 * (BM * BK * 2 + 64 * BK * 2) - 2 * 256 * BK * 2) --p.slab_stages;
   p.tx_bytes = (uint32_t)(BM * BK * 2 + p.umma_n * BK * 2);
   p.out = a.out;
   p.out2 = a.out2;
@@ -347,7 +420,7 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
     const uint64_t bstride = a.a_batch_stride ? (uint64_t)a.a_batch_stride : rows * (uint64_t)a.a_row_stride;
     const uint64_t dims[3] = {(uint64_t)a.a_inner, rows, (uint64_t)a.batch};
     const uint64_t strides[2] = {(uint64_t)a.a_row_stride * eb, bstride * eb};
-    const uint32_t box[3] = {(uint32_t)p.bk, BM, 1};
+    const uint32_t box[3] = {(uint32_t)p.bk, (uint32_t)(p.slab ? 256 : BM), 1};
     int e = make_tmap(&tmA, a.a, eb, 3, dims, strides, box, 1);
     if (e) return e;
   }
