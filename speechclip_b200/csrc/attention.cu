@@ -146,37 +146,44 @@ __global__ void __launch_bounds__(128) attention_fwd_kernel(const AttnParams p) 
         mma16816<BF16>(s[nb2 * 2 + 1], qf[ks], kb[2], kb[3]);
       }
     }
-    // ---- scale + mask + online softmax
+    // ---- mask (boundary / causal tiles only) + online softmax.  The softmax scale is folded into the exponent:
+    //      p = 2^(s * scale_log2 - m * scale_log2), with the running max kept on the raw scores (scale > 0).
     const int key0 = tile * BKV;
+    if (key0 + BKV > kv_len || p.causal) {
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int key = key0 + nb * 8 + t4 * 2 + (j & 1);
+          const int row = (j < 2) ? row_a : row_b;
+          const bool ok = key < kv_len && (!p.causal || key <= row);
+          if (!ok) s[nb][j] = -INFINITY;
+        }
+      }
+    }
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int key = key0 + nb * 8 + t4 * 2 + (j & 1);
-        const int row = (j < 2) ? row_a : row_b;
-        const bool ok = key < kv_len && (!p.causal || key <= row);
-        const float val = ok ? s[nb][j] * p.scale_log2 : -INFINITY;
-        s[nb][j] = val;
-        mx[j >> 1] = fmaxf(mx[j >> 1], val);
-      }
+      mx[0] = fmaxf(mx[0], fmaxf(s[nb][0], s[nb][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[nb][2], s[nb][3]));
     }
-    float corr[2], m_use[2];
+    float corr[2], m_off[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
       const float m_new = fmaxf(m_run[r], mx[r]);
-      m_use[r] = (m_new == -INFINITY) ? 0.f : m_new;
-      corr[r] = exp2f(m_run[r] - m_use[r]);  // m_run = -inf -> 0
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      corr[r] = ex2_approx((m_run[r] - m_use) * p.scale_log2);  // m_run = -inf -> 0
+      m_off[r] = -m_use * p.scale_log2;
       m_run[r] = m_new;
     }
     float rs[2] = {0.f, 0.f};
     uint32_t pf[4][4];  // P as A fragments for 4 k16 steps over the 64 keys
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
-      const float p0 = exp2f(s[nb][0] - m_use[0]), p1 = exp2f(s[nb][1] - m_use[0]);
-      const float p2 = exp2f(s[nb][2] - m_use[1]), p3 = exp2f(s[nb][3] - m_use[1]);
+      const float p0 = ex2_approx(fmaf(s[nb][0], p.scale_log2, m_off[0])), p1 = ex2_approx(fmaf(s[nb][1], p.scale_log2, m_off[0]));
+      const float p2 = ex2_approx(fmaf(s[nb][2], p.scale_log2, m_off[1])), p3 = ex2_approx(fmaf(s[nb][3], p.scale_log2, m_off[1]));
       rs[0] += p0 + p1;
       rs[1] += p2 + p3;
       const uint32_t lo = BF16 ? H16<SCB_BF16>::pack(p0, p1) : H16<SCB_F16>::pack(p0, p1);
