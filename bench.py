@@ -217,8 +217,10 @@ def run_own(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t_host = time.perf_counter()
         for _ in range(steps):
             fn()
+        timed.host_ms = (time.perf_counter() - t_host) * 1e3 / steps  # python + launch time to ENQUEUE one step
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -239,6 +241,7 @@ def run_own(args):
     ops.PROFILE = []
     ms_total = timed(lambda: step(resident), args.steps)
     prof, ops.PROFILE = ops.PROFILE, None
+    host_ms = timed.host_ms
     launches = lib.launch_count() - n0
     ms_step = ms_total / args.steps
     value = global_batch / (ms_step * 1e-3)
@@ -303,7 +306,7 @@ def run_own(args):
                    "l2": "inputs (259 MB) and activations (GBs) larger than the 126 MB L2; no flush needed"},
         "e2e": {"value": global_batch / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms,
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (scb_gemm)", "achieved": achieved, "peak": pk["tflops"],
                      "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": traffic, "peak_source": pk["src"] + " (sustained cuBLAS bf16)",
                      "launches_per_step": gemm_n / args.steps, "gemm_ms_per_step": gemm_ms / args.steps,

@@ -25,9 +25,13 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
 }
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* p) {
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 template <bool BF16>
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -79,8 +83,44 @@ __device__ __forceinline__ void load_tile(uint16_t* smem, const uint16_t* g, lon
   }
 }
 
+// Same copy with every address computed once per CTA: when 128 threads tile the 64 x CH chunk grid in whole rows
+// (128 % CH == 0) thread t owns chunk column c0 = t % CH of rows r0 + i * (128 / CH); both the global pointer and the
+// swizzled shared offset then advance by constants.
+template <int HD>
+struct TileLoader {
+  static constexpr int CH = Cfg<HD>::CHUNKS;
+  static constexpr bool FAST = (128 % CH) == 0;
+  static constexpr int RSTEP = FAST ? 128 / CH : 0;
+  static constexpr int NI = FAST ? CH / 2 : 0;  // 64 * CH / 128 chunks per thread (CH = 2 -> 1)
+  const uint16_t* g0;   // global pointer of this thread's first chunk at tile row 0
+  long long step;       // elements between this thread's consecutive rows (RSTEP * ld)
+  long long tile_step;  // elements per 64-row tile
+  uint32_t s0;          // shared byte offset of the first chunk inside a tile buffer
+  int r0;
+  __device__ __forceinline__ void init(const uint16_t* g, long long ld) {
+    r0 = threadIdx.x / CH;
+    const int c0 = threadIdx.x % CH;
+    g0 = g + (long long)r0 * ld + c0 * 8;
+    step = (long long)RSTEP * ld;
+    tile_step = 64 * ld;
+    s0 = (uint32_t)((r0 * Cfg<HD>::PITCH_CHUNKS + ((c0 & ~7) | ((c0 ^ r0) & 7))) * 16);
+  }
+  // rows row0 .. row0+63 of the tensor -> tile buffer at shared address sbase; rows >= nrows_valid are zero-filled
+  __device__ __forceinline__ void load(uint32_t sbase, int tile_idx, int nrows_valid) const {
+    const uint16_t* gp = g0 + (long long)tile_idx * tile_step;
+    const int row0 = tile_idx * 64 + r0;
+#pragma unroll
+    for (int i = 0; i < (NI > 0 ? NI : 1); ++i) {
+      const bool ok = row0 + i * RSTEP < nrows_valid;
+      const int sz = ok ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + s0 + (uint32_t)(i * RSTEP * Cfg<HD>::PITCH_CHUNKS * 16)),
+                   "l"(ok ? gp + (long long)i * step : g0), "r"(sz) : "memory");
+    }
+  }
+};
+
 template <int HD, bool BF16>
-__global__ void __launch_bounds__(128) attention_fwd_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(128, HD <= 64 ? 4 : 2) attention_fwd_kernel(const AttnParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint16_t* sQ = reinterpret_cast<uint16_t*>(smem_raw);
   uint16_t* sK = sQ + Cfg<HD>::TILE_ELEMS;       // 2 buffers
@@ -100,10 +140,36 @@ __global__ void __launch_bounds__(128) attention_fwd_kernel(const AttnParams p) 
   if (p.causal) kv_end = min(kv_end, q0 + BQ);
   const int n_tiles = (kv_end + BKV - 1) / BKV;
 
-  load_tile<HD>(sQ, Q, p.q_ld, q0, p.Tq);
-  load_tile<HD>(sK, K, p.k_ld, 0, kv_end);
-  load_tile<HD>(sV, V, p.v_ld, 0, kv_end);
+  constexpr int TILE_BYTES = Cfg<HD>::TILE_ELEMS * 2;
+  constexpr int PITCH_B = Cfg<HD>::PITCH_CHUNKS * 16;  // bytes per tile row
+  const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV);
+  TileLoader<HD> ldk, ldv;
+  if (TileLoader<HD>::FAST) {
+    TileLoader<HD> ldq;
+    ldq.init(Q + (long long)q0 * p.q_ld, p.q_ld);
+    ldk.init(K, p.k_ld);
+    ldv.init(V, p.v_ld);
+    ldq.load(sQ_a, 0, p.Tq - q0);
+    ldk.load(sK_a, 0, kv_end);
+    ldv.load(sV_a, 0, kv_end);
+  } else {
+    load_tile<HD>(sQ, Q, p.q_ld, q0, p.Tq);
+    load_tile<HD>(sK, K, p.k_ld, 0, kv_end);
+    load_tile<HD>(sV, V, p.v_ld, 0, kv_end);
+  }
   cp_async_commit();
+
+  // ldmatrix addresses: (row, 16-byte chunk) of a tile lives at row*PITCH_B + ((chunk & ~7) | ((chunk ^ row) & 7)) * 16.  For
+  // a lane, row & 7 and the low bit of the chunk are fixed, and the unrolled loops add EVEN chunk bases / row bases that are
+  // multiples of 8, so the swizzled chunk is (base & ~7) | ((base & 7) ^ x_lane): four per-lane offsets + immediates.
+  const int rk_l = (lane & 7) + ((lane >> 4) << 3), xk = ((lane >> 3) & 1) ^ (lane & 7);                    // K (non-transposed)
+  const int rv_l = (lane & 7) + (((lane >> 3) & 1) << 3), xv = (lane >> 4) ^ (lane & 7);                    // V (transposed)
+  uint32_t kxo[4], vxo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    kxo[j] = (uint32_t)(rk_l * PITCH_B + (((2 * j) ^ xk) << 4));
+    vxo[j] = (uint32_t)(rv_l * PITCH_B + (((2 * j) ^ xv) << 4));
+  }
 
   constexpr int KS = HD / 16;  // k-steps over the head dim
   uint32_t qf[KS][4];
@@ -119,16 +185,25 @@ __global__ void __launch_bounds__(128) attention_fwd_kernel(const AttnParams p) 
     cp_async_wait<0>();
     __syncthreads();
     if (tile + 1 < n_tiles) {  // prefetch next K/V tile into the other buffer
-      load_tile<HD>(sK + ((tile + 1) & 1) * Cfg<HD>::TILE_ELEMS, K, p.k_ld, (tile + 1) * BKV, kv_end);
-      load_tile<HD>(sV + ((tile + 1) & 1) * Cfg<HD>::TILE_ELEMS, V, p.v_ld, (tile + 1) * BKV, kv_end);
+      if (TileLoader<HD>::FAST) {
+        ldk.load(sK_a + ((tile + 1) & 1) * TILE_BYTES, tile + 1, kv_end);
+        ldv.load(sV_a + ((tile + 1) & 1) * TILE_BYTES, tile + 1, kv_end);
+      } else {
+        load_tile<HD>(sK + ((tile + 1) & 1) * Cfg<HD>::TILE_ELEMS, K, p.k_ld, (tile + 1) * BKV, kv_end);
+        load_tile<HD>(sV + ((tile + 1) & 1) * Cfg<HD>::TILE_ELEMS, V, p.v_ld, (tile + 1) * BKV, kv_end);
+      }
       cp_async_commit();
     }
     if (tile == 0) {
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) ldmatrix_x4(qf[ks], tile_ptr<HD>(sQ, warp * 16 + (lane & 15), ks * 2 + (lane >> 4)));
     }
-    const uint16_t* sKt = sK + (tile & 1) * Cfg<HD>::TILE_ELEMS;
-    const uint16_t* sVt = sV + (tile & 1) * Cfg<HD>::TILE_ELEMS;
+    uint32_t ka[4], va[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      ka[j] = sK_a + (tile & 1) * TILE_BYTES + kxo[j];
+      va[j] = sV_a + (tile & 1) * TILE_BYTES + vxo[j];
+    }
 
     // ---- S = Q K^T  (16 x 64 per warp)
     float s[8][4];
@@ -141,7 +216,7 @@ __global__ void __launch_bounds__(128) attention_fwd_kernel(const AttnParams p) 
 #pragma unroll
       for (int nb2 = 0; nb2 < 4; ++nb2) {
         uint32_t kb[4];
-        ldmatrix_x4(kb, tile_ptr<HD>(const_cast<uint16_t*>(sKt), nb2 * 16 + (lane & 7) + ((lane >> 4) << 3), ks * 2 + ((lane >> 3) & 1)));
+        ldsm_x4(kb, ka[((ks * 2) & 7) >> 1] + (uint32_t)(nb2 * 16 * PITCH_B + ((ks * 2) & ~7) * 16));
         mma16816<BF16>(s[nb2 * 2], qf[ks], kb[0], kb[1]);
         mma16816<BF16>(s[nb2 * 2 + 1], qf[ks], kb[2], kb[3]);
       }
@@ -205,7 +280,7 @@ __global__ void __launch_bounds__(128) attention_fwd_kernel(const AttnParams p) 
 #pragma unroll
       for (int db2 = 0; db2 < HD / 16; ++db2) {
         uint32_t vb[4];
-        ldmatrix_x4_trans(vb, tile_ptr<HD>(const_cast<uint16_t*>(sVt), ks2 * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), db2 * 2 + (lane >> 4)));
+        ldsm_x4_trans(vb, va[((db2 * 2) & 7) >> 1] + (uint32_t)(ks2 * 16 * PITCH_B + ((db2 * 2) & ~7) * 16));
         mma16816<BF16>(o_acc[db2 * 2], pf[ks2], vb[0], vb[1]);
         mma16816<BF16>(o_acc[db2 * 2 + 1], pf[ks2], vb[2], vb[3]);
       }
@@ -249,167 +324,184 @@ int launch_attn(const AttnParams& p, int batch, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------ single-query attention
-// One warp per (batch, head).  q fp32 [heads*hd] shared by all batches.  kv 16-bit [B, Tk, ld] with K at column k_off + h*hd
-// and V at v_off + h*hd.  probs saved [B, heads, Tk] fp32 for backward.  ctx fp32 [B, heads*hd] (+ optional 16-bit copy).
+// One CTA (128 threads) per (utterance, head).  q fp32 [heads*hd] shared by all utterances.  kv 16-bit [B, Tk, ld] with K at
+// column k_off + h*hd and V at v_off + h*hd.  probs saved [B, heads, Tk] fp32 for backward.  ctx fp32 [B, heads*hd].
+//   scores : one KEY per thread (a full hd-long dot product from 16-byte loads; no per-key warp reduction)
+//   softmax: block reduction over the <= Tk scores held in shared memory
+//   context: one pair of output dims per thread, keys split over 128 / (hd/2) thread groups, coalesced row reads
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();  // red may still be read from a previous reduction
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+  return r;
+}
+
 template <int HD>
 __global__ void __launch_bounds__(128) cls_attention_fwd_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kv, int kv_fmt,
                                                                 long long kv_ld, long long kv_bs, int k_off, int v_off,
                                                                 const int* __restrict__ kv_len, int Tk, int heads, float scale,
                                                                 float* __restrict__ probs, float* __restrict__ ctx32,
                                                                 uint16_t* __restrict__ ctx16, int ctx16_fmt, int batch) {
-  extern __shared__ float sprob[];  // [warps][Tk]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int idx = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (idx >= batch * heads) return;
-  const int b = idx / heads, h = idx % heads;
-  float* pr = sprob + warp * Tk;
+  extern __shared__ float sm[];  // [Tk] scores/probs | [HD] q | [128 x 2] context partials | [8] reduction scratch
+  float* sc = sm;
+  float* sq = sc + Tk;
+  float* part = sq + HD;
+  float* red = part + 256;
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int len = kv_len ? min(kv_len[b], Tk) : Tk;
-  const uint16_t* base = kv + (long long)b * kv_bs;
-  // q slice in registers: each lane holds HD/32 pairs? use strided ownership: lane owns dims {2*lane + 64*i}
-  constexpr int PAIRS = (HD + 63) / 64;
-  float2 qv[PAIRS];
-#pragma unroll
-  for (int i = 0; i < PAIRS; ++i) {
-    const int d = 2 * lane + 64 * i;
-    qv[i] = d < HD ? make_float2(q[h * HD + d] * scale, q[h * HD + d + 1] * scale) : make_float2(0.f, 0.f);
-  }
+  const uint16_t* base = kv + (long long)b * kv_bs + h * HD;
+  for (int d = tid; d < HD; d += 128) sq[d] = q[h * HD + d] * scale;
+  __syncthreads();
   float mx = -INFINITY;
-  for (int j = 0; j < len; ++j) {
-    const uint16_t* kr = base + (long long)j * kv_ld + k_off + h * HD;
+  for (int j = tid; j < len; j += 128) {
+    const uint16_t* kr = base + (long long)j * kv_ld + k_off;
     float dot = 0.f;
 #pragma unroll
-    for (int i = 0; i < PAIRS; ++i) {
-      const int d = 2 * lane + 64 * i;
-      if (d < HD) {
-        const float2 kk = unpack16(kv_fmt, *reinterpret_cast<const uint32_t*>(kr + d));
-        dot += qv[i].x * kk.x + qv[i].y * kk.y;
-      }
+    for (int c = 0; c < HD / 8; ++c) {
+      const uint4 u = *reinterpret_cast<const uint4*>(kr + c * 8);
+      const float2 a = unpack16(kv_fmt, u.x), bb = unpack16(kv_fmt, u.y), cc = unpack16(kv_fmt, u.z), dd = unpack16(kv_fmt, u.w);
+      const float* qq = sq + c * 8;
+      dot += a.x * qq[0] + a.y * qq[1] + bb.x * qq[2] + bb.y * qq[3] + cc.x * qq[4] + cc.y * qq[5] + dd.x * qq[6] + dd.y * qq[7];
     }
-    dot = warp_sum(dot);
-    if (lane == 0) pr[j] = dot;
+    sc[j] = dot;
     mx = fmaxf(mx, dot);
   }
-  __syncwarp();
+  mx = block_reduce(mx, red, true);
   float sum = 0.f;
-  for (int j = lane; j < len; j += 32) {
-    const float e = __expf(pr[j] - mx);
-    pr[j] = e;
+  for (int j = tid; j < len; j += 128) {
+    const float e = __expf(sc[j] - mx);
+    sc[j] = e;
     sum += e;
   }
-  sum = warp_sum(sum);
+  sum = block_reduce(sum, red, false);  // (its barriers also publish sc[])
   const float inv = 1.f / sum;
-  __syncwarp();
-  float2 acc[PAIRS];
-#pragma unroll
-  for (int i = 0; i < PAIRS; ++i) acc[i] = make_float2(0.f, 0.f);
-  for (int j = 0; j < len; ++j) {
-    const float pj = pr[j] * inv;
-    const uint16_t* vr = base + (long long)j * kv_ld + v_off + h * HD;
-#pragma unroll
-    for (int i = 0; i < PAIRS; ++i) {
-      const int d = 2 * lane + 64 * i;
-      if (d < HD) {
-        const float2 vv = unpack16(kv_fmt, *reinterpret_cast<const uint32_t*>(vr + d));
-        acc[i].x += pj * vv.x;
-        acc[i].y += pj * vv.y;
-      }
+  float* po = probs + ((long long)b * heads + h) * Tk;
+  for (int j = tid; j < Tk; j += 128) po[j] = j < len ? sc[j] * inv : 0.f;
+  constexpr int P = HD / 2;                    // dim pairs
+  constexpr int G = P >= 128 ? 1 : 128 / P;    // key groups
+  const int pr = tid % P, grp = tid / P;
+  float2 acc = make_float2(0.f, 0.f);
+  if (grp < G) {
+    const uint16_t* vr = base + v_off + pr * 2;
+#pragma unroll 4
+    for (int j = grp; j < len; j += G) {
+      const float2 vv = unpack16(kv_fmt, *reinterpret_cast<const uint32_t*>(vr + (long long)j * kv_ld));
+      const float pj = sc[j];
+      acc.x += pj * vv.x;
+      acc.y += pj * vv.y;
     }
   }
-  float* po = probs + ((long long)b * heads + h) * Tk;
-  for (int j = lane; j < Tk; j += 32) po[j] = j < len ? pr[j] * inv : 0.f;
-#pragma unroll
-  for (int i = 0; i < PAIRS; ++i) {
-    const int d = 2 * lane + 64 * i;
-    if (d < HD) {
-      const long long off = (long long)b * heads * HD + h * HD + d;
-      if (ctx32) *reinterpret_cast<float2*>(ctx32 + off) = acc[i];
-      if (ctx16) *reinterpret_cast<uint32_t*>(ctx16 + off) = pack16(ctx16_fmt, acc[i].x, acc[i].y);
+  part[tid * 2] = acc.x;
+  part[tid * 2 + 1] = acc.y;
+  __syncthreads();
+  if (tid < P) {
+    float2 r = make_float2(0.f, 0.f);
+    for (int g2 = 0; g2 < G; ++g2) {
+      r.x += part[(g2 * P + tid) * 2];
+      r.y += part[(g2 * P + tid) * 2 + 1];
     }
+    r.x *= inv;
+    r.y *= inv;
+    const long long off = (long long)b * heads * HD + h * HD + tid * 2;
+    if (ctx32) *reinterpret_cast<float2*>(ctx32 + off) = r;
+    if (ctx16) *reinterpret_cast<uint32_t*>(ctx16 + off) = pack16(ctx16_fmt, r.x, r.y);
   }
 }
 
 // Backward of the single-query attention.  dctx fp32 [B, heads*hd].  Writes dKV 16-bit [B, Tk, ld] (K grads at k_off, V grads
-// at v_off; rows >= len are zero) and accumulates dq (unscaled q gradient, fp32 [heads*hd]) with atomics.
+// at v_off; rows >= len are zero) and accumulates dq (gradient of the UNSCALED q, fp32 [heads*hd]) with atomics.
 template <int HD>
 __global__ void __launch_bounds__(128) cls_attention_bwd_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kv, int kv_fmt,
                                                                 long long kv_ld, long long kv_bs, int k_off, int v_off,
                                                                 const int* __restrict__ kv_len, int Tk, int heads, float scale,
                                                                 const float* __restrict__ probs, const float* __restrict__ dctx,
                                                                 uint16_t* __restrict__ dkv, int dkv_fmt, float* __restrict__ dq, int batch) {
-  extern __shared__ float sds[];  // [warps][Tk]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int idx = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (idx >= batch * heads) return;
-  const int b = idx / heads, h = idx % heads;
-  float* ds = sds + warp * Tk;
+  extern __shared__ float sm[];  // [Tk] ds | [Tk] p | [HD] q | [HD] dctx | [256] partials | [8] scratch
+  float* sds = sm;
+  float* sp = sds + Tk;
+  float* sq = sp + Tk;
+  float* sdc = sq + HD;
+  float* part = sdc + HD;
+  float* red = part + 256;
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int len = kv_len ? min(kv_len[b], Tk) : Tk;
-  const uint16_t* base = kv + (long long)b * kv_bs;
-  uint16_t* dbase = dkv + (long long)b * kv_bs;
-  const float* pr = probs + ((long long)b * heads + h) * Tk;
-  constexpr int PAIRS = (HD + 63) / 64;
-  float2 qv[PAIRS], dc[PAIRS], dqa[PAIRS];
-#pragma unroll
-  for (int i = 0; i < PAIRS; ++i) {
-    const int d = 2 * lane + 64 * i;
-    const bool ok = d < HD;
-    qv[i] = ok ? make_float2(q[h * HD + d], q[h * HD + d + 1]) : make_float2(0.f, 0.f);
-    dc[i] = ok ? *reinterpret_cast<const float2*>(dctx + (long long)b * heads * HD + h * HD + d) : make_float2(0.f, 0.f);
-    dqa[i] = make_float2(0.f, 0.f);
+  const uint16_t* base = kv + (long long)b * kv_bs + h * HD;
+  uint16_t* dbase = dkv + (long long)b * kv_bs + h * HD;
+  const float* pr_g = probs + ((long long)b * heads + h) * Tk;
+  for (int d = tid; d < HD; d += 128) {
+    sq[d] = q[h * HD + d];
+    sdc[d] = dctx[(long long)b * heads * HD + h * HD + d];
   }
-  // dp_j = <dctx, v_j>;  dot = sum_j p_j dp_j
+  __syncthreads();
+  // dp_j = <dctx, v_j> (one key per thread);  dot = sum_j p_j dp_j
   float dot = 0.f;
-  for (int j = 0; j < len; ++j) {
-    const uint16_t* vr = base + (long long)j * kv_ld + v_off + h * HD;
+  for (int j = tid; j < len; j += 128) {
+    const uint16_t* vr = base + (long long)j * kv_ld + v_off;
     float dp = 0.f;
 #pragma unroll
-    for (int i = 0; i < PAIRS; ++i) {
-      const int d = 2 * lane + 64 * i;
-      if (d < HD) {
-        const float2 vv = unpack16(kv_fmt, *reinterpret_cast<const uint32_t*>(vr + d));
-        dp += dc[i].x * vv.x + dc[i].y * vv.y;
-      }
+    for (int c = 0; c < HD / 8; ++c) {
+      const uint4 u = *reinterpret_cast<const uint4*>(vr + c * 8);
+      const float2 a = unpack16(kv_fmt, u.x), bb = unpack16(kv_fmt, u.y), cc = unpack16(kv_fmt, u.z), dd = unpack16(kv_fmt, u.w);
+      const float* g = sdc + c * 8;
+      dp += a.x * g[0] + a.y * g[1] + bb.x * g[2] + bb.y * g[3] + cc.x * g[4] + cc.y * g[5] + dd.x * g[6] + dd.y * g[7];
     }
-    dp = warp_sum(dp);
-    if (lane == 0) ds[j] = dp;
-    dot += pr[j] * dp;
+    const float pj = pr_g[j];
+    sp[j] = pj;
+    sds[j] = dp;
+    dot += pj * dp;
   }
-  __syncwarp();
-  for (int j = 0; j < Tk; ++j) {
-    uint16_t* dkr = dbase + (long long)j * kv_ld + k_off + h * HD;
-    uint16_t* dvr = dbase + (long long)j * kv_ld + v_off + h * HD;
+  dot = block_reduce(dot, red, false);
+  for (int j = tid; j < len; j += 128) sds[j] = sp[j] * (sds[j] - dot) * scale;  // d(score_j) * scale: score = scale * <q, k_j>
+  __syncthreads();
+  // dK_j = ds_j * q, dV_j = p_j * dctx : one 16-byte chunk (8 dims) of one key row per thread per step, coalesced
+  constexpr int CH = HD / 8;
+  for (int idx = tid; idx < Tk * CH; idx += 128) {
+    const int j = idx / CH, c = idx % CH;
+    uint4 uk = make_uint4(0u, 0u, 0u, 0u), uv = uk;
     if (j < len) {
-      const float pj = pr[j];
-      const float dsj = pj * (ds[j] - dot) * scale;  // d(score_j) * scale: score = scale * <q, k_j>
-      const uint16_t* kr = base + (long long)j * kv_ld + k_off + h * HD;
-#pragma unroll
-      for (int i = 0; i < PAIRS; ++i) {
-        const int d = 2 * lane + 64 * i;
-        if (d < HD) {
-          const float2 kk = unpack16(kv_fmt, *reinterpret_cast<const uint32_t*>(kr + d));
-          dqa[i].x += dsj * kk.x;
-          dqa[i].y += dsj * kk.y;
-          *reinterpret_cast<uint32_t*>(dkr + d) = pack16(dkv_fmt, dsj * qv[i].x, dsj * qv[i].y);
-          *reinterpret_cast<uint32_t*>(dvr + d) = pack16(dkv_fmt, pj * dc[i].x, pj * dc[i].y);
-        }
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < PAIRS; ++i) {
-        const int d = 2 * lane + 64 * i;
-        if (d < HD) {
-          *reinterpret_cast<uint32_t*>(dkr + d) = 0u;
-          *reinterpret_cast<uint32_t*>(dvr + d) = 0u;
-        }
-      }
+      const float ds = sds[j], pj = sp[j];
+      const float* qq = sq + c * 8;
+      const float* g = sdc + c * 8;
+      uk.x = pack16(dkv_fmt, ds * qq[0], ds * qq[1]); uk.y = pack16(dkv_fmt, ds * qq[2], ds * qq[3]);
+      uk.z = pack16(dkv_fmt, ds * qq[4], ds * qq[5]); uk.w = pack16(dkv_fmt, ds * qq[6], ds * qq[7]);
+      uv.x = pack16(dkv_fmt, pj * g[0], pj * g[1]); uv.y = pack16(dkv_fmt, pj * g[2], pj * g[3]);
+      uv.z = pack16(dkv_fmt, pj * g[4], pj * g[5]); uv.w = pack16(dkv_fmt, pj * g[6], pj * g[7]);
+    }
+    *reinterpret_cast<uint4*>(dbase + (long long)j * kv_ld + k_off + c * 8) = uk;
+    *reinterpret_cast<uint4*>(dbase + (long long)j * kv_ld + v_off + c * 8) = uv;
+  }
+  // dq += sum_j ds_j k_j : a pair of dims per thread, keys split over thread groups
+  constexpr int P = HD / 2;
+  constexpr int G = P >= 128 ? 1 : 128 / P;
+  const int pr = tid % P, grp = tid / P;
+  float2 acc = make_float2(0.f, 0.f);
+  if (grp < G) {
+    const uint16_t* kr = base + k_off + pr * 2;
+#pragma unroll 4
+    for (int j = grp; j < len; j += G) {
+      const float2 kk = unpack16(kv_fmt, *reinterpret_cast<const uint32_t*>(kr + (long long)j * kv_ld));
+      const float ds = sds[j];
+      acc.x += ds * kk.x;
+      acc.y += ds * kk.y;
     }
   }
-#pragma unroll
-  for (int i = 0; i < PAIRS; ++i) {
-    const int d = 2 * lane + 64 * i;
-    if (d < HD) {
-      atomicAdd(&dq[h * HD + d], dqa[i].x);
-      atomicAdd(&dq[h * HD + d + 1], dqa[i].y);
+  part[tid * 2] = acc.x;
+  part[tid * 2 + 1] = acc.y;
+  __syncthreads();
+  if (tid < P) {
+    float2 r = make_float2(0.f, 0.f);
+    for (int g2 = 0; g2 < G; ++g2) {
+      r.x += part[(g2 * P + tid) * 2];
+      r.y += part[(g2 * P + tid) * 2 + 1];
     }
+    atomicAdd(&dq[h * HD + tid * 2], r.x);
+    atomicAdd(&dq[h * HD + tid * 2 + 1], r.y);
   }
 }
 
@@ -457,11 +549,12 @@ int cls_attention_fwd(const float* q, const void* kv, int kv_fmt, long long kv_l
                       int ctx16_fmt, cudaStream_t st) {
   SCB_CHECK(q && kv && probs && (ctx32 || ctx16), SCB_EINVAL, "scb_cls_attention_fwd: null operand");
   if (batch == 0) return SCB_OK;
-  const int warps = 4;
-  const size_t smem = (size_t)warps * Tk * sizeof(float);
+  const size_t smem = (size_t)(Tk + head_dim + 256 + 8) * sizeof(float);
   SCB_CHECK(smem <= 48 * 1024, SCB_EUNSUPPORTED, "scb_cls_attention_fwd: Tk=%d too long", Tk);
-  const unsigned grid = (unsigned)((batch * heads + warps - 1) / warps);
-  SCB_HD_SWITCH(head_dim, (cls_attention_fwd_kernel<HD_><<<grid, warps * 32, smem, st>>>(q, (const uint16_t*)kv, kv_fmt, kv_ld, kv_bs, k_off, v_off, kv_len, Tk, heads, scale, probs, ctx32, (uint16_t*)ctx16, ctx16_fmt, batch)));
+  SCB_CHECK(kv_ld % 8 == 0 && kv_bs % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0 && head_dim % 8 == 0, SCB_EINVAL,
+            "scb_cls_attention_fwd: kv strides / offsets / head_dim must be multiples of 8 elements");
+  const unsigned grid = (unsigned)(batch * heads);
+  SCB_HD_SWITCH(head_dim, (cls_attention_fwd_kernel<HD_><<<grid, 128, smem, st>>>(q, (const uint16_t*)kv, kv_fmt, kv_ld, kv_bs, k_off, v_off, kv_len, Tk, heads, scale, probs, ctx32, (uint16_t*)ctx16, ctx16_fmt, batch)));
   note_launch();
   SCB_LAUNCH_OK("cls_attention_fwd");
   return SCB_OK;
@@ -472,11 +565,12 @@ int cls_attention_bwd(const float* q, const void* kv, int kv_fmt, long long kv_l
                       void* dkv, int dkv_fmt, float* dq, cudaStream_t st) {
   SCB_CHECK(q && kv && probs && dctx && dkv && dq, SCB_EINVAL, "scb_cls_attention_bwd: null operand");
   if (batch == 0) return SCB_OK;
-  const int warps = 4;
-  const size_t smem = (size_t)warps * Tk * sizeof(float);
+  const size_t smem = (size_t)(2 * Tk + 2 * head_dim + 256 + 8) * sizeof(float);
   SCB_CHECK(smem <= 48 * 1024, SCB_EUNSUPPORTED, "scb_cls_attention_bwd: Tk=%d too long", Tk);
-  const unsigned grid = (unsigned)((batch * heads + warps - 1) / warps);
-  SCB_HD_SWITCH(head_dim, (cls_attention_bwd_kernel<HD_><<<grid, warps * 32, smem, st>>>(q, (const uint16_t*)kv, kv_fmt, kv_ld, kv_bs, k_off, v_off, kv_len, Tk, heads, scale, probs, dctx, (uint16_t*)dkv, dkv_fmt, dq, batch)));
+  SCB_CHECK(kv_ld % 8 == 0 && kv_bs % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0 && head_dim % 8 == 0, SCB_EINVAL,
+            "scb_cls_attention_bwd: kv strides / offsets / head_dim must be multiples of 8 elements");
+  const unsigned grid = (unsigned)(batch * heads);
+  SCB_HD_SWITCH(head_dim, (cls_attention_bwd_kernel<HD_><<<grid, 128, smem, st>>>(q, (const uint16_t*)kv, kv_fmt, kv_ld, kv_bs, k_off, v_off, kv_len, Tk, heads, scale, probs, dctx, (uint16_t*)dkv, dkv_fmt, dq, batch)));
   note_launch();
   SCB_LAUNCH_OK("cls_attention_bwd");
   return SCB_OK;

@@ -198,14 +198,27 @@ class ParallelHead:
         ops.sgemm(dq.view(d, 1), cls.view(d, 1), g_w[:d])            # dWq = dq (x) cls
         ops.sgemm(dq.view(1, d), w_in[:d].t(), dcls, beta=1.0)        # dcls += Wq^T dq
         ops.column_sum(dkv.view(M, 2 * d), g_b[d:])
-        # K/V projection: wgrad dWkv = dKV^T src, dgrad dsrc = dKV Wkv  (bf16 operands on the tensor cores)
-        ldt = _ceil8(M)
-        dkv_t = ws.view("head_dkv_t", (2 * d, ldt), BF)
-        src_t = ws.view("head_src_t", (d, ldt), BF)
+        # K/V projection: wgrad dWkv = dKV^T src, dgrad dsrc = dKV Wkv  (bf16 operands on the tensor cores).
+        # The wgrad contracts over all M = B*(T+1) rows into only 12 x 3 output tiles, so it is split NS ways along M
+        # (the GEMM's group dimension walks the M slices of both operands) into NS partial [2d, d] results that are summed.
+        NS = 4 if M >= 4096 else 1
+        kc = (M + NS * 64 - 1) // (NS * 64) * 64   # rows per split, multiple of the 64-wide k-block
+        ldt = NS * kc                               # padded row length: every split stays inside its own row
+        dkv_t = ws.view(f"head_dkv_t_{ldt}", (2 * d, ldt), BF, zero=True)
+        src_t = ws.view(f"head_src_t_{ldt}", (d, ldt), BF, zero=True)
         ops.transpose(dkv.view(M, 2 * d), dkv_t[:, :M])
         ops.transpose(s["src"].view(M, d), src_t[:, :M])
-        ops.gemm_raw(a=dkv_t, a_inner=M, a_rows=2 * d, a_row_stride=ldt, m_per_batch=2 * d, w=src_t, n=d, k=M, b_row_stride=ldt,
-                     out=g_w, out_offset=d * d, ldc=d)
+        if NS == 1:
+            ops.gemm_raw(a=dkv_t, a_inner=M, a_rows=2 * d, a_row_stride=ldt, m_per_batch=2 * d, w=src_t, n=d, k=M, b_row_stride=ldt,
+                         out=g_w, out_offset=d * d, ldc=d)
+        else:
+            parts = ws.view("head_wgrad_parts", (2 * d, NS * d), torch.float32)
+            ops.gemm_raw(a=dkv_t, a_inner=ldt, a_rows=2 * d, a_row_stride=ldt, m_per_batch=2 * d, w=src_t, n=d, k=kc, b_row_stride=ldt,
+                         groups=NS, a_group_cols=kc, b_group_stride=kc, out=parts, ldc=NS * d, out_group_cols=d)
+            acc = g_w[d:]
+            ops.rows_bias_act(parts[:, 0:d], None, parts[:, d:2 * d], NS * d, ops.ACT_NONE, None, acc, rows=2 * d, d=d, x_ld=NS * d, y_ld=d)
+            for i in range(2, NS):
+                ops.rows_bias_act(acc, None, parts[:, i * d:(i + 1) * d], NS * d, ops.ACT_NONE, None, acc, rows=2 * d, d=d, x_ld=d, y_ld=d)
         dsrc = None
         if need_dfeat:
             wkv_t = ws.view("head_wkv_t", (d, 2 * d), BF)
