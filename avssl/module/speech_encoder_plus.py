@@ -13,7 +13,7 @@ import torch
 from torch import nn
 from torch.nn.utils.rnn import pad_sequence
 
-from speechclip_b200 import ops
+from speechclip_b200 import engine, ops
 from speechclip_b200.engine import HubertPlan, conv_out_len
 from speechclip_b200.functional import workspace
 from speechclip_b200.init import seeded_init_
@@ -143,7 +143,7 @@ class FairseqSpeechEncoder_Hubert(nn.Module):
         if T < 1:
             raise ValueError(f"utterances of {tw} samples are shorter than HuBERT's receptive field (400 samples)")
         ws = workspace(dev)
-        ints = torch.empty(4, B, device=dev, dtype=torch.int32)
+        ints = ws.view("len_ints", (4, B), torch.int32)  # persistent: valid_frames' address is part of the tower's graph signature
         crop_off, crop_len, valid_frames, feat_len32 = ints[0], ints[1], ints[2], ints[3]
         feat_len = torch.empty(B, device=dev, dtype=torch.int64)
         u = torch.rand(B, device=dev) if crop else None  # random crop offset (audio_transforms.py:5-23)
@@ -156,9 +156,11 @@ class FairseqSpeechEncoder_Hubert(nn.Module):
             hidden, T = self.plan(dev).forward(ws, wav_p, valid_frames if lens is not None else None)
         d = self.out_dim
         slab = hidden.view(hidden.shape[0], B, T, d)
-
         if feat_select_idx is None:
             feat_select_idx = self.feat_select_idx
+        if engine.GRAPHS and (feat_select_idx != FEAT_SELECT_IDX_WEIGHTED_SUM_MODE or return_hidden_states):
+            slab = slab.clone()  # hidden states handed to the caller must survive the next forward (the plan reuses its buffers)
+
         states = lambda: tuple(slab[i] for i in range(slab.shape[0]))
         ret = []
         if feat_select_idx == "all":

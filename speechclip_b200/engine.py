@@ -20,6 +20,7 @@ residual streams / LayerNorm statistics / softmax.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -47,6 +48,61 @@ class Workspace:
 
     def view(self, name: str, shape, dtype, zero: bool = False) -> torch.Tensor:
         return self.get(name, int(math.prod(shape)), dtype, zero).view(*shape)
+
+
+GRAPHS = os.environ.get("SCB_CUDA_GRAPHS", "1") != "0"   # replay the frozen towers as CUDA graphs (launch-bound at small batch)
+MAX_GRAPHS = 4                                            # per plan; further input shapes run eagerly
+
+
+class GraphCache:
+    """Capture a frozen tower's kernel sequence once per input signature and replay it with one launch.
+
+    The towers are ~115 (HuBERT) / ~100 (ViT) dependent kernels whose launch parameters (TMA tensor maps included) only
+    depend on the input shape and on buffer addresses; python + ctypes spend ~30 us on each, which bounds a 32-pair step on
+    8 GPUs by the host.  ``run(key, fn)`` executes ``fn(workspace)`` eagerly the first time a signature is seen (this also
+    performs the one-off cudaFuncSetAttribute calls), captures it the second time into a graph with a PRIVATE workspace
+    (all scratch comes from the graph's memory pool, so addresses stay valid for the graph's lifetime) and replays
+    afterwards.  Outputs live in the graph's pool and are overwritten by the next replay.
+    """
+
+    def __init__(self, device):
+        self.device = device
+        self.entries: Dict[tuple, object] = {}
+        self.kernels_replayed = 0
+
+    def run(self, key: tuple, eager_ws: "Workspace", fn):
+        from . import lib as _l
+        if not GRAPHS or ops.PROFILE is not None:  # profiling wants one event pair per kernel: run eagerly
+            return fn(eager_ws)
+        ent = self.entries.get(key)
+        if ent is None:
+            if sum(1 for v in self.entries.values() if v != "warm") >= MAX_GRAPHS:
+                return fn(eager_ws)
+            self.entries[key] = "warm"
+            return fn(eager_ws)
+        if ent == "warm":
+            graph = torch.cuda.CUDAGraph()
+            ws = Workspace(self.device)
+            n0 = _l.launch_count()
+            prof, ops.PROFILE = ops.PROFILE, None  # per-call events cannot be recorded into a capture
+            try:
+                with torch.cuda.graph(graph):
+                    out = fn(ws)
+            finally:
+                ops.PROFILE = prof
+            ent = self.entries[key] = (graph, out, ws, _l.launch_count() - n0)
+        graph, out, _, n_kernels = ent
+        graph.replay()
+        self.kernels_replayed += n_kernels
+        return out
+
+
+def graph_replayed_kernels() -> int:
+    """Kernels executed through graph replays (they do not pass through the library's launch counter)."""
+    return sum(c.kernels_replayed for c in _ALL_CACHES)
+
+
+_ALL_CACHES: List[GraphCache] = []
 
 
 def _f32(t: torch.Tensor, dev) -> torch.Tensor:
@@ -169,6 +225,8 @@ class HubertPlan:
                 ln2=(g(p + "final_layer_norm.weight"), g(p + "final_layer_norm.bias")),
                 heads=heads, pre_ln=self.pre_ln, act=ops.ACT_GELU))
         self.n_hidden = n_layers + 1
+        self.graphs = GraphCache(dev)
+        _ALL_CACHES.append(self.graphs)
 
     # -------------------------------------------------------------------------------------------------
     def conv_stack(self, ws: Workspace, wav: torch.Tensor) -> Tuple[torch.Tensor, int]:
@@ -194,7 +252,12 @@ class HubertPlan:
         return cur, T
 
     def forward(self, ws: Workspace, wav: torch.Tensor, valid_frames: Optional[torch.Tensor]) -> Tuple[torch.Tensor, int]:
-        """-> (hidden fp32 [L+1, B*T, d] freshly allocated, T)."""
+        """-> (hidden fp32 [L+1, B*T, d], T).  ``wav`` / ``valid_frames`` must be persistent buffers (their addresses are part
+        of the graph signature); under graph replay ``hidden`` is overwritten by the next call with the same signature."""
+        key = (wav.data_ptr(), tuple(wav.shape), valid_frames.data_ptr() if valid_frames is not None else 0)
+        return self.graphs.run(key, ws, lambda w: self._forward(w, wav, valid_frames))
+
+    def _forward(self, ws: Workspace, wav: torch.Tensor, valid_frames: Optional[torch.Tensor]) -> Tuple[torch.Tensor, int]:
         B = wav.shape[0]
         d = self.d
         feats, T = self.conv_stack(ws, wav)
@@ -254,13 +317,22 @@ class VitPlan:
                 bo=g(p + "attn.out_proj.bias"), ln1=(g(p + "ln_1.weight"), g(p + "ln_1.bias")), w1=g(p + "mlp.c_fc.weight"),
                 b1=g(p + "mlp.c_fc.bias"), w2=g(p + "mlp.c_proj.weight"), b2=g(p + "mlp.c_proj.bias"),
                 ln2=(g(p + "ln_2.weight"), g(p + "ln_2.bias")), heads=heads, pre_ln=True, act=ops.ACT_QUICK_GELU))
+        self.graphs = GraphCache(dev)
+        _ALL_CACHES.append(self.graphs)
 
     def forward(self, ws: Workspace, image: torch.Tensor) -> torch.Tensor:
         """image fp32 [B, 3, S, S] -> un-normalised embedding fp32 [B, E] (ln_post(x[:,0]) @ proj)."""
         B = image.shape[0]
-        Wd, L, G2 = self.width, self.tokens, self.tokens - 1
-        patches = ws.view("vit_patches", (B * G2, self.ldk), H)
+        G2 = self.tokens - 1
+        patches = ws.view("vit_patches", (B * G2, self.ldk), H)  # persistent: the graph starts after the im2col of the caller's tensor
         ops.patchify(image, patches, self.patch, self.ldk)
+        out = self.graphs.run((patches.data_ptr(), B), ws, lambda w: self._forward(w, patches, B))
+        res = torch.empty_like(out)  # the graph's output slot is overwritten by the next replay: hand out a copy
+        ops.cast_rows(out, res)
+        return res
+
+    def _forward(self, ws: Workspace, patches: torch.Tensor, B: int) -> torch.Tensor:
+        Wd, L, G2 = self.width, self.tokens, self.tokens - 1
         xa = ws.view("vit_x0", (B * L, Wd), torch.float32)
         xb = ws.view("vit_x1", (B * L, Wd), torch.float32)
         ops.gemm_raw(a=patches, a_inner=self.ldk, a_rows=G2, a_row_stride=self.ldk, a_batch_stride=G2 * self.ldk, batch=B,
