@@ -85,44 +85,94 @@ __global__ void conv0_finalize_kernel(const double* __restrict__ acc, const floa
 }
 
 // out[b, t, c] = gelu(conv0(wav)[b, c, t] * scale[b,c] + shift[b,c])   channel-last, 16-bit.
-// Block = 64 frames x 512 channels; thread owns channel pair (2*tid, 2*tid+1).
-constexpr int kFramesPerBlock = 64;
+// The 10-tap convolution runs on the tensor cores (mma.sync m16n8k16, fp16 operands like the reference's autocast conv1d,
+// fp32 accumulate): A = 16 frames x 16 "taps" (10 waveform samples, then two constant-1 columns, then zeros), B = the
+// channel's 10 weights pre-multiplied by the GroupNorm scale plus the GroupNorm shift split into an fp16 hi/lo pair on the two
+// constant columns — so the accumulator IS scale*conv + shift and the epilogue is only GELU + pack + store.  That leaves
+// ~16 instructions per output element instead of ~32 on the fp32 SIMT path (the kernel evaluates 2.7 G activations per step).
+// Block = 8 warps = 2 frame halves x 4 channel groups of 128; a warp keeps its 16 B-fragments (128 channels) in registers
+// and walks frame tiles of 16.  The fragment column -> channel map is chosen so that every lane ends up with 32 CONTIGUOUS
+// channels of a frame (64 bytes): column j of n-block n is channel (j/2)*32 + n*2 + (j%2).
+constexpr int kFramesPerBlock = 128;
 __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restrict__ wav, long long wav_ld, const float* __restrict__ w,
                                                           const float2* __restrict__ scale_shift, void* __restrict__ out, int out_fmt,
                                                           int n_frames, long long out_batch_stride, int channels) {
-  __shared__ float xs[kFramesPerBlock * kStride + kTaps];
+  __shared__ float xs[kFramesPerBlock * kStride + kTaps + 6];
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * kFramesPerBlock;
   const int nt = min(kFramesPerBlock, n_frames - t0);
   const int nsamp = (nt - 1) * kStride + kTaps;
   const float* x = wav + (long long)b * wav_ld + (long long)t0 * kStride;
-  for (int i = threadIdx.x; i < nsamp; i += blockDim.x) xs[i] = __ldg(x + i);
-  __syncthreads();
-  for (int cp = threadIdx.x; cp * 2 < channels; cp += blockDim.x) {
-    const int c = cp * 2;
-    float w0[kTaps], w1[kTaps];
+  for (int i = threadIdx.x; i < kFramesPerBlock * kStride + kTaps + 6; i += blockDim.x) xs[i] = i < nsamp ? __ldg(x + i) : 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int cgrp = warp & 3, fhalf = warp >> 2;
+  const bool bf = out_fmt == SCB_BF16;
+  // ---- B fragments: 16 n-blocks x {taps t4*2, t4*2+1 | taps t4*2+8, t4*2+9} of channel ch(nb, g)
+  uint32_t bfrag[16][2];
 #pragma unroll
-    for (int k = 0; k < kTaps; ++k) {
-      w0[k] = __ldg(w + c * kTaps + k);
-      w1[k] = __ldg(w + (c + 1) * kTaps + k);
+  for (int nb = 0; nb < 16; ++nb) {
+    const int ch = cgrp * 128 + (g >> 1) * 32 + nb * 2 + (g & 1);
+    const float2 ss = scale_shift[(long long)b * channels + ch];
+    const float* wc = w + ch * kTaps;
+    bfrag[nb][0] = H16<SCB_F16>::pack(wc[t4 * 2] * ss.x, wc[t4 * 2 + 1] * ss.x);
+    if (t4 == 0) {
+      bfrag[nb][1] = H16<SCB_F16>::pack(wc[8] * ss.x, wc[9] * ss.x);
+    } else if (t4 == 1) {
+      const float hi = __half2float(__float2half_rn(ss.y));
+      bfrag[nb][1] = H16<SCB_F16>::pack(hi, ss.y - hi);  // shift = hi + lo on the two constant-1 columns
+    } else {
+      bfrag[nb][1] = 0u;
     }
-    const float2 ss0 = scale_shift[(long long)b * channels + c], ss1 = scale_shift[(long long)b * channels + c + 1];
-    uint32_t* o = reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(out) + (long long)b * out_batch_stride + (long long)t0 * channels + c);
-    for (int t = 0; t < nt; ++t) {
-      float a0 = 0.f, a1 = 0.f;
+  }
+  __syncthreads();
+  uint16_t* obase = reinterpret_cast<uint16_t*>(out) + (long long)b * out_batch_stride + (long long)t0 * channels + cgrp * 128 + t4 * 32;
+  for (int ft = fhalf; ft * 16 < nt; ft += 2) {
+    const int f0 = ft * 16;
+    // ---- A fragment: rows g / g+8 of the tile, columns (t4*2, +1) and (t4*2+8, +9)
+    const float* xa = xs + (f0 + g) * kStride + t4 * 2;
+    const float* xb = xa + 8 * kStride;
+    uint32_t a[4];
+    a[0] = H16<SCB_F16>::pack(xa[0], xa[1]);
+    a[1] = H16<SCB_F16>::pack(xb[0], xb[1]);
+    if (t4 == 0) {
+      a[2] = H16<SCB_F16>::pack(xa[8], xa[9]);
+      a[3] = H16<SCB_F16>::pack(xb[8], xb[9]);
+    } else if (t4 == 1) {
+      a[2] = a[3] = 0x3C003C00u;  // (1.0, 1.0)
+    } else {
+      a[2] = a[3] = 0u;
+    }
+    const bool ok_a = f0 + g < nt, ok_b = f0 + g + 8 < nt;
+    uint16_t* oa = obase + (long long)(f0 + g) * channels;
+    uint16_t* ob = oa + 8LL * channels;
 #pragma unroll
-      for (int k = 0; k < kTaps; ++k) {
-        const float xv = xs[t * kStride + k];
-        a0 = fmaf(w0[k], xv, a0);
-        a1 = fmaf(w1[k], xv, a1);
+    for (int q4 = 0; q4 < 4; ++q4) {  // 4 n-blocks -> 8 channels (16 bytes) per row
+      float c[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[j][0]), "+f"(c[j][1]), "+f"(c[j][2]), "+f"(c[j][3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(bfrag[q4 * 4 + j][0]), "r"(bfrag[q4 * 4 + j][1]));
       }
-      a0 = gelu_fast(fmaf(a0, ss0.x, ss0.y));
-      a1 = gelu_fast(fmaf(a1, ss1.x, ss1.y));
-      o[(long long)t * (channels / 2)] = pack16(out_fmt, a0, a1);
+      uint4 ua, ub;
+      if (bf) {
+        ua.x = H16<SCB_BF16>::pack(gelu_fast(c[0][0]), gelu_fast(c[0][1])); ua.y = H16<SCB_BF16>::pack(gelu_fast(c[1][0]), gelu_fast(c[1][1]));
+        ua.z = H16<SCB_BF16>::pack(gelu_fast(c[2][0]), gelu_fast(c[2][1])); ua.w = H16<SCB_BF16>::pack(gelu_fast(c[3][0]), gelu_fast(c[3][1]));
+        ub.x = H16<SCB_BF16>::pack(gelu_fast(c[0][2]), gelu_fast(c[0][3])); ub.y = H16<SCB_BF16>::pack(gelu_fast(c[1][2]), gelu_fast(c[1][3]));
+        ub.z = H16<SCB_BF16>::pack(gelu_fast(c[2][2]), gelu_fast(c[2][3])); ub.w = H16<SCB_BF16>::pack(gelu_fast(c[3][2]), gelu_fast(c[3][3]));
+      } else {
+        ua.x = H16<SCB_F16>::pack(gelu_fast(c[0][0]), gelu_fast(c[0][1])); ua.y = H16<SCB_F16>::pack(gelu_fast(c[1][0]), gelu_fast(c[1][1]));
+        ua.z = H16<SCB_F16>::pack(gelu_fast(c[2][0]), gelu_fast(c[2][1])); ua.w = H16<SCB_F16>::pack(gelu_fast(c[3][0]), gelu_fast(c[3][1]));
+        ub.x = H16<SCB_F16>::pack(gelu_fast(c[0][2]), gelu_fast(c[0][3])); ub.y = H16<SCB_F16>::pack(gelu_fast(c[1][2]), gelu_fast(c[1][3]));
+        ub.z = H16<SCB_F16>::pack(gelu_fast(c[2][2]), gelu_fast(c[2][3])); ub.w = H16<SCB_F16>::pack(gelu_fast(c[3][2]), gelu_fast(c[3][3]));
+      }
+      if (ok_a) *reinterpret_cast<uint4*>(oa + q4 * 8) = ua;
+      if (ok_b) *reinterpret_cast<uint4*>(ob + q4 * 8) = ub;
     }
   }
 }
-
 
 // HuBERT-large conv0 block: conv (C_in = 1) -> LayerNorm over the 512 channels of each frame (affine, fp32) -> GELU.
 // One warp per frame; lane owns channels {lane*4 + 128*i .. +3}, i < 4 (coalesced 8-byte 16-bit stores).
