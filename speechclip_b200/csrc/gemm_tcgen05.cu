@@ -7,6 +7,8 @@
 //
 // The two TMEM accumulator buffers let the epilogue of tile i overlap the MMAs of tile i+1.
 // See include/speechclip_b200.h (scb_gemm) for the operand model (plain / strided-conv / grouped tap walk).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ops.cuh"
 
@@ -67,6 +69,108 @@ __device__ __forceinline__ void store4(void* base, int dtype, long long off, con
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off) = make_float4(x[0], x[1], x[2], x[3]);
   } else {
     *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(base) + off) = make_uint2(pack16(dtype, x[0], x[1]), pack16(dtype, x[2], x[3]));
+  }
+}
+
+// One output tile of the epilogue, executed by every epilogue warp of a CTA.  tfull_bar: the CTA-local "accumulator ready"
+// barrier; tempty_addr: shared::cluster address of the "accumulator drained" barrier of the CTA that issues the MMAs (the CTA
+// itself, or the pair leader in cta_group::2 mode).
+//
+// tcgen05.ld (32x32b) hands each lane one ROW of the accumulator.  Writing global memory in that layout costs one LSU
+// wavefront per lane per instruction (32 different cache lines): measured 20 us per 128x256 fp32+residual tile against
+// 3.5 us of MMA.  So every 32x16 chunk is transposed through a private, XOR-swizzled (bank-conflict-free) 2 KB shared
+// patch: afterwards 4 lanes cover one 64-byte row segment and a warp instruction touches 8 rows instead of 32.  The
+// residual loads of a chunk are issued before the TMEM load (out may alias residual, so the compiler cannot hoist them).
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoord& t, uint32_t tmem_base, int acc, uint32_t acc_phase,
+                                              uint64_t* tfull_bar, uint32_t tempty_addr, float* stage, int warp, int lane) {
+  constexpr int COLS = EpiCfg<BN>::COLS;
+  const int q = warp & 3;            // TMEM lane quarter this warp may touch
+  const int part = (warp - 4) >> 2;  // which slice of the tile's columns
+  float4* stg = reinterpret_cast<float4*>(stage + (warp - 4) * (32 * 16));
+  const int prow = lane >> 2, u = lane & 3;  // after the transpose: row (within a pass of 8) and 4-column unit of this lane
+  {
+      const int m_base = t.m0 + q * 32;
+      const int col_base = t.n0 + part * COLS;
+      const long long gcol = (long long)t.g * p.out_group_cols;
+      const long long out_base = (long long)t.b * p.out_batch_stride + (long long)m_base * p.ldc + gcol;
+      const long long res_base = (long long)t.b * p.res_batch_stride + (long long)m_base * p.res_ld + gcol;
+      int nchunks = 0;
+      if (col_base < p.n && m_base < p.m_per_batch) nchunks = min(COLS / 16, (p.n - col_base + 15) / 16);
+      mbar_wait(tfull_bar, acc_phase);
+      tc_fence_after();
+      if (nchunks == 0) {
+        tc_fence_before();
+        if (lane == 0) mbar_arrive_cluster(tempty_addr);
+      }
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int col = col_base + ch * 16 + u * 4;  // first of this lane's 4 columns
+        const bool col_ok = col < p.n;               // n % 8 == 0: a 4-column unit is entirely inside or outside
+        // ---- residual + bias: everything this chunk needs from global memory, in flight at once
+        uint4 rr[4];
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok) {
+          if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol + col));
+          if (p.residual) {
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+              const int r = ps * 8 + prow;
+              if (m_base + r < p.m_per_batch) {
+                const long long off = res_base + (long long)r * p.res_ld + col;
+                if (p.residual_dtype == SCB_F32) {
+                  rr[ps] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.residual) + off));
+                } else {
+                  const uint2 h2 = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.residual) + off));
+                  rr[ps] = make_uint4(h2.x, h2.y, 0u, 0u);
+                }
+              }
+            }
+          }
+        }
+        uint32_t v[16];
+        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + part * COLS + ch * 16), v);
+        tmem_ld_wait();
+        if (ch == nchunks - 1) {  // accumulator fully read by this warp: hand the buffer back to the MMA warp
+          tc_fence_before();
+          if (lane == 0) mbar_arrive_cluster(tempty_addr);
+        }
+        __syncwarp();  // the previous chunk's reads of the patch are done
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // row = lane; 16-byte unit k lands at k ^ ((lane >> 1) & 3): conflict-free both ways
+          stg[lane * 4 + (k ^ ((lane >> 1) & 3))] = make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]),
+                                                               __uint_as_float(v[4 * k + 2]), __uint_as_float(v[4 * k + 3]));
+        __syncwarp();
+        if (col_ok) {
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) {
+            const int r = ps * 8 + prow;
+            if (m_base + r < p.m_per_batch) {
+              const float4 a = stg[r * 4 + (u ^ ((r >> 1) & 3))];
+              float x[4] = {fmaf(p.alpha, a.x, bias4.x), fmaf(p.alpha, a.y, bias4.y), fmaf(p.alpha, a.z, bias4.z),
+                            fmaf(p.alpha, a.w, bias4.w)};
+              if (p.act == SCB_ACT_GELU_ERF) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) x[i] = gelu_fast(x[i]);
+              } else if (p.act == SCB_ACT_QUICK_GELU) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) x[i] = quick_gelu(x[i]);
+              }
+              if (p.residual) {
+                if (p.residual_dtype == SCB_F32) {
+                  x[0] += __uint_as_float(rr[ps].x); x[1] += __uint_as_float(rr[ps].y);
+                  x[2] += __uint_as_float(rr[ps].z); x[3] += __uint_as_float(rr[ps].w);
+                } else {
+                  const float2 f0 = unpack16(p.residual_dtype, rr[ps].x), f1 = unpack16(p.residual_dtype, rr[ps].y);
+                  x[0] += f0.x; x[1] += f0.y; x[2] += f1.x; x[3] += f1.y;
+                }
+              }
+              const long long off = out_base + (long long)r * p.ldc + col;
+              store4(p.out, p.out_dtype, off, x);
+              if (p.out2) store4(p.out2, p.out2_dtype, off, x);
+            }
+          }
+        }
+      }
   }
 }
 
@@ -229,102 +333,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (acc == 0) acc_phase ^= 1u;
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue
-    // tcgen05.ld (32x32b) hands each lane one ROW of the accumulator.  Writing global memory in that layout costs one LSU
-    // wavefront per lane per instruction (32 different cache lines): measured 20 us per 128x256 fp32+residual tile against
-    // 3.5 us of MMA.  So every 32x16 chunk is transposed through a private, XOR-swizzled (bank-conflict-free) 2 KB shared
-    // patch: afterwards 4 lanes cover one 64-byte row segment and a warp instruction touches 8 rows instead of 32.  The
-    // residual loads of a chunk are issued before the TMEM load (out may alias residual, so the compiler cannot hoist them).
-    constexpr int COLS = EpiCfg<BN>::COLS;
-    const int q = warp & 3;            // TMEM lane quarter this warp may touch
-    const int part = (warp - 4) >> 2;  // which slice of the tile's columns
-    float4* stg = reinterpret_cast<float4*>(stage + (warp - 4) * (32 * 16));
-    const int prow = lane >> 2, u = lane & 3;  // after the transpose: row (within a pass of 8) and 4-column unit of this lane
+    // ------------------------------------------------------------------ epilogue (see epilogue_tile)
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile<BN>(p, tile);
-      const int m_base = t.m0 + q * 32;
-      const int col_base = t.n0 + part * COLS;
-      const long long gcol = (long long)t.g * p.out_group_cols;
-      const long long out_base = (long long)t.b * p.out_batch_stride + (long long)m_base * p.ldc + gcol;
-      const long long res_base = (long long)t.b * p.res_batch_stride + (long long)m_base * p.res_ld + gcol;
-      int nchunks = 0;
-      if (col_base < p.n && m_base < p.m_per_batch) nchunks = min(COLS / 16, (p.n - col_base + 15) / 16);
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
-      if (nchunks == 0) {
-        tc_fence_before();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
-      }
-      for (int ch = 0; ch < nchunks; ++ch) {
-        const int col = col_base + ch * 16 + u * 4;  // first of this lane's 4 columns
-        const bool col_ok = col < p.n;               // n % 8 == 0: a 4-column unit is entirely inside or outside
-        // ---- residual + bias: everything this chunk needs from global memory, in flight at once
-        uint4 rr[4];
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (col_ok) {
-          if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol + col));
-          if (p.residual) {
-#pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
-              const int r = ps * 8 + prow;
-              if (m_base + r < p.m_per_batch) {
-                const long long off = res_base + (long long)r * p.res_ld + col;
-                if (p.residual_dtype == SCB_F32) {
-                  rr[ps] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.residual) + off));
-                } else {
-                  const uint2 h2 = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.residual) + off));
-                  rr[ps] = make_uint4(h2.x, h2.y, 0u, 0u);
-                }
-              }
-            }
-          }
-        }
-        uint32_t v[16];
-        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + part * COLS + ch * 16), v);
-        tmem_ld_wait();
-        if (ch == nchunks - 1) {  // accumulator fully read by this warp: hand the buffer back to the MMA warp
-          tc_fence_before();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
-        }
-        __syncwarp();  // the previous chunk's reads of the patch are done
-#pragma unroll
-        for (int k = 0; k < 4; ++k)  // row = lane; 16-byte unit k lands at k ^ ((lane >> 1) & 3): conflict-free both ways
-          stg[lane * 4 + (k ^ ((lane >> 1) & 3))] = make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]),
-                                                               __uint_as_float(v[4 * k + 2]), __uint_as_float(v[4 * k + 3]));
-        __syncwarp();
-        if (col_ok) {
-#pragma unroll
-          for (int ps = 0; ps < 4; ++ps) {
-            const int r = ps * 8 + prow;
-            if (m_base + r < p.m_per_batch) {
-              const float4 a = stg[r * 4 + (u ^ ((r >> 1) & 3))];
-              float x[4] = {fmaf(p.alpha, a.x, bias4.x), fmaf(p.alpha, a.y, bias4.y), fmaf(p.alpha, a.z, bias4.z),
-                            fmaf(p.alpha, a.w, bias4.w)};
-              if (p.act == SCB_ACT_GELU_ERF) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) x[i] = gelu_fast(x[i]);
-              } else if (p.act == SCB_ACT_QUICK_GELU) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) x[i] = quick_gelu(x[i]);
-              }
-              if (p.residual) {
-                if (p.residual_dtype == SCB_F32) {
-                  x[0] += __uint_as_float(rr[ps].x); x[1] += __uint_as_float(rr[ps].y);
-                  x[2] += __uint_as_float(rr[ps].z); x[3] += __uint_as_float(rr[ps].w);
-                } else {
-                  const float2 f0 = unpack16(p.residual_dtype, rr[ps].x), f1 = unpack16(p.residual_dtype, rr[ps].y);
-                  x[0] += f0.x; x[1] += f0.y; x[2] += f1.x; x[3] += f1.y;
-                }
-              }
-              const long long off = out_base + (long long)r * p.ldc + col;
-              store4(p.out, p.out_dtype, off, x);
-              if (p.out2) store4(p.out2, p.out2_dtype, off, x);
-            }
-          }
-        }
-      }
+      epilogue_tile<BN>(p, t, tmem_base, acc, acc_phase, &tfull[acc], smem_u32(&tempty[acc]), stage, warp, lane);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -336,6 +350,164 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_after();
     tmem_dealloc<2 * BN>(tmem_base);
   }
+}
+
+// ------------------------------------------------------------------------------------------------ cta_group::2 variant
+// A CTA pair (one cluster of 2 on a TPC) computes a 256 x 256 output tile: each CTA stages its own 128 A rows and HALF of the
+// B tile (128 of the 256 N rows) per k-block, the leader issues tcgen05.mma.cta_group::2 (M = 256 across the pair, both CTAs'
+// B halves are read by the pair's tensor cores), and each CTA's TMEM receives its 128 x 256 accumulator.  Per output tile the
+// pair pulls (128 + 128) x 64 operand elements per CTA instead of (128 + 256): a third less L2 -> SM traffic per flop (the
+// 1-CTA kernel saturates at ~1.1 PFLOP/s on the big shapes), and the 32 KB stages make the TMA ring 6 deep instead of 4.
+//   full[s]   (leader)  : 1 arrival (leader's expect_tx) + 64 KB of transaction bytes from BOTH CTAs' TMA loads
+//   empty[s]  (each CTA): tcgen05.commit multicast from the leader -> that CTA's producer may refill the stage
+//   tfull[a]  (each CTA): tcgen05.commit multicast -> that CTA's epilogue may read its accumulator half
+//   tempty[a] (leader)  : 2 x 16 epilogue warps (local + remote arrivals) -> the leader may overwrite the accumulators
+constexpr int kStages2 = 6;
+constexpr int BN2 = 256;
+
+__device__ __forceinline__ TileCoord decode_tile2(const GemmParams& p, int tile, int rank) {
+  TileCoord t;
+  const int nt = tile % p.n_tiles;
+  int rest = tile / p.n_tiles;
+  const int mt = rest % p.m_tiles_per_batch;  // 256-row super tiles
+  rest /= p.m_tiles_per_batch;
+  t.b = rest % p.batch;
+  t.g = rest / p.batch;
+  t.m0 = mt * 256 + rank * BM;
+  t.n0 = nt * BN2;
+  return t;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<BN2>::THREADS, 1)
+gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  constexpr int A_BYTES = BM * BK * 2;
+  constexpr int B_BYTES = (BN2 / 2) * BK * 2;
+  constexpr int STAGES = kStages2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* stage = reinterpret_cast<float*>(sB + STAGES * B_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 2 * EpiCfg<BN2>::WARPS);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc_2sm<2 * BN2>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / cross-CTA TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    int stage_i = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < p.num_tiles; tile += num_pairs) {
+      const TileCoord t = decode_tile2(p, tile, (int)rank);
+      const int a_c0 = p.a_col0 + t.g * p.a_group_cols;
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(&empty[stage_i], phase ^ 1u);
+        const uint32_t full_leader = mapa_u32(smem_u32(&full[stage_i]), 0);
+        if (leader) mbar_expect_tx(&full[stage_i], 2u * (uint32_t)(A_BYTES + B_BYTES));
+        const int tap = kb / p.kb_per_tap;
+        const int kin = kb - tap * p.kb_per_tap;
+        tma_load_3d_2sm(sA + stage_i * A_BYTES, &tmA, full_leader, a_c0 + kin * p.bk, t.m0 + tap * p.tap_row_shift, t.b);
+        tma_load_3d_2sm(sB + stage_i * B_BYTES, &tmB, full_leader, kb * p.bk, t.n0 + (int)rank * (BN2 / 2), t.g);
+        if (++stage_i == STAGES) {
+          stage_i = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    const uint32_t idesc = umma_idesc_f16(256, BN2, p.ab_fmt);
+    const bool tf32 = p.ab_fmt == 2;
+    int stage_i = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < p.num_tiles; tile += num_pairs) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN2);
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(&full[stage_i], phase);
+        tc_fence_after();
+        const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(sA + stage_i * A_BYTES));
+        const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(sB + stage_i * B_BYTES));
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          if (tf32) tc_mma_tf32_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          else tc_mma_f16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+        }
+        tc_commit_2sm(&empty[stage_i], 3);
+        if (++stage_i == STAGES) {
+          stage_i = 0;
+          phase ^= 1u;
+        }
+      }
+      tc_commit_2sm(&tfull[acc], 3);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (both CTAs; drains report to the leader)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < p.num_tiles; tile += num_pairs) {
+      const TileCoord t = decode_tile2(p, tile, (int)rank);
+      epilogue_tile<BN2>(p, t, tmem_base, acc, acc_phase, &tfull[acc], mapa_u32(smem_u32(&tempty[acc]), 0), stage, warp, lane);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer may still signal this CTA's barriers / read its shared memory until here
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm<2 * BN2>(tmem_base);
+  }
+}
+
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  constexpr int smem_bytes = kStages2 * (BM * BK * 2 + (BN2 / 2) * BK * 2) + 1024 + 256 + EpiCfg<BN2>::WARPS * 32 * 16 * 4;
+  static_assert(smem_bytes <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
+  static bool configured = false;
+  if (!configured) {
+    SCB_CUDA(cudaFuncSetAttribute(gemm2_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured = true;
+  }
+  int pairs = num_sms() / 2;
+  if (p.num_tiles < pairs) pairs = p.num_tiles;
+  gemm2_tcgen05_kernel<<<2 * pairs, EpiCfg<BN2>::THREADS, smem_bytes, stream>>>(tmA, tmB, p);
+  note_launch();
+  SCB_LAUNCH_OK("gemm2_tcgen05");
+  return SCB_OK;
 }
 
 template <int BN, int STAGES>
@@ -376,9 +548,14 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
   SCB_CHECK(a.groups == 1 || a.out_group_cols >= a.n, SCB_EINVAL, "scb_gemm: out_group_cols < n");
 
   const int bn = a.n > 128 ? 256 : (a.n > 64 ? 128 : 64);
+  // CTA pairs (256 x 256 tiles) for the large shapes; SCB_GEMM_2CTA=0 keeps every problem on the single-CTA kernel
+  static const int two_env = [] { const char* e = getenv("SCB_GEMM_2CTA"); return e ? atoi(e) : 1; }();
+  // (the tap-walk conv GEMMs measured 7 % faster on single CTAs, the plain linears 2-3 % faster on pairs)
+  const bool two = two_env != 0 && bn == 256 && a.m_per_batch >= 256 && a.tap_row_shift == 0 &&
+                   (long long)a.batch * a.groups * ((a.m_per_batch + 255) / 256) * ((a.n + 255) / 256) >= num_sms() / 2;
   GemmParams p{};
   p.batch = a.batch;
-  p.m_tiles_per_batch = (a.m_per_batch + BM - 1) / BM;
+  p.m_tiles_per_batch = two ? (a.m_per_batch + 255) / 256 : (a.m_per_batch + BM - 1) / BM;
   p.n_tiles = (a.n + bn - 1) / bn;
   p.groups = a.groups;
   p.num_tiles = p.groups * p.batch * p.m_tiles_per_batch * p.n_tiles;
@@ -390,8 +567,8 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
   p.tap_row_shift = a.tap_row_shift;
   p.a_col0 = a.a_col0;
   p.a_group_cols = a.a_group_cols;
-  p.umma_n = ((a.n < bn ? a.n : bn) + 15) / 16 * 16;
-  p.slab = (eb == 2 && bn == 64 && a.kb_per_tap == 1 && a.tap_row_shift == 1 && p.k_blocks + BM - 1 <= 256) ? 1 : 0;
+  p.umma_n = two ? 128 : ((a.n < bn ? a.n : bn) + 15) / 16 * 16;  // rows of the B box (cta_group::2: half of the 256-wide tile per CTA)
+  p.slab = (!two && eb == 2 && bn == 64 && a.kb_per_tap == 1 && a.tap_row_shift == 1 && p.k_blocks + BM - 1 <= 256) ? 1 : 0;
   p.slab_sub_bytes = p.umma_n * BK * 2;  // 48 x 128 B = 6 KB (base) / 8 KB (large): multiples of the 1024-byte swizzle atom
   if (p.slab && p.slab_sub_bytes % 1024 != 0) p.slab = 0;
   p.slab_stages = 8;
@@ -432,6 +609,7 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
     int e = make_tmap(&tmB, a.b, eb, 3, dims, strides, box, 1);
     if (e) return e;
   }
+  if (two) return launch2(tmA, tmB, p, stream);
   if (bn == 256) return launch<256, 4>(tmA, tmB, p, stream);
   if (bn == 128) return launch<128, 6>(tmA, tmB, p, stream);
   return launch<64, 8>(tmA, tmB, p, stream);
