@@ -190,7 +190,7 @@ def run_own(args):
     use_graphs = args.graphs == "on" or (args.graphs == "auto" and per_gpu < 256)
     engine.GRAPHS = use_graphs
 
-    cfg = parallel_config("base")
+    cfg = parallel_config(args.config)
     model = KWClip_GeneralTransformer(OrderedNamespace(cfg)).to(dev)
     model.train()
     opts, scheds = model.configure_optimizers()
@@ -299,6 +299,7 @@ def run_own(args):
             for shp, (ms, fl, n) in sorted(shapes.items(), key=lambda kv: -kv[1][0]):
                 f.write(f"{ms / prof_steps:.4f},{n / prof_steps:.1f},{fl / (ms * 1e-3) / 1e12 if ms > 0 else 0:.1f},{shp}\n")
     pk = peaks()
+    gf_step = GF_PER_PAIR_STEP if args.config == "base" else 427.2  # dense algorithmic GFLOP per pair per step
     g = agg.get("scb_gemm", [0.0, 0.0, 0])
     gemm_ms, gemm_flops, gemm_n = g
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
@@ -316,7 +317,8 @@ def run_own(args):
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f16",
         "data": "synthetic",
-        "config": {"workload": "Parallel SpeechCLIP-base (HuBERT-base + CLIP ViT-B/32) training step, batch 256, 102400-sample utterances",
+        "config": {"workload": ("Parallel SpeechCLIP-base (HuBERT-base + CLIP ViT-B/32)" if args.config == "base" else
+                                "Parallel SpeechCLIP-large (HuBERT-large + CLIP ViT-L/14)") + " training step, batch 256, 102400-sample utterances",
                    "global_batch": global_batch, "pairs_per_gpu": per_gpu, "frames": 319, "parallelism": f"dp{world}",
                    "mode": "training step, eval-mode arithmetic (dropout p=0), frozen towers, trainable branch 7.48 M params",
                    "l2": "inputs (259 MB) and activations (GBs) larger than the 126 MB L2; no flush needed",
@@ -330,8 +332,8 @@ def run_own(args):
                      "launches_per_step": gemm_n / prof_steps, "gemm_ms_per_step": gemm_ms / prof_steps,
                      "gemm_share_of_step": gemm_ms / prof_steps / ms_step,
                      "events": "per C-ABI call inside the timed steps" if not use_graphs else "one eager instrumented step after the timed region (towers replay as CUDA graphs inside it)",
-                     "step_tflops_dense_algorithmic": value / world * GF_PER_PAIR_STEP / 1e3,
-                     "step_frac_of_peak": value / world * GF_PER_PAIR_STEP / 1e3 / pk["tflops"]},
+                     "step_tflops_dense_algorithmic": value / world * gf_step / 1e3,
+                     "step_frac_of_peak": value / world * gf_step / 1e3 / pk["tflops"]},
         "breakdown_ms_per_step": breakdown,
         "clocks": clocks,
     }
@@ -364,6 +366,8 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--batch", type=int, default=0, help="pairs per GPU (default: 256 / N strong, 256 weak)")
+    ap.add_argument("--config", default="base", choices=["base", "large"],
+                    help="base = BASELINE.json configs[1] (headline); large = HuBERT-large + ViT-L/14 (configs[3])")
     ap.add_argument("--graphs", default="auto", choices=["auto", "on", "off"], help="replay the frozen towers as CUDA graphs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-profile", default="", help="write the per-GEMM-shape timing table (CSV) here")

@@ -79,6 +79,23 @@ def test_hubert_base_full_size_one_utterance():
         assert rel_err(a.cpu(), b) < 1.5e-2, (i, rel_err(a.cpu(), b))
 
 
+def test_hubert_large_full_size_one_utterance():
+    """Full-size HuBERT-large structure (LayerNorm extractor, pre-LN, d=1024, 24 layers, 16 heads, pos-conv 16 x 64, waveform
+    normalisation), two utterances of different length."""
+    from oracle import hubert as oh
+    enc, om = _hubert_pair("hubert_large_ll60k")
+    g = torch.Generator().manual_seed(6)
+    wavs = [0.1 * torch.randn(n, generator=g) for n in (24000, 17000)]
+    states, feat_len = enc([w.to(DEV) for w in wavs])
+    with torch.no_grad():
+        out = om.custom_forward(*oh.preprocess_input(wavs, True))
+    ref, valid = out["layer_results"], ~out["frame_pad"]
+    assert len(states) == 25 and states[0].shape == (2, 74, 1024)
+    for i, (a, b) in enumerate(zip(states, ref)):
+        e = rel_err(a.cpu()[valid], b[valid])
+        assert e < 2e-2, (i, e)
+
+
 def test_hubert_weighted_sum_and_training_crop():
     from avssl.module import FairseqSpeechEncoder_Hubert
     enc = FairseqSpeechEncoder_Hubert("tiny", feat_select_idx="weighted_sum", max_audio_len=4000).to(DEV)
@@ -92,7 +109,7 @@ def test_hubert_weighted_sum_and_training_crop():
     assert feat_e.shape[1] == 27  # eval mode never crops
 
 
-@pytest.mark.parametrize("name,size", [("tiny", 32), ("ViT-B/32", 224)])
+@pytest.mark.parametrize("name,size", [("tiny", 32), ("ViT-B/32", 224), ("ViT-L/14", 224)])
 def test_clip_vit_matches_oracle(name, size):
     from avssl.module import ClipModel
     from oracle import clip as oc
