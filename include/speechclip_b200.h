@@ -204,7 +204,7 @@ int scb_column_sum(const void* in, int32_t in_dtype, int64_t ld, int64_t rows, i
  * s = upstream * (upstream_dev ? *upstream_dev : 1) — upstream_dev is autograd's incoming dloss on the device (no host sync).
  * logits_out nullable [B][B].
  * ---------------------------------------------------------------------------------------------- */
-int64_t scb_infonce_scratch_bytes(int32_t B);
+int64_t scb_infonce_scratch_bytes(int32_t B); /* enough for any D <= 1024 */
 int scb_infonce(const float* feat_a, const float* feat_b, const int64_t* ids, int32_t B, int32_t D, const float* log_mult, float fixed_mult,
                 float margin, int32_t dcl, int32_t a2b, int32_t b2a, int32_t phase, float* loss, float* logits_out, float upstream,
                 const float* upstream_dev, float* dA, float* dB, float* dlog_mult, void* scratch, int64_t scratch_bytes, void* stream);

@@ -188,7 +188,28 @@ int sgemm(const float* a, long long a_rs, long long a_cs, const float* b, long l
   return SCB_OK;
 }
 
-long long infonce_scratch_bytes(int B) { return ((long long)B * B + 2LL * B + 64) * (long long)sizeof(float); }
+// Above this batch the three B x B x D contractions (25.8 GFLOP each at B=4096, D=768: BASELINE config 5) run on the tensor
+// cores as TF32 (fp32 operands, fp32 accumulate) instead of the fp32 SIMT kernel; below it the SIMT kernel keeps the loss and
+// its gradients at fp32-exact parity with the reference fixtures.
+constexpr int kNceTensorMinB = 1024;
+static bool nce_tensor_path(int B, int D) { return B >= kNceTensorMinB && B % 8 == 0 && D % 8 == 0; }
+
+// scratch: logits [B*B] | rowsum [B] | colsum [B] | pad ; tensor path adds G^T [B*B] and the two transposed feature matrices
+long long infonce_scratch_bytes2(int B, int D) {
+  long long fl = (long long)B * B + 2LL * B + 64;
+  if (nce_tensor_path(B, D)) fl += (long long)B * B + 2LL * B * D;
+  return fl * (long long)sizeof(float);
+}
+long long infonce_scratch_bytes(int B) { return infonce_scratch_bytes2(B, 1024); }  // D-independent upper bound for D <= 1024
+
+static int tf32_gemm(const float* a, long long a_ld, const float* b, long long b_ld, float* c, long long ldc, int M, int N, int K,
+                     cudaStream_t st) {
+  scb_gemm_args g{};
+  g.a = a; g.a_inner = K; g.a_rows = M; g.a_row_stride = a_ld; g.batch = 1; g.m_per_batch = M;
+  g.kb_per_tap = (K + 31) / 32; g.b = b; g.b_row_stride = b_ld; g.n = N; g.k = K; g.groups = 1;
+  g.out = c; g.out_dtype = SCB_F32; g.ldc = ldc; g.ab_format = SCB_F32; g.alpha = 1.f;
+  return gemm(g, st);
+}
 
 int infonce(const float* feat_a, const float* feat_b, const long long* ids, int B, int D, const float* log_mult, float fixed_mult,
             float margin, int dcl, int a2b, int b2a, int phase, float* loss, float* logits_out, float upstream, const float* upstream_dev,
@@ -198,8 +219,8 @@ int infonce(const float* feat_a, const float* feat_b, const long long* ids, int 
   SCB_CHECK(B > 0 && D > 0, SCB_EINVAL, "scb_infonce: empty batch");
   SCB_CHECK(phase >= 1 && phase <= 3, SCB_EINVAL, "scb_infonce: phase must be 1 (forward), 2 (backward) or 3 (both)");
   SCB_CHECK(!(phase & 1) || loss, SCB_EINVAL, "scb_infonce: forward phase needs loss");
-  SCB_CHECK(scratch_bytes >= infonce_scratch_bytes(B), SCB_EINVAL, "scb_infonce: scratch too small (%lld < %lld)", scratch_bytes,
-            infonce_scratch_bytes(B));
+  SCB_CHECK(scratch_bytes >= infonce_scratch_bytes2(B, D), SCB_EINVAL, "scb_infonce: scratch too small (%lld < %lld)", scratch_bytes,
+            infonce_scratch_bytes2(B, D));
   float* l = reinterpret_cast<float*>(scratch);
   float* rowsum = l + (long long)B * B;
   float* colsum = rowsum + B;
@@ -209,7 +230,7 @@ int infonce(const float* feat_a, const float* feat_b, const long long* ids, int 
   if (eb > 8u * num_sms()) eb = 8u * num_sms();
   int e;
   if (phase & 1) {
-    e = sgemm(feat_a, D, 1, feat_b, D, 1, l, B, B, B, D, 1.f, 0.f, st);
+    e = nce_tensor_path(B, D) ? tf32_gemm(feat_a, D, feat_b, D, l, B, B, B, D, st) : sgemm(feat_a, D, 1, feat_b, D, 1, l, B, B, B, D, 1.f, 0.f, st);
     if (e) return e;
     nce_scale_kernel<<<eb, 256, 0, st>>>(l, c);
     note_launch();
@@ -231,14 +252,28 @@ int infonce(const float* feat_a, const float* feat_b, const long long* ids, int 
     SCB_LAUNCH_OK("infonce_grad");
     unsigned sb = (unsigned)(((long long)B * D + 255) / 256);
     if (sb > 8u * num_sms()) sb = 8u * num_sms();
+    const bool tens = nce_tensor_path(B, D);
+    float* gt = colsum + B + 64;            // tensor path: G^T, then B^T / A^T ([D][B])
+    float* ft = gt + (long long)B * B;
     if (dA) {  // dA = mult * G B
-      e = sgemm(l, B, 1, feat_b, 1, D, dA, D, B, D, B, 1.f, 0.f, st);
+      if (tens) {
+        e = transpose(feat_b, SCB_F32, D, ft, SCB_F32, B, B, D, st);
+        if (!e) e = tf32_gemm(l, B, ft, B, dA, D, B, D, B, st);
+      } else {
+        e = sgemm(l, B, 1, feat_b, 1, D, dA, D, B, D, B, 1.f, 0.f, st);
+      }
       if (e) return e;
       scale_by_mult_kernel<<<sb, 256, 0, st>>>(dA, (long long)B * D, log_mult, fixed_mult);
       note_launch();
     }
     if (dB) {  // dB = mult * G^T A
-      e = sgemm(l, 1, B, feat_a, 1, D, dB, D, B, D, B, 1.f, 0.f, st);
+      if (tens) {
+        e = transpose(l, SCB_F32, B, gt, SCB_F32, B, B, B, st);
+        if (!e) e = transpose(feat_a, SCB_F32, D, ft + (long long)B * D, SCB_F32, B, B, D, st);
+        if (!e) e = tf32_gemm(gt, B, ft + (long long)B * D, B, dB, D, B, D, B, st);
+      } else {
+        e = sgemm(l, 1, B, feat_a, 1, D, dB, D, B, D, B, 1.f, 0.f, st);
+      }
       if (e) return e;
       scale_by_mult_kernel<<<sb, 256, 0, st>>>(dB, (long long)B * D, log_mult, fixed_mult);
       note_launch();

@@ -419,6 +419,24 @@ def test_infonce_vs_oracle(B, D, variant):
     assert torch.equal(logits.argmax(1).cpu(), ref_logits.argmax(1)) and torch.equal(logits.argmax(0).cpu(), ref_logits.argmax(0))
 
 
+def test_infonce_global_batch_4096_tensor_path():
+    """BASELINE config 5: 4096 x 768 global contrastive — the three 25.8 GFLOP contractions run as TF32 on the tensor cores.
+    Tolerance: logits within 1e-3 of the logit scale (north_star), loss 1e-3 relative, gradients 2 % of their max."""
+    from oracle import speechclip as osc
+    B, D = 4096, 768
+    a = F.normalize(randn(B, D, seed=61), dim=-1)
+    b = F.normalize(randn(B, D, seed=62) + 0.5 * a, dim=-1)  # correlated pairs: a realistic, peaked similarity matrix
+    ids = (torch.randperm(B, device=DEV, generator=gen(63)) // 5).contiguous()
+    a_c, b_c = a.cpu().requires_grad_(), b.cpu().requires_grad_()
+    ref, ref_logits = osc.masked_contrastive_loss(a_c, b_c, ids.cpu(), 1 / 0.07, return_logits=True)
+    ref.backward()
+    loss, dA, dB, _, logits = _loss_call(a, b, ids)
+    assert (logits.cpu() - ref_logits.detach()).abs().max() < 1e-3 / 0.07
+    assert abs(loss.item() - ref.item()) < 1e-3 * abs(ref.item())
+    gmax = a_c.grad.abs().max().item()
+    assert (dA.cpu() - a_c.grad).abs().max() < 2e-2 * gmax and (dB.cpu() - b_c.grad).abs().max() < 2e-2 * gmax
+
+
 def test_adam_step_matches_torch_adam_with_clipping():
     from speechclip_b200 import ops
     n = 100003
