@@ -81,7 +81,9 @@ __device__ __forceinline__ void store4(void* base, int dtype, long long off, con
 // 3.5 us of MMA.  So every 32x16 chunk is transposed through a private, XOR-swizzled (bank-conflict-free) 2 KB shared
 // patch: afterwards 4 lanes cover one 64-byte row segment and a warp instruction touches 8 rows instead of 32.  The
 // residual loads of a chunk are issued before the TMEM load (out may alias residual, so the compiler cannot hoist them).
-template <int BN>
+// ACT / RES / ODT >= 0 pin the activation, the residual dtype (3 = no residual) and the output dtype at compile time (and imply
+// out2 == NULL) for the shapes that dominate the step; -1 keeps the runtime switch.
+template <int BN, int ACT, int RES, int ODT>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoord& t, uint32_t tmem_base, int acc, uint32_t acc_phase,
                                               uint64_t* tfull_bar, uint32_t tempty_addr, float* stage, int warp, int lane) {
   constexpr int COLS = EpiCfg<BN>::COLS;
@@ -89,6 +91,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
   const int part = (warp - 4) >> 2;  // which slice of the tile's columns
   float4* stg = reinterpret_cast<float4*>(stage + (warp - 4) * (32 * 16));
   const int prow = lane >> 2, u = lane & 3;  // after the transpose: row (within a pass of 8) and 4-column unit of this lane
+  const int act = ACT >= 0 ? ACT : p.act;
+  const bool has_res = RES >= 0 ? (RES != 3) : (p.residual != nullptr);
+  const int res_dt = (RES >= 0 && RES != 3) ? RES : p.residual_dtype;
+  const int out_dt = ODT >= 0 ? ODT : p.out_dtype;
+  void* const out2 = ODT >= 0 ? nullptr : p.out2;
   {
       const int m_base = t.m0 + q * 32;
       const int col_base = t.n0 + part * COLS;
@@ -111,13 +118,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (col_ok) {
           if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol + col));
-          if (p.residual) {
+          if (has_res) {
 #pragma unroll
             for (int ps = 0; ps < 4; ++ps) {
               const int r = ps * 8 + prow;
               if (m_base + r < p.m_per_batch) {
                 const long long off = res_base + (long long)r * p.res_ld + col;
-                if (p.residual_dtype == SCB_F32) {
+                if (res_dt == SCB_F32) {
                   rr[ps] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.residual) + off));
                 } else {
                   const uint2 h2 = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.residual) + off));
@@ -148,25 +155,25 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
               const float4 a = stg[r * 4 + (u ^ ((r >> 1) & 3))];
               float x[4] = {fmaf(p.alpha, a.x, bias4.x), fmaf(p.alpha, a.y, bias4.y), fmaf(p.alpha, a.z, bias4.z),
                             fmaf(p.alpha, a.w, bias4.w)};
-              if (p.act == SCB_ACT_GELU_ERF) {
+              if (act == SCB_ACT_GELU_ERF) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) x[i] = gelu_fast(x[i]);
-              } else if (p.act == SCB_ACT_QUICK_GELU) {
+              } else if (act == SCB_ACT_QUICK_GELU) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) x[i] = quick_gelu(x[i]);
               }
-              if (p.residual) {
-                if (p.residual_dtype == SCB_F32) {
+              if (has_res) {
+                if (res_dt == SCB_F32) {
                   x[0] += __uint_as_float(rr[ps].x); x[1] += __uint_as_float(rr[ps].y);
                   x[2] += __uint_as_float(rr[ps].z); x[3] += __uint_as_float(rr[ps].w);
                 } else {
-                  const float2 f0 = unpack16(p.residual_dtype, rr[ps].x), f1 = unpack16(p.residual_dtype, rr[ps].y);
+                  const float2 f0 = unpack16(res_dt, rr[ps].x), f1 = unpack16(res_dt, rr[ps].y);
                   x[0] += f0.x; x[1] += f0.y; x[2] += f1.x; x[3] += f1.y;
                 }
               }
               const long long off = out_base + (long long)r * p.ldc + col;
-              store4(p.out, p.out_dtype, off, x);
-              if (p.out2) store4(p.out2, p.out2_dtype, off, x);
+              store4(p.out, out_dt, off, x);
+              if (out2) store4(out2, p.out2_dtype, off, x);
             }
           }
         }
@@ -174,7 +181,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int ACT, int RES, int ODT>
 __global__ void __launch_bounds__(EpiCfg<BN>::THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   constexpr int A_BYTES = BM * BK * 2;
@@ -338,7 +345,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile<BN>(p, tile);
-      epilogue_tile<BN>(p, t, tmem_base, acc, acc_phase, &tfull[acc], smem_u32(&tempty[acc]), stage, warp, lane);
+      epilogue_tile<BN, ACT, RES, ODT>(p, t, tmem_base, acc, acc_phase, &tfull[acc], smem_u32(&tempty[acc]), stage, warp, lane);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -378,6 +385,7 @@ __device__ __forceinline__ TileCoord decode_tile2(const GemmParams& p, int tile,
   return t;
 }
 
+template <int ACT, int RES, int ODT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<BN2>::THREADS, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   constexpr int A_BYTES = BM * BK * 2;
@@ -480,7 +488,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < p.num_tiles; tile += num_pairs) {
       const TileCoord t = decode_tile2(p, tile, (int)rank);
-      epilogue_tile<BN2>(p, t, tmem_base, acc, acc_phase, &tfull[acc], mapa_u32(smem_u32(&tempty[acc]), 0), stage, warp, lane);
+      epilogue_tile<BN2, ACT, RES, ODT>(p, t, tmem_base, acc, acc_phase, &tfull[acc], mapa_u32(smem_u32(&tempty[acc]), 0), stage, warp, lane);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -494,33 +502,34 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
+template <int ACT, int RES, int ODT>
 int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   constexpr int smem_bytes = kStages2 * (BM * BK * 2 + (BN2 / 2) * BK * 2) + 1024 + 256 + EpiCfg<BN2>::WARPS * 32 * 16 * 4;
   static_assert(smem_bytes <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
   static bool configured = false;
   if (!configured) {
-    SCB_CUDA(cudaFuncSetAttribute(gemm2_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    SCB_CUDA(cudaFuncSetAttribute(gemm2_tcgen05_kernel<ACT, RES, ODT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = true;
   }
   int pairs = num_sms() / 2;
   if (p.num_tiles < pairs) pairs = p.num_tiles;
-  gemm2_tcgen05_kernel<<<2 * pairs, EpiCfg<BN2>::THREADS, smem_bytes, stream>>>(tmA, tmB, p);
+  gemm2_tcgen05_kernel<ACT, RES, ODT><<<2 * pairs, EpiCfg<BN2>::THREADS, smem_bytes, stream>>>(tmA, tmB, p);
   note_launch();
   SCB_LAUNCH_OK("gemm2_tcgen05");
   return SCB_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int ACT = -1, int RES = -1, int ODT = -1>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   constexpr int smem_bytes = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + 256 + EpiCfg<BN>::WARPS * 32 * 16 * 4;
   static_assert(smem_bytes <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
   static bool configured = false;
   if (!configured) {
-    SCB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    SCB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES, ACT, RES, ODT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  gemm_tcgen05_kernel<BN, STAGES><<<grid, EpiCfg<BN>::THREADS, smem_bytes, stream>>>(tmA, tmB, p);
+  gemm_tcgen05_kernel<BN, STAGES, ACT, RES, ODT><<<grid, EpiCfg<BN>::THREADS, smem_bytes, stream>>>(tmA, tmB, p);
   note_launch();
   SCB_LAUNCH_OK("gemm_tcgen05");
   return SCB_OK;
@@ -609,8 +618,33 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
     int e = make_tmap(&tmB, a.b, eb, 3, dims, strides, box, 1);
     if (e) return e;
   }
-  if (two) return launch2(tmA, tmB, p, stream);
-  if (bn == 256) return launch<256, 4>(tmA, tmB, p, stream);
+  // epilogue specialisations for the shapes that carry the step (compile-time activation / residual / output type)
+  int mode = 0;
+  if (!a.out2 && bn == 256) {
+    const bool nores = a.residual == nullptr;
+    if (a.act == SCB_ACT_NONE && nores && a.out_dtype == SCB_F16) mode = 1;                                                    // QKV, K/V
+    else if (a.act == SCB_ACT_NONE && !nores && a.residual_dtype == SCB_F32 && a.out_dtype == SCB_F32) mode = 2;               // out-proj, fc2
+    else if (a.act == SCB_ACT_GELU_ERF && nores && a.out_dtype == SCB_F16) mode = 3;                                            // fc1, conv1..6
+    else if (a.act == SCB_ACT_QUICK_GELU && nores && a.out_dtype == SCB_F16) mode = 4;                                          // CLIP c_fc
+  }
+  if (two) {
+    switch (mode) {
+      case 1: return launch2<SCB_ACT_NONE, 3, SCB_F16>(tmA, tmB, p, stream);
+      case 2: return launch2<SCB_ACT_NONE, SCB_F32, SCB_F32>(tmA, tmB, p, stream);
+      case 3: return launch2<SCB_ACT_GELU_ERF, 3, SCB_F16>(tmA, tmB, p, stream);
+      case 4: return launch2<SCB_ACT_QUICK_GELU, 3, SCB_F16>(tmA, tmB, p, stream);
+      default: return launch2<-1, -1, -1>(tmA, tmB, p, stream);
+    }
+  }
+  if (bn == 256) {
+    switch (mode) {
+      case 1: return launch<256, 4, SCB_ACT_NONE, 3, SCB_F16>(tmA, tmB, p, stream);
+      case 2: return launch<256, 4, SCB_ACT_NONE, SCB_F32, SCB_F32>(tmA, tmB, p, stream);
+      case 3: return launch<256, 4, SCB_ACT_GELU_ERF, 3, SCB_F16>(tmA, tmB, p, stream);
+      case 4: return launch<256, 4, SCB_ACT_QUICK_GELU, 3, SCB_F16>(tmA, tmB, p, stream);
+      default: return launch<256, 4>(tmA, tmB, p, stream);
+    }
+  }
   if (bn == 128) return launch<128, 6>(tmA, tmB, p, stream);
   return launch<64, 8>(tmA, tmB, p, stream);
 }

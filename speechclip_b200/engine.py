@@ -50,6 +50,7 @@ class Workspace:
         return self.get(name, int(math.prod(shape)), dtype, zero).view(*shape)
 
 
+LAYER_CHUNKS = int(os.environ.get("SCB_LAYER_CHUNKS", "1"))   # batch slices for the transformer layer stack (L2 residency)
 GRAPHS = os.environ.get("SCB_CUDA_GRAPHS", "1") != "0"   # replay the frozen towers as CUDA graphs (launch-bound at small batch)
 MAX_GRAPHS = 4                                            # per plan; further input shapes run eagerly
 
@@ -135,7 +136,8 @@ class EncoderLayerPlan:
         self.ffn = self.w1.shape[0]
 
     def forward(self, ws: Workspace, x32: torch.Tensor, x16: Optional[torch.Tensor], out32: torch.Tensor, B: int, T: int,
-                kv_len: Optional[torch.Tensor], causal: bool = False, want_x16: bool = True, tag: str = "") -> Optional[torch.Tensor]:
+                kv_len: Optional[torch.Tensor], causal: bool = False, want_x16: bool = True, tag: str = "",
+                out16: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
         """x32: fp32 [B*T, d] residual stream in; x16: its fp16 copy (post-LN only; None for pre-LN).
         out32: fp32 [B*T, d] receives the layer output.  Returns the fp16 copy of the output (post-LN) or None."""
         d, M = self.d, B * T
@@ -164,7 +166,7 @@ class EncoderLayerPlan:
         ops.layernorm(y, *self.ln1, y32=x1, y16=a16, rows=M, d=d, eps=self.eps)
         ops.gemm(a16, self.w1, bias=self.b1, act=self.act, out=ffn)
         ops.gemm(ffn, self.w2, bias=self.b2, residual=x1, out=y)
-        o16 = ws.view(tag + "o16", (M, d), H) if want_x16 else None
+        o16 = out16 if out16 is not None else (ws.view(tag + "o16", (M, d), H) if want_x16 else None)
         ops.layernorm(y, *self.ln2, y32=out32, y16=o16, rows=M, d=d, eps=self.eps)
         return o16
 
@@ -272,17 +274,30 @@ class HubertPlan:
         xpad = ws.view(f"xpad_{B}_{T}", (B, rows_pad, G * 64), H, zero=True)
         ops.posconv_pack(x, valid_frames, xpad, B, T, d, G, K // 2, rows_pad)
         hidden = torch.empty(self.n_hidden, M, d, device=self.dev, dtype=torch.float32)
-        x16 = None
         tgt = hidden[0] if self.pre_ln else x
         ops.gemm_raw(a=xpad, a_inner=G * 64, a_rows=rows_pad, a_row_stride=G * 64, a_batch_stride=rows_pad * G * 64, batch=B,
                      m_per_batch=T, w=self.pos_w, n=cpg, k=K * 64, groups=G, b_group_stride=cpg * K * 64, kb_per_tap=1,
                      tap_row_shift=1, a_group_cols=64, out=tgt, ldc=d, out_batch_stride=T * d, out_group_cols=cpg,
                      bias=self.pos_b, act=ops.ACT_GELU, residual=x, algo_k=K * cpg)
+        x16s = None
         if not self.pre_ln:
-            x16 = ws.view("h16", (M, d), H)
-            ops.layernorm(x, *self.enc_ln, y32=hidden[0], y16=x16, rows=M, d=d, eps=1e-5)
+            x16s = [ws.view("hub_x16_a", (M, d), H), ws.view("hub_x16_b", (M, d), H)]
+            ops.layernorm(x, *self.enc_ln, y32=hidden[0], y16=x16s[0], rows=M, d=d, eps=1e-5)
+        # The layer stack runs over slices of the batch: with all 256 utterances a layer's intermediates (QKV 376 MB, MLP 502 MB,
+        # pre-LN sums 250 MB) stream through HBM between producer and consumer kernels; per slice they stay in the 126 MB L2.
+        chunks = max(1, min(LAYER_CHUNKS, B))
+        while B % chunks:
+            chunks -= 1
+        Bc = B // chunks
+        Mc = Bc * T
+        cur = 0
         for l, layer in enumerate(self.layers):
-            x16 = layer.forward(ws, hidden[l], x16, hidden[l + 1], B, T, valid_frames, tag="hub_")
+            for c in range(chunks):
+                rows = slice(c * Mc, (c + 1) * Mc)
+                vf = valid_frames[c * Bc:(c + 1) * Bc] if valid_frames is not None else None
+                layer.forward(ws, hidden[l][rows], None if self.pre_ln else x16s[cur][rows], hidden[l + 1][rows], Bc, T, vf, tag="hub_",
+                              out16=None if self.pre_ln else x16s[1 - cur][rows])
+            cur = 1 - cur  # fp16 copies ping-pong: later slices of this layer still read the previous layer's copy
         return hidden, T
 
 
