@@ -7,6 +7,8 @@
 //   cls_attention_fwd/bwd : the parallel branch only consumes output row 0 (kwClip.py:1103), and row 0 of its input is
 //                   the same [CLS] vector for every utterance, so attention reduces to ONE query per (utterance, head)
 //                   against all keys: an HBM-bound kernel that reads K,V once.  Backward yields dK, dV and dq.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ops.cuh"
 
@@ -515,6 +517,14 @@ int attention_fwd(const void* q, const void* k, const void* v, void* o, int fmt,
   SCB_CHECK((q_ld | k_ld | v_ld | o_ld | q_bs | k_bs | v_bs | o_bs) % 8 == 0, SCB_EINVAL, "scb_attention_fwd: strides must be multiples of 8");
   SCB_CHECK(heads <= 65535 && batch <= 65535, SCB_EUNSUPPORTED, "scb_attention_fwd: batch/heads exceed grid limits");
   if (batch == 0 || Tq == 0) return SCB_OK;
+  {  // tcgen05 / TMEM kernel for head_dim 64 and <= 320 keys (all tower attentions); SCB_ATTN_TC=0 forces the mma.sync kernel
+    static const int tc_env = [] { const char* e = getenv("SCB_ATTN_TC"); return e ? atoi(e) : 1; }();
+    if (tc_env) {
+      const int e = attention_fwd_tc(q, k, v, o, fmt, q_ld, k_ld, v_ld, o_ld, q_bs, k_bs, v_bs, o_bs, kv_len, batch, heads, head_dim, Tq, Tk,
+                                     scale, causal, st);
+      if (e != SCB_EUNSUPPORTED) return e;
+    }
+  }
   AttnParams p;
   p.q = (const uint16_t*)q; p.k = (const uint16_t*)k; p.v = (const uint16_t*)v; p.o = (uint16_t*)o;
   p.q_ld = q_ld; p.k_ld = k_ld; p.v_ld = v_ld; p.o_ld = o_ld;

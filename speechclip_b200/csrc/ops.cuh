@@ -16,6 +16,10 @@ int infonce(const float* feat_a, const float* feat_b, const long long* ids, int 
 int attention_fwd(const void* q, const void* k, const void* v, void* o, int fmt, long long q_ld, long long k_ld, long long v_ld,
                   long long o_ld, long long q_bs, long long k_bs, long long v_bs, long long o_bs, const int* kv_len, int batch, int heads,
                   int head_dim, int Tq, int Tk, float scale, int causal, cudaStream_t st);
+// attention_tc.cu (tcgen05 path; SCB_EUNSUPPORTED = shape outside its envelope, use the mma.sync kernel)
+int attention_fwd_tc(const void* q, const void* k, const void* v, void* o, int fmt, long long q_ld, long long k_ld, long long v_ld,
+                     long long o_ld, long long q_bs, long long k_bs, long long v_bs, long long o_bs, const int* kv_len, int batch, int heads,
+                     int head_dim, int Tq, int Tk, float scale, int causal, cudaStream_t st);
 int cls_attention_fwd(const float* q, const void* kv, int kv_fmt, long long kv_ld, long long kv_bs, int k_off, int v_off,
                       const int* kv_len, int batch, int heads, int head_dim, int Tk, float scale, float* probs, float* ctx32, void* ctx16,
                       int ctx16_fmt, cudaStream_t st);

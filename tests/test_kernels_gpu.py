@@ -194,6 +194,41 @@ def test_attention_fwd(hd, heads, T, mode):
     assert err < 4e-3, err  # fp16 P and fp16 output
 
 
+def test_attention_tcgen05_kernel_all_supported_shapes(monkeypatch):
+    """The tcgen05/TMEM attention on every shape class it supports, including the short ones the dispatcher normally leaves to
+    the mma.sync kernel (run in a subprocess: the dispatch knob is read once per process)."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import torch
+from speechclip_b200 import ops
+for (B, T, heads, causal, lens) in [(3, 319, 12, False, [319, 100, 318]), (2, 50, 12, False, None), (2, 77, 8, True, None), (2, 257, 16, False, None), (5, 320, 4, False, [320, 1, 64, 65, 200])]:
+    d = heads * 64
+    g = torch.Generator(device="cuda").manual_seed(T)
+    qkv = (0.7 * torch.randn(B, T, 3 * d, device="cuda", generator=g)).half()
+    q, k, v = qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+    out = torch.empty(B, T, d, device="cuda", dtype=torch.float16)
+    kv_len = torch.tensor(lens, device="cuda", dtype=torch.int32) if lens else None
+    ops.attention(q, k, v, out, heads, 0.125, kv_len, causal=causal)
+    qf, kf, vf = (t.float().view(B, T, heads, 64).transpose(1, 2) for t in (q, k, v))
+    s = qf @ kf.transpose(-1, -2) * 0.125
+    if lens:
+        pad = torch.arange(T, device="cuda")[None] >= torch.tensor(lens, device="cuda")[:, None]
+        s = s.masked_fill(pad[:, None, None, :], float("-inf"))
+    if causal:
+        s = s + torch.full((T, T), float("-inf"), device="cuda").triu_(1)
+    ref = (torch.softmax(s, -1) @ vf).transpose(1, 2).reshape(B, T, d)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 4e-3, (T, heads, causal, err)
+print("ok")
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SCB_ATTN_TC="2")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.parametrize("hd,heads,Tk", [(96, 8, 320), (16, 4, 13), (128, 8, 320), (8, 8, 12)])
 def test_cls_attention_fwd_bwd(hd, heads, Tk):
     from speechclip_b200 import ops
