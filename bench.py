@@ -305,7 +305,7 @@ def run_own(args):
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "gemm_dram_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and args.config == "base" and per_gpu == 256:  # captured for exactly this workload
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
     breakdown = {k: {"ms_per_step": v[0] / prof_steps, "calls_per_step": v[2] / prof_steps} for k, v in
                  sorted(agg.items(), key=lambda kv: -kv[1][0])}
