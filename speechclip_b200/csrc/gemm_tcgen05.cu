@@ -556,7 +556,13 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
   SCB_CHECK(a.kb_per_tap > 0, SCB_EINVAL, "scb_gemm: kb_per_tap must be positive");
   SCB_CHECK(a.groups == 1 || a.out_group_cols >= a.n, SCB_EINVAL, "scb_gemm: out_group_cols < n");
 
-  const int bn = a.n > 128 ? 256 : (a.n > 64 ? 128 : 64);
+  // Tile width: 256 columns for throughput; when that leaves most of the 148 SMs without a tile (CLIP ViT and the head at small
+  // per-GPU batch: strong scaling at 32 pairs per GPU), narrower tiles trade per-tile efficiency for occupancy.
+  int bn = a.n > 128 ? 256 : (a.n > 64 ? 128 : 64);
+  {
+    const long long mt = (long long)a.batch * a.groups * ((a.m_per_batch + BM - 1) / BM);
+    while (bn > 64 && mt * ((a.n + bn - 1) / bn) < (num_sms() * 3) / 4) bn >>= 1;
+  }
   // CTA pairs (256 x 256 tiles) for the large shapes; SCB_GEMM_2CTA=0 keeps every problem on the single-CTA kernel
   static const int two_env = [] { const char* e = getenv("SCB_GEMM_2CTA"); return e ? atoi(e) : 1; }();
   // (the tap-walk conv GEMMs measured 7 % faster on single CTAs, the plain linears 2-3 % faster on pairs)
