@@ -108,6 +108,114 @@ class ParallelBranch(nn.Module):
         return tuple(h[:, 1:] for h in hidden)                                # kwClip.py:1071-1073
 
 
+class AttentionAndNorm(nn.Module):
+    """``MultiheadAttentionAndNorm`` (TransformerModels.py:99-135): LN(MHA(src, src, src) + src); keys
+    ``multihead_attn_layer.*``, ``attentionBlock_Norm.*``."""
+
+    def __init__(self, d_model=768, nhead=1, dropout=0.1, layer_norm_eps=1e-5, batch_first=True, **_):
+        super().__init__()
+        assert batch_first
+        self.multihead_attn_layer = nn.MultiheadAttention(d_model, num_heads=nhead, dropout=dropout, batch_first=True)
+        self.attentionBlock_Norm = nn.LayerNorm(d_model, eps=layer_norm_eps)
+        self.nhead = nhead
+
+    def forward(self, src, key_padding_mask):
+        m = self.multihead_attn_layer
+        B, L, D = src.shape
+        hd = D // self.nhead
+        qkv = src @ m.in_proj_weight.t() + m.in_proj_bias
+        q, k, v = qkv.split(D, -1)
+        q = q.view(B, L, self.nhead, hd).transpose(1, 2) * hd ** -0.5
+        k = k.view(B, L, self.nhead, hd).transpose(1, 2)
+        v = v.view(B, L, self.nhead, hd).transpose(1, 2)
+        s = (q @ k.transpose(-1, -2)).masked_fill(key_padding_mask[:, None, None, :], float("-inf"))
+        o = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, L, D)
+        return self.attentionBlock_Norm(o @ m.out_proj.weight.t() + m.out_proj.bias + src)
+
+
+class KwBatchNorm(nn.Module):
+    """``Kw_BatchNorm`` with batchnorm_type=eachKw, parallel=True (kw_bn.py:97-123): one BatchNorm1d over kw_dim * kw_num
+    features ordered (dim, kw); key ``bn_layer.*``."""
+
+    def __init__(self, kw_num, kw_dim, init_bias, init_scale, std_scale=1.0, learnable=True):
+        super().__init__()
+        self.kw_num, self.kw_dim = kw_num, kw_dim
+        self.bn_layer = nn.BatchNorm1d(kw_dim * kw_num)
+        with torch.no_grad():
+            self.bn_layer.weight.copy_((init_scale * std_scale).repeat(kw_num))   # (sic) the reference tiles per-dim values
+            self.bn_layer.bias.copy_(init_bias.repeat(kw_num))                    # over a (dim, kw)-ordered axis
+        self.bn_layer.weight.requires_grad = learnable
+        self.bn_layer.bias.requires_grad = learnable
+
+    def forward(self, keywords):
+        B = keywords.shape[0]
+        x = keywords.permute(0, 2, 1).reshape(B, -1)
+        x = self.bn_layer(x)
+        return x.reshape(B, self.kw_dim, self.kw_num).permute(0, 2, 1)
+
+
+def simple_vector_quantizer(x, temp, training, prob_msk=(0, 2, 3)):
+    """``SimpleVectorQuantizer.forward`` (my_vector_quantizer.py:64-165) with use_gumbel=False, hard=True, time_first=True."""
+    bsz, tsz, fsz = x.shape
+    x = x.reshape(bsz * tsz, fsz).clone()
+    for i in prob_msk:
+        x[:, i] = x[:, i] + float("-inf")
+    k = x.argmax(-1)
+    hard_x = torch.zeros_like(x).scatter_(-1, k.view(-1, 1), 1.0)
+    hard_probs = hard_x.float().mean(0)
+    result = {"num_vars": fsz}
+    result["code_perplexity"] = torch.exp(-torch.sum(hard_probs * torch.log(hard_probs + 1e-7), dim=-1)).sum()
+    avg_probs = torch.softmax(x.float(), dim=-1).mean(0)
+    probs_per_t = torch.softmax(x.view(bsz, tsz, -1), dim=-1).permute(1, 0, 2)
+    result["ent_per_t"] = (-torch.sum(probs_per_t * torch.log(probs_per_t + 1e-9), dim=-1)).mean(-1)
+    result["prob_perplexity"] = torch.exp(-torch.sum(avg_probs * torch.log(avg_probs + 1e-7), dim=-1)).sum()
+    result["temp"] = float(temp)
+    if training:
+        soft = torch.softmax(x / temp, dim=-1)
+        y = hard_x + soft - soft.detach()
+    else:
+        y = hard_x
+    result["subword_prob"] = y.view(bsz, tsz, -1)
+    result["diversity_loss"] = (fsz - result["prob_perplexity"]) / fsz
+    result["targets"] = y.argmax(-1).view(bsz, tsz, 1).detach()
+    return result
+
+
+class CascadedBranch(nn.Module):
+    """``KW_CascadedBranch`` (kwClip.py:697-916) with MultiheadAttentionAndNorm, eachKw/parallel BatchNorm, SimpleVectorQuantizer."""
+
+    def __init__(self, clip_model: "oclip.CLIP", d_model: int, keyword_num: int = 8, nhead: int = 1, vq_temp: float = 0.1,
+                 sot_token: int = 1, eot_token: int = 2):
+        super().__init__()
+        self.clip_model = [clip_model]  # not registered: the reference registers it twice, the state dict is compared per branch
+        self.keyword_num = keyword_num
+        text_dim = clip_model.token_embedding.weight.shape[1]
+        self.cls = nn.Parameter(torch.randn(1, keyword_num, d_model))
+        self.self_att = AttentionAndNorm(d_model=d_model, nhead=nhead)
+        self.linear_proj = nn.Linear(d_model, text_dim)
+        emb = clip_model.token_embedding.weight.detach()
+        self.bn_layer = KwBatchNorm(keyword_num, text_dim, emb.mean(0), emb.std(0))
+        self.vq_temp = vq_temp
+        self.sot_token, self.eot_token = sot_token, eot_token
+
+    def forward(self, audio_feat, audio_len, training=True, collect=None):
+        B, T = audio_feat.shape[:2]
+        K = self.keyword_num
+        src = torch.cat([self.cls.expand(B, K, -1), audio_feat], 1)                     # kwClip.py:870-872
+        kpm = keypadding_mask(T + K, audio_len + K)                                        # :874-876
+        kw = self.self_att(src, kpm)[:, :K]                                                # :878-882
+        kw = self.linear_proj(kw)                                                          # :884
+        kw = self.bn_layer(kw)                                                             # :886-887
+        emb = self.clip_model[0].token_embedding.weight
+        cos = torch.stack([F.cosine_similarity(kw[:, i, :].unsqueeze(-1), emb.t().unsqueeze(0), dim=1) for i in range(K)], 1)  # :890-900
+        vq = simple_vector_quantizer(cos, self.vq_temp, training)                          # :909
+        keywords = vq["subword_prob"] @ emb                                                # :911
+        feat = self.clip_model[0].encode_keywords(keywords, K, self.sot_token, self.eot_token)  # :914
+        if collect is not None:
+            collect.update(kw_bn=kw, cos=cos, keywords=keywords)
+        return feat, vq, keywords
+
+
 def masked_contrastive_loss(feat_a, feat_b, index=None, temperature=1.0 / 0.07, margin=0.0, dcl=False,
                             a2b=True, b2a=True, return_logits=False):
     """losses.py:185-245.  ``temperature`` is the multiplier (1/0.07 fixed, or exp(param) when learnable)."""

@@ -118,6 +118,46 @@ def part1_reference():
         s.step()
     save("ref_scheduler.npz", lrs=np.array(lrs, dtype=np.float64))
 
+    # ---- cascaded-branch pieces: MultiheadAttentionAndNorm (TransformerModels.py:99-135), Kw_BatchNorm (kw_bn.py:8-164,
+    #      eachKw / parallel), SimpleVectorQuantizer (my_vector_quantizer.py:12-165, fixed temperature, hard straight-through)
+    torch.manual_seed(13)
+    mha = tm.MultiheadAttentionAndNorm(d_model=64, nhead=1, dropout=0.1)
+    for p in mha.parameters():
+        p.data.add_(0.05 * torch.randn(p.shape, generator=g))
+    mha.eval()
+    src = torch.randn(3, 12, 64, generator=g)
+    kpm = du.get_keypadding_mask(12, torch.tensor([12, 6, 9]))
+    with torch.no_grad():
+        out = mha(src, kpm)
+    save("ref_mha_norm.npz", src=src, kpm=kpm, out=out, **{"sd." + k: v for k, v in mha.state_dict().items()})
+
+    kb = load_ref("module/speechclip_c_modules/kw_bn.py", "ref_kb")
+    ib, isc = torch.randn(16, generator=g), torch.rand(16, generator=g) + 0.5
+    bn = kb.Kw_BatchNorm(kw_num=4, kw_dim=16, batchnorm_type="eachKw", init_bias=ib, init_scale=isc, std_scale=1.0,
+                         learnable=True, parallel=True).train()
+    x = torch.randn(6, 4, 16, generator=g).requires_grad_()
+    y = bn(x)
+    w = torch.randn(6, 4, 16, generator=g)
+    (y * w).sum().backward()
+    bn.eval()
+    with torch.no_grad():
+        y_eval = bn(x.detach())
+    save("ref_kw_bn.npz", x=x, init_bias=ib, init_scale=isc, y_train=y, w=w, dx=x.grad, dgamma=bn.bn_layer.weight.grad,
+         dbeta=bn.bn_layer.bias.grad, running_mean=bn.bn_layer.running_mean, running_var=bn.bn_layer.running_var, y_eval=y_eval)
+
+    vqm = load_ref("module/speechclip_c_modules/my_vector_quantizer.py", "ref_vq")
+    vq = vqm.SimpleVectorQuantizer(temp="fixed=0.1", time_first=True, use_gumbel=False, hard=True).train()
+    cos = (0.3 * torch.randn(3, 4, 40, generator=g)).requires_grad_()
+    r = vq(cos.clone())
+    wv = torch.randn(3, 4, 40, generator=g)
+    (r["subword_prob"] * wv).sum().backward()
+    vq.eval()
+    with torch.no_grad():
+        r_eval = vq(cos.detach().clone())
+    save("ref_vq.npz", cos=cos, w=wv, dcos=cos.grad, subword_prob=r["subword_prob"], targets=r["targets"],
+         code_perplexity=r["code_perplexity"], prob_perplexity=r["prob_perplexity"], ent_per_t=r["ent_per_t"],
+         diversity_loss=r["diversity_loss"], subword_prob_eval=r_eval["subword_prob"])
+
     # ---- random_crop_max_length semantics (audio_transforms.py:5-23): shapes only (np.random offset)
     at = load_ref("data/audio_transforms.py", "ref_at")
     assert at.random_crop_max_length(torch.arange(10), 4, 10).shape == (4,)

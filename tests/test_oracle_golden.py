@@ -77,3 +77,35 @@ def test_scheduler_matches_reference(golden):
     lrs = golden("ref_scheduler.npz")["lrs"]
     mine = [1e-4 * osc.linear_warmup_decay(s, 1e-4, 5, 20, 1e-8) for s in range(20)]
     assert np.allclose(mine, lrs, rtol=1e-12, atol=0)
+
+
+def test_cascaded_pieces_match_reference(golden):
+    z = golden("ref_mha_norm.npz")
+    m = osc.AttentionAndNorm(64, 1).eval()
+    m.load_state_dict({k[3:]: T(z[k]) for k in z.files if k.startswith("sd.")})
+    with torch.no_grad():
+        out = m(T(z["src"]), T(z["kpm"]))
+    valid = ~T(z["kpm"])
+    assert torch.allclose(out[valid], T(z["out"])[valid], atol=2e-6)
+
+    z = golden("ref_kw_bn.npz")
+    bn = osc.KwBatchNorm(4, 16, T(z["init_bias"]), T(z["init_scale"])).train()
+    x = T(z["x"]).clone().requires_grad_()
+    y = bn(x)
+    (y * T(z["w"])).sum().backward()
+    assert torch.allclose(y, T(z["y_train"]), atol=1e-6) and torch.allclose(x.grad, T(z["dx"]), atol=1e-6)
+    assert torch.allclose(bn.bn_layer.weight.grad, T(z["dgamma"]), atol=1e-5) and torch.allclose(bn.bn_layer.bias.grad, T(z["dbeta"]), atol=1e-5)
+    assert torch.allclose(bn.bn_layer.running_var, T(z["running_var"]), atol=1e-6)
+    bn.eval()
+    with torch.no_grad():
+        assert torch.allclose(bn(T(z["x"])), T(z["y_eval"]), atol=1e-6)
+
+    z = golden("ref_vq.npz")
+    cos = T(z["cos"]).clone().requires_grad_()
+    r = osc.simple_vector_quantizer(cos, 0.1, True)
+    (r["subword_prob"] * T(z["w"])).sum().backward()
+    assert torch.allclose(r["subword_prob"], T(z["subword_prob"]), atol=1e-6) and torch.equal(r["targets"], T(z["targets"]))
+    assert torch.allclose(cos.grad, T(z["dcos"]), atol=1e-6)
+    for k in ("code_perplexity", "prob_perplexity", "ent_per_t", "diversity_loss"):
+        assert torch.allclose(r[k], T(z[k]), atol=1e-5), k
+    assert torch.equal(osc.simple_vector_quantizer(T(z["cos"]), 0.1, False)["subword_prob"], T(z["subword_prob_eval"]))
