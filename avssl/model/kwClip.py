@@ -16,19 +16,23 @@ import torch.distributed as dist
 from torch import nn
 
 from speechclip_b200 import ops
-from speechclip_b200.functional import GradArena, L2NormFn, ParallelBranchFn
+from speechclip_b200.cascaded import PARAM_ORDER as CASCADED_PARAM_ORDER
+from speechclip_b200.cascaded import CascadedHead
+from speechclip_b200.functional import CascadedBranchFn, GradArena, L2NormFn, ParallelBranchFn
 from speechclip_b200.head import PARAM_ORDER, ParallelHead
 from speechclip_b200.optim import FusedAdam
 
 from ..base import OrderedNamespace
 from ..module import ClipModel, FairseqSpeechEncoder_Hubert, MLPLayers, losses, mutualRetrieval
 from ..module.kw_modules import TransformerModels
+from ..module.speechclip_c_modules import vector_quantizers
+from ..module.speechclip_c_modules.kw_bn import Kw_BatchNorm
 from ..optim import get_scheduler
 from .base_model import BaseLightningModel
 
 logger = logging.getLogger(__name__)
 
-__all__ = ["KWClipBase", "KW_ParallelBranch", "KWClip_GeneralTransformer"]
+__all__ = ["KWClipBase", "KW_CascadedBranch", "KW_ParallelBranch", "KWClip_GeneralTransformer"]
 
 METRIC_REDUCEFN_MAPPING = {
     torch.Tensor: lambda x: torch.mean(x),
@@ -279,6 +283,128 @@ class KWClipBase(BaseLightningModel):
         return [audio_optimizer], [{"scheduler": audio_scheduler, "interval": "step"}]
 
 
+class VQResults(dict):
+    """``vq_results`` of the reference (my_vector_quantizer.py:66-164).  ``temp``, ``num_vars`` and ``targets`` are filled
+    eagerly; the logging statistics (``code_perplexity``, ``prob_perplexity``, ``ent_per_t``, ``diversity_loss``) and the dense
+    one-hot ``subword_prob`` [B, K, V] are computed on first access -- the training step reads none of them."""
+
+    _LAZY_STATS = ("code_perplexity", "prob_perplexity", "ent_per_t", "diversity_loss")
+
+    def __init__(self, vq, cos, idx, stats, bsz, tsz):
+        super().__init__(num_vars=cos.shape[1], temp=vq.temperature(), targets=idx.view(bsz, tsz, 1))
+        self._src = (vq, cos, idx, stats, bsz, tsz)
+
+    def __missing__(self, key):
+        vq, cos, idx, stats, bsz, tsz = self._src
+        if key in self._LAZY_STATS:
+            for k, v in vq.results(cos, idx, stats, bsz, tsz, produce_targets=False).items():
+                self.setdefault(k, v)
+            return dict.__getitem__(self, key)
+        if key == "subword_prob":
+            prob = torch.zeros(bsz * tsz, cos.shape[1], device=cos.device).scatter_(1, idx.view(-1, 1), 1.0).view(bsz, tsz, -1)
+            self[key] = prob
+            return prob
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._LAZY_STATS or key == "subword_prob"
+
+
+class KW_CascadedBranch(nn.Module):
+    """The cascaded branch (kwClip.py:697-1001): K learned [CLS] queries -> attention block -> projection -> keyword
+    BatchNorm -> cosine scores against the CLIP vocabulary -> hard straight-through quantiser -> frozen CLIP text tower."""
+
+    def __init__(self, config: OrderedNamespace, audio_dim: int, text_dim: int, clip: ClipModel) -> None:
+        super().__init__()
+        self.audio_dim = audio_dim
+        self.text_dim = text_dim
+        self.clip = clip
+        self.config = config
+        cb = self.config.model_settings.cascaded_branch
+        self.kw_projection_config = cb.keyword.get("kw_projection", None)
+        logger.info("Using KW_CascadedBranch")
+        self.keyword_num = cb.keyword.number
+        self.cls = self._create_cls()
+        logger.info("Start init [CLS] {}".format(self.cls.shape))
+        assert hasattr(TransformerModels, cb.transformer_type), "transformer structure '{}' not supported".format(cb.transformer_type)
+        if cb.transformer_type != "MultiheadAttentionAndNorm":
+            raise NotImplementedError("KW_CascadedBranch on B200: transformer_type MultiheadAttentionAndNorm (every shipped cascaded config)")
+        logger.info(f"Using {cb.transformer_type} as KW_CascadedBranch")
+        self.self_att = getattr(TransformerModels, cb.transformer_type)(**cb.transformer_args)
+        if self.kw_projection_config is None:
+            logger.info("kw_projection not specified, using single linear layer as default")
+            self.linear_proj = nn.Linear(cb.transformer_args.d_model, self.text_dim)
+        else:
+            self.linear_proj = MLPLayers(units=self.kw_projection_config.dimensions, dropout=self.kw_projection_config.dropout)
+        self.vq_type = cb.vq.type
+        if not hasattr(vector_quantizers, cb.vq.type):
+            raise NotImplementedError("Vq ({}) not implemented".format(cb.vq.type))
+        self.vector_quantizer = getattr(vector_quantizers, self.vq_type)(**cb.vq.args)
+        if not hasattr(cb.keyword, "batchnorms"):
+            raise NotImplementedError("KW_CascadedBranch on B200: keyword.batchnorms is required (every shipped cascaded config sets it)")
+        bn = cb.keyword.batchnorms
+        emb = self.clip.model.token_embedding.weight
+        self.bn_layer = Kw_BatchNorm(kw_num=self.keyword_num, kw_dim=self.text_dim, batchnorm_type=bn.type,
+                                     init_bias=torch.mean(emb, dim=0), init_scale=torch.std(emb, dim=0), std_scale=bn.std_scale,
+                                     learnable=bn.learnable if hasattr(bn, "learnable") else True,
+                                     parallel=bn.parallel if hasattr(bn, "parallel") else False)
+        self._scb_arena_fn = None
+
+    def _create_cls(self) -> torch.nn.Parameter:
+        return torch.nn.Parameter(torch.randn([1, self.keyword_num, self.config.model_settings.cascaded_branch.transformer_args.d_model]))
+
+    def parameters(self, recurse: bool = True):
+        """The branch's own parameters.  The reference registers the shared ClipModel as a submodule, so its
+        ``parameters()`` also yields the frozen CLIP weights (which the optimiser then ignores); they are skipped here."""
+        own = {id(p) for p in self.clip.parameters()}
+        return (p for p in super().parameters(recurse) if id(p) not in own)
+
+    def _head(self):
+        p = self.self_att.head_params()
+        p["cls"] = self.cls
+        p["linear_proj.weight"], p["linear_proj.bias"] = self.linear_proj.weight, self.linear_proj.bias
+        p["bn_layer.bn_layer.weight"], p["bn_layer.bn_layer.bias"] = self.bn_layer.bn_layer.weight, self.bn_layer.bn_layer.bias
+        bn = self.bn_layer.bn_layer
+        head = CascadedHead(self.self_att.d_model, self.self_att.nhead, self.keyword_num, self.text_dim, self.self_att.layer_norm_eps,
+                            bn.eps, bn.momentum)
+        return head, p
+
+    def _kv_len(self, audio_len: torch.Tensor, total_len: int, dev) -> torch.Tensor:
+        # get_keypadding_mask(max_length=T+K, data_lens=audio_len+K) as valid-key counts
+        kv_len = torch.empty(audio_len.shape[0], device=dev, dtype=torch.int32)
+        ops.lengths_to_i32(audio_len.to(device=dev, dtype=torch.int64).contiguous(), self.keyword_num, total_len, kv_len)
+        return kv_len
+
+    @torch.no_grad()
+    def extract_hidden_states(self, audio_feat: torch.Tensor, audio_len: torch.Tensor) -> Tuple:
+        from speechclip_b200.functional import workspace
+        head, p = self._head()
+        kv_len = self._kv_len(audio_len, audio_feat.size(1) + self.keyword_num, audio_feat.device)
+        hidden = head.full_forward(workspace(audio_feat.device), p, audio_feat.float().contiguous(), kv_len)
+        return tuple(x[:, self.keyword_num:, ...] for x in hidden)
+
+    def forward(self, audio_feat: torch.Tensor, audio_len: torch.Tensor) -> Tuple[torch.Tensor, dict, torch.Tensor]:
+        """-> (audio_feat [B, D] from the CLIP text tower, vq_results, keywords [B, K, W])  (kwClip.py:857-916)."""
+        head, p = self._head()
+        dev = audio_feat.device
+        kv_len = self._kv_len(audio_len, audio_feat.size(1) + self.keyword_num, dev)
+        arena = self._scb_arena_fn() if self._scb_arena_fn is not None else None
+        bn = self.bn_layer.bn_layer
+        sot, eot = self.clip.special_tokens()
+        rt = dict(vocab=self.clip.vocabulary(dev), text=self.clip.text_plan(dev), bn_buffers=(bn.running_mean, bn.running_var),
+                  temp=self.vector_quantizer.temperature(), sot=int(sot), eot=int(eot), training=self.training,
+                  need_grad=torch.is_grad_enabled())
+        feat, keywords, cos, idx, stats = CascadedBranchFn.apply(audio_feat, kv_len, head, arena, rt,
+                                                                 *[p[k] for k in CASCADED_PARAM_ORDER])
+        if self.training:
+            bn.num_batches_tracked += 1
+        bsz = audio_feat.size(0)
+        return feat, VQResults(self.vector_quantizer, cos, idx, stats, bsz, self.keyword_num), keywords
+
+    def getAttentionMap(self, audio_feat: torch.Tensor, audio_len: torch.Tensor):
+        raise NotImplementedError("attention-map / top-k keyword visualisation (kwClip.py:918-1001) needs the BPE tokenizer; out of scope")
+
+
 class KW_ParallelBranch(nn.Module):
     """The parallel branch (kwClip.py:1004-1108): [CLS] + transformer encoder + projection."""
 
@@ -338,7 +464,12 @@ class KWClip_GeneralTransformer(KWClipBase):
         self.cascaded_branch = None
         self.parallel_branch = None
         if self.config.model_settings.cascaded_objective_weight > 0:
-            raise NotImplementedError("cascaded branch (keyword VQ + CLIP text tower): SURVEY.md §8 row a9, not built yet")
+            logger.info("Create Cascaded Branch")
+            if self.config.model_settings.cascaded_branch.type == "KW_CascadedBranch":
+                self.cascaded_branch = KW_CascadedBranch(config=self.config, audio_dim=self.audio_embd_dim,
+                                                         text_dim=self.subword_embd_dim, clip=self.clip)
+            else:
+                raise NotImplementedError()
         if self.config.model_settings.parallel_objective_weight > 0:
             logger.info("Create Parallel Branch")
             self.parallel_branch = KW_ParallelBranch(config=self.config, audio_dim=self.audio_embd_dim, out_dim=self.subword_embd_dim)
@@ -354,9 +485,14 @@ class KWClip_GeneralTransformer(KWClipBase):
         super()._wire_arena()
         if self.parallel_branch is not None:
             self.parallel_branch._scb_arena_fn = self.arena
+        if self.cascaded_branch is not None:
+            self.cascaded_branch._scb_arena_fn = self.arena
 
     def getTrainableParams(self) -> list:
         _params = super().getTrainableParams()
+        if self.cascaded_branch is not None:
+            logger.info("Add cascaded_branch parameters")
+            _params += list(self.cascaded_branch.parameters())
         if self.parallel_branch is not None:
             _params += list(self.parallel_branch.parameters())
         return _params
@@ -365,6 +501,10 @@ class KWClip_GeneralTransformer(KWClipBase):
         wav, wav_len = self.processWavs(wav)
         audio_feat, audio_len, hidden_states = self.forward_audio(wav, wav_len, return_hidden_states=True)
         assert isinstance(hidden_states, tuple)
+        if self.cascaded_branch is not None:
+            cascaded_hidden_states = self.cascaded_branch.extract_hidden_states(audio_feat, audio_len)
+            assert isinstance(cascaded_hidden_states, tuple)
+            hidden_states = hidden_states + tuple(cascaded_hidden_states[1:])
         if self.parallel_branch is not None:
             parallel_hidden_states = self.parallel_branch.extract_hidden_states(audio_feat, audio_len)
             assert isinstance(parallel_hidden_states, tuple)
@@ -376,24 +516,31 @@ class KWClip_GeneralTransformer(KWClipBase):
         assert "id" in input_feats
         assert "cascaded_audio_feat" in input_feats or "parallel_audio_feat" in input_feats
         assert "image_feat" in input_feats
+        cascaded_audio_feat = input_feats["cascaded_audio_feat"].float() if "cascaded_audio_feat" in input_feats else None
         parallel_audio_feat = input_feats["parallel_audio_feat"].float() if "parallel_audio_feat" in input_feats else None
         image_feat = input_feats["image_feat"].float()
         id = input_feats["id"]
         losses_ = {"loss": 0}
-        w = self.config.model_settings.parallel_objective_weight
-        if w > 0:
-            losses_["p_cl_loss"] = self.criterion(feat_A=parallel_audio_feat, feat_B=image_feat, index=id)
-            # weight 1.0 (every shipped config) adds nothing to the graph; other weights scale through autograd
-            losses_["loss"] = losses_["p_cl_loss"] if w == 1.0 else w * losses_["p_cl_loss"]
+        # weight 1.0 (every shipped config) adds nothing to the graph; other weights scale through autograd
+        for key, w, feat in (("c_cl_loss", self.config.model_settings.cascaded_objective_weight, cascaded_audio_feat),
+                             ("p_cl_loss", self.config.model_settings.parallel_objective_weight, parallel_audio_feat)):
+            if w > 0:
+                losses_[key] = self.criterion(feat_A=feat, feat_B=image_feat, index=id)
+                term = losses_[key] if w == 1.0 else w * losses_[key]
+                losses_["loss"] = term if isinstance(losses_["loss"], int) else losses_["loss"] + term
         return losses_
 
     def encode_speech(self, wav) -> dict:
         wav, wav_len = self.processWavs(wav)
         audio_feat, audio_len = self.forward_audio(wav, wav_len)
-        parallel_audio_feat = None
+        cascaded_audio_feat = parallel_audio_feat = vq_results = keywords = None
+        if self.cascaded_branch is not None:
+            cascaded_audio_feat, vq_results, keywords = self.cascaded_branch(audio_feat=audio_feat, audio_len=audio_len)
+            cascaded_audio_feat = l2_normalize(cascaded_audio_feat)
         if self.parallel_branch is not None:
             parallel_audio_feat = l2_normalize(self.parallel_branch(audio_feat=audio_feat, audio_len=audio_len))
-        return {"cascaded_audio_feat": None, "parallel_audio_feat": parallel_audio_feat, "vq_results": None, "keywords": None}
+        return {"cascaded_audio_feat": cascaded_audio_feat, "parallel_audio_feat": parallel_audio_feat, "vq_results": vq_results,
+                "keywords": keywords}
 
     def forward(self, batch) -> tuple:
         wav, wav_len, image, id = batch["wav"], batch["wav_len"], batch["image"], batch["id"]
@@ -402,11 +549,17 @@ class KWClip_GeneralTransformer(KWClipBase):
         image_feat = l2_normalize(self.forward_image(image))
         losses_ = {"id": id, "image_feat": image_feat}
         log_metrics = {}
-        parallel_audio_feat = None
+        cascaded_audio_feat = parallel_audio_feat = vq_results = keywords = None
+        if self.cascaded_branch is not None:
+            cascaded_audio_feat, vq_results, keywords = self.cascaded_branch(audio_feat=audio_feat, audio_len=audio_len)
+            cascaded_audio_feat = l2_normalize(cascaded_audio_feat)
+            losses_["cascaded_audio_feat"] = cascaded_audio_feat
         if self.parallel_branch is not None:
             parallel_audio_feat = l2_normalize(self.parallel_branch(audio_feat=audio_feat, audio_len=audio_len))
             losses_["parallel_audio_feat"] = parallel_audio_feat
+        if self.config.model_settings.cascaded_objective_weight > 0:
+            log_metrics["softmax_temp"] = vq_results["temp"]
         log_metrics.update({"cl_temp": self.criterion.current_temperature})
         return (losses_, log_metrics,
-                {"cascaded_audio_feat": None, "parallel_audio_feat": parallel_audio_feat, "image_feat": image_feat, "id": id,
-                 "vq_results": None, "keywords": None})
+                {"cascaded_audio_feat": cascaded_audio_feat, "parallel_audio_feat": parallel_audio_feat, "image_feat": image_feat, "id": id,
+                 "vq_results": vq_results, "keywords": keywords})

@@ -12,6 +12,8 @@ import numpy as np
 import torch
 from torch import nn
 
+from speechclip_b200 import ops
+from speechclip_b200.cascaded import TextTowerPlan, Vocabulary
 from speechclip_b200.engine import VitPlan
 from speechclip_b200.functional import workspace
 from speechclip_b200.init import seeded_init_
@@ -27,7 +29,7 @@ class ClipModel(nn.Module):
     def __init__(self, name: str, device: str = "cpu", image_encoder_trainable: bool = False, text_encoder_trainable: bool = False,
                  reduce_subword_embbedding: str = None, **kwargs):
         super().__init__()
-        assert name in _clip_models or name == "tiny", name
+        assert name in _clip_models or name in ("tiny", "tiny_c"), name
         if name.startswith("RN"):
             raise NotImplementedError("ResNet CLIP towers are outside the B200 hot path (shipped configs use ViT-B/32 and ViT-L/14)")
         if image_encoder_trainable or text_encoder_trainable:
@@ -69,13 +71,15 @@ class ClipModel(nn.Module):
             self.endOfTxt_reduced = self.original2Reduced[EOT_TOKEN]
         self._vit = None
         self._vit_key = None
+        self._text = None
+        self._vocab = None
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_plan())
 
     def invalidate_plan(self):
-        self._vit = None
+        self._vit = self._text = self._vocab = None
 
     def _apply(self, fn, *a, **k):
-        self._vit = None
+        self._vit = self._text = self._vocab = None
         return super()._apply(fn, *a, **k)
 
     def freeze_models(self):
@@ -119,8 +123,67 @@ class ClipModel(nn.Module):
             raise ValueError(f"Incorrect image tensor shape {tuple(image.shape)}")
         return self.vit_plan(image.device).forward(workspace(image.device), image.float().contiguous())
 
-    def encode_text(self, text: torch.Tensor) -> torch.Tensor:
-        raise NotImplementedError("CLIP text tower: cascaded-branch row of SURVEY.md §8 (a9), not built yet")
+    def text_plan(self, device) -> TextTowerPlan:
+        """Frozen text transformer in GEMM layout (+ fp32 transposed weights for the activation-gradient backward)."""
+        key = str(device)
+        if self._text is None or self._text[0] != key:
+            sd = {k: v for k, v in self.model.state_dict().items() if not k.startswith("visual.")}
+            self._text = (key, TextTowerPlan(sd, device, heads=self.arch.t_heads))
+        return self._text[1]
 
+    def vocabulary(self, device) -> Vocabulary:
+        """The (reduced) token-embedding table prepared for the cosine / VQ kernels."""
+        key = str(device)
+        if self._vocab is None or self._vocab[0] != key:
+            self._vocab = (key, Vocabulary(self.model.token_embedding.weight, device))
+        return self._vocab[1]
+
+    def special_tokens(self) -> tuple:
+        """(sot, eot) row indices into ``model.token_embedding`` (clip_official.py:236-243)."""
+        if self.selected_text_emb_ids is None:
+            return (min(SOT_TOKEN, self.arch.vocab - 2), min(EOT_TOKEN, self.arch.vocab - 1))
+        return self.startOfTxt_reduced, self.endOfTxt_reduced
+
+    @torch.no_grad()
+    def encode_text(self, text: torch.Tensor) -> torch.Tensor:
+        """Token ids [B, L] (indices into ``model.token_embedding``) -> text features [B, D]; the feature is read at
+        ``text.argmax(-1)`` (the [EOT] position) as in openai CLIP.encode_text (clip_official.py:211-218)."""
+        if not text.is_cuda:
+            raise RuntimeError("ClipModel.encode_text: CUDA tensor required (no CPU path)")
+        plan, vocab = self.text_plan(text.device), self.vocabulary(text.device)
+        B, L = text.shape
+        if L > plan.context:
+            raise ValueError(f"text length {L} exceeds the context length {plan.context}")
+        text = text.to(torch.int64).contiguous()
+        x0 = torch.empty(B, L, plan.d, device=text.device, dtype=torch.float32)
+        ops.token_embed(vocab.E, plan.pos, text, x0)
+        return plan.forward(workspace(text.device), x0, text.argmax(dim=-1).contiguous(), save=False)[0]
+
+    @torch.no_grad()
     def encode_keywords(self, keywords: torch.Tensor, keyword_num: int) -> torch.Tensor:
-        raise NotImplementedError("CLIP text tower: cascaded-branch row of SURVEY.md §8 (a9), not built yet")
+        """Keyword embeddings [B, K, W] -> text features [B, D] (clip_official.py:220-268): [SOT], the K keyword vectors,
+        [EOT]; the causal transformer is evaluated on those K+2 positions only.  Inference surface (no autograd): training
+        differentiates through ``KW_CascadedBranch.forward``, which fuses this with the quantiser."""
+        if not isinstance(keywords, torch.Tensor):
+            raise TypeError(f"Unknown keywords type {type(keywords)}")
+        if not keywords.is_cuda:
+            raise RuntimeError("ClipModel.encode_keywords: CUDA tensor required (no CPU path)")
+        plan, vocab = self.text_plan(keywords.device), self.vocabulary(keywords.device)
+        B, K, W = keywords.shape
+        assert K == keyword_num and W == plan.d
+        sot, eot = self.special_tokens()
+        return self._encode_rows(plan, vocab, keywords.float().contiguous(), sot, eot)
+
+    def _encode_rows(self, plan, vocab, keywords, sot, eot):
+        B, K, W = keywords.shape
+        dev = keywords.device
+        L = K + 2
+        x0 = torch.empty(B, L, W, device=dev, dtype=torch.float32)
+        tok = torch.zeros(B, L, device=dev, dtype=torch.int64)
+        tok[:, 0], tok[:, K + 1] = sot, eot
+        ops.token_embed(vocab.E, plan.pos, tok, x0)                       # every row = E[token] + pos
+        # rows 1..K: keywords + pos  (residual-add of the positional rows onto the given vectors)
+        pos_rows = plan.pos[1:K + 1].reshape(1, K * W).expand(B, K * W).contiguous()
+        mid = x0.view(B, L * W)[:, W:(K + 1) * W]
+        ops.rows_bias_act(keywords.view(B, K * W), None, pos_rows, K * W, ops.ACT_NONE, None, mid, rows=B, d=K * W, x_ld=K * W, y_ld=L * W)
+        return plan.forward(workspace(dev), x0, K + 1, save=False)[0]

@@ -224,6 +224,78 @@ int scb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, doubl
 int scb_retrieval_rank(const float* score, int64_t ld, int32_t rows, int32_t cols, const int64_t* cand_ids, const int64_t* answers,
                        int32_t* rank, int32_t* top1, void* stream);
 
+/* ---- cascaded branch (avssl/model/kwClip.py:857-916 KW_CascadedBranch.extract_hidden_states / forward) ------------------- */
+
+/* MultiheadAttentionAndNorm (avssl/module/kw_modules/TransformerModels.py:11-60) with the keyword [CLS] vectors as queries
+ * (kwClip.py:866-872): nq <= 8 learned queries shared by every utterance attend over that utterance's frames.
+ * q fp32 [nq][heads*head_dim] (already projected, unscaled); kv 16-bit [batch][Tk][kv_ld], K of head h at k_off + h*head_dim,
+ * V at v_off + h*head_dim; kv_len[b] = valid rows (NULL = all) -- the key_padding_mask of kwClip.py:870.
+ * probs fp32 [batch][heads][nq][Tk] (saved for the backward; zero beyond kv_len), ctx fp32 [batch][nq][heads*head_dim]. */
+int scb_mq_attention_fwd(const float* q, const void* kv, int32_t kv_fmt, int64_t kv_ld, int64_t kv_batch_stride, int32_t k_off, int32_t v_off,
+                         const int32_t* kv_len, int32_t batch, int32_t heads, int32_t head_dim, int32_t nq, int32_t Tk, float scale,
+                         float* probs, float* ctx, void* stream);
+/* Backward: dkv (16-bit, layout of kv; rows >= kv_len zeroed; only the K and V column ranges are written), dq fp32
+ * [nq][heads*head_dim] ACCUMULATED with atomics across the batch (zero it first). */
+int scb_mq_attention_bwd(const float* q, const void* kv, int32_t kv_fmt, int64_t kv_ld, int64_t kv_batch_stride, int32_t k_off, int32_t v_off,
+                         const int32_t* kv_len, int32_t batch, int32_t heads, int32_t head_dim, int32_t nq, int32_t Tk, float scale,
+                         const float* probs, const float* dctx, void* dkv, int32_t dkv_fmt, float* dq, void* stream);
+
+/* Kw_BatchNorm, eachKw + parallel (avssl/module/speechclip_c_modules/kw_bn.py:96-125): x fp32 [batch][n_kw][d] is viewed as
+ * BatchNorm1d over d*n_kw features with feature index f = dim * n_kw + kw (the permute/reshape of kw_bn.py:116-118).
+ * training != 0: batch statistics (biased variance), running stats updated with `momentum` (unbiased variance), save_mean /
+ * save_rstd [n_kw*d] kept for the backward; training == 0: running statistics. gamma/beta/running_* are indexed by f. */
+int scb_batchnorm_fwd(const float* x, float* y, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                      float* save_mean, float* save_rstd, int32_t batch, int32_t n_kw, int32_t d, float eps, float momentum,
+                      int32_t training, void* stream);
+int scb_batchnorm_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_rstd, float* dx,
+                      float* dgamma, float* dbeta, int32_t batch, int32_t n_kw, int32_t d, void* stream);
+
+/* Cosine similarity against the vocabulary + SimpleVectorQuantizer (kwClip.py:884-896; my_vector_quantizer.py:66-125).
+ * dots fp32 [rows][ld] holds kw @ E^T on entry and the masked cosine scores on exit (cos = dot / max(|kw||E_v|, 1e-8); the ids
+ * in mask_ids -> -inf, kwClip.py:886-888 / my_vector_quantizer.py:77-80); idx[r] = argmax_v (lowest index on ties);
+ * stats fp32 [rows][4] = {max cos, sum exp((cos-max)/temp), sum exp(cos-max), |kw_r|}.  The forward VALUE of
+ * subword_prob is the one-hot of idx (hard straight-through), so keywords = E[idx] (scb_keyword_embed).
+ * kw == emb_norm == NULL: the rows already hold final scores (SimpleVectorQuantizer used on its own); stats[..][3] = 0. */
+int scb_vq_forward(float* dots, const float* kw, const float* emb_norm, int32_t rows, int32_t vocab, int32_t d, int64_t ld,
+                   const int32_t* mask_ids, int32_t n_mask, float temp, int64_t* idx, float* stats, void* stream);
+/* g fp32 [rows][ld] = d loss / d subword_prob (= dkeywords @ E^T) on entry, d loss / d cos on exit (softmax(cos/temp) Jacobian,
+ * the straight-through path of my_vector_quantizer.py:104-110); t2[r] = <dcos_r, cos_r>. */
+int scb_vq_backward(float* g, const float* cos, int32_t rows, int32_t vocab, int64_t ld, const float* stats, float temp, float* t2,
+                    void* stream);
+/* Cosine-similarity backward wrt the keyword rows: dkw = t1 / |kw| - t2 * kw / |kw|^2 with t1 = dcos @ (E / |E|). */
+int scb_cosine_bwd_rows(const float* t1, const float* t2, const float* kw, const float* stats, float* dkw, int32_t rows, int32_t d,
+                        void* stream);
+/* Logging statistics of my_vector_quantizer.py:84-118: hist[v] += [idx == v], avg[v] += softmax(cos)[v] (both ACCUMULATE over
+ * rows; zero first), ent[r] = -sum_v p log(p + 1e-9). */
+int scb_vq_diagnostics(const float* cos, int32_t rows, int32_t vocab, int64_t ld, const float* stats, const int64_t* idx, float* hist,
+                       float* avg, float* ent, void* stream);
+/* Text-tower input of ClipModel.encode_keywords (avssl/module/clip_official.py:220-268): x0 fp32 [batch][n_kw+2][d] =
+ * {E[sot], E[idx[b][0..n_kw)], E[eot]} + positional rows 0..n_kw+1; keywords fp32 [batch][n_kw][d] = E[idx] (may be NULL). */
+int scb_keyword_embed(const float* emb, const float* pos, const int64_t* idx, int64_t sot, int64_t eot, int32_t batch, int32_t n_kw, int32_t d,
+                      float* x0, float* keywords, void* stream);
+/* ClipModel.encode_text input (avssl/module/clip_official.py:211-218 -> openai CLIP.encode_text): x fp32 [batch][L][d] = E[tokens] + positional rows. */
+int scb_token_embed(const float* emb, const float* pos, const int64_t* tokens, int32_t batch, int32_t L, int32_t d, int64_t vocab, float* x,
+                    void* stream);
+/* out[b] = src[b][row[b]] (the `x[arange(B), text.argmax(-1)]` pick of the EOT position in openai CLIP.encode_text). */
+int scb_gather_rows(const float* src, const int64_t* row, int32_t batch, int32_t L, int32_t d, float* out, void* stream);
+/* dQ/dK/dV of softmax attention over short sequences (the n_kw+2 live positions of the causal CLIP text tower):
+ * qkv 16-bit [batch][L][3*heads*head_dim], dctx fp32 [batch][L][heads*head_dim], dqkv fp32 (layout of qkv). L <= 128. */
+int scb_attention_small_bwd(const void* qkv, int32_t fmt, const float* dctx, float* dqkv, int32_t batch, int32_t L, int32_t heads,
+                            int32_t head_dim, float scale, int32_t causal, void* stream);
+/* Row softmax for attention with one wide head (MultiheadAttentionAndNorm has nhead = 1, head_dim = d_model, which the
+ * flash kernels do not cover): out[r][c] = softmax(s[r][0..len))[c] for c < len[r / rows_per_batch] (len NULL = cols), zero for
+ * len <= c < out_cols.  s fp32 [rows][ld] (already scaled), out 16-bit [rows][out_ld]. */
+int scb_softmax_rows(const float* s, int64_t ld, int64_t rows, int32_t rows_per_batch, const int32_t* len, int32_t cols, void* out, int32_t fmt,
+                     int64_t out_ld, int32_t out_cols, void* stream);
+/* Split fp32 rows [rows][cols] (row stride src_ld) into TF32-exact halves hi / lo = x - hi, written as dst [rows][3*cols]:
+ * role 0 (left operand) = [hi | lo | hi], role 1 (right operand) = [hi | hi | lo].  One SCB_F32 scb_gemm over k = 3*cols of a
+ * role-0 and a role-1 buffer yields the product to ~2^-21 relative -- used for the keyword-vs-vocabulary scores whose argmax
+ * selects the token (kwClip.py:890-911), where plain TF32 rounding could move the index. */
+int scb_split_tf32(const float* src, int64_t src_ld, float* dst, int64_t rows, int32_t cols, int32_t role, void* stream);
+/* out = act(pre) on 16-bit rows (n even), and dx = dy * act'(pre) with a 16-bit pre-activation. */
+int scb_act16_fwd(const void* pre, int32_t fmt, int32_t act, void* out, int64_t n, void* stream);
+int scb_act_bwd(const float* dy, const void* pre, int32_t fmt, int32_t act, float* dx, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,8 @@ class ClipCfg:
             return ClipCfg(224, 14, 1024, 24, 16, 768, 768, 12, 12)
         if name == "tiny":
             return ClipCfg(32, 16, 64, 2, 4, 32, 32, 2, 4, 16, 64)
+        if name == "tiny_c":
+            return ClipCfg(32, 16, 64, 2, 4, 32, 64, 2, 4, 16, 96)
         raise KeyError(name)
 
 

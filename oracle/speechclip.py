@@ -154,13 +154,15 @@ class KwBatchNorm(nn.Module):
         return x.reshape(B, self.kw_dim, self.kw_num).permute(0, 2, 1)
 
 
-def simple_vector_quantizer(x, temp, training, prob_msk=(0, 2, 3)):
-    """``SimpleVectorQuantizer.forward`` (my_vector_quantizer.py:64-165) with use_gumbel=False, hard=True, time_first=True."""
+def simple_vector_quantizer(x, temp, training, prob_msk=(0, 2, 3), force_idx=None):
+    """``SimpleVectorQuantizer.forward`` (my_vector_quantizer.py:64-165) with use_gumbel=False, hard=True, time_first=True.
+    ``force_idx`` (test hook, not in the reference): use these ids instead of the argmax, so that a run whose upstream
+    features differ in the last bits can be compared downstream even where two scores are within rounding of each other."""
     bsz, tsz, fsz = x.shape
     x = x.reshape(bsz * tsz, fsz).clone()
     for i in prob_msk:
         x[:, i] = x[:, i] + float("-inf")
-    k = x.argmax(-1)
+    k = x.argmax(-1) if force_idx is None else force_idx.reshape(-1)
     hard_x = torch.zeros_like(x).scatter_(-1, k.view(-1, 1), 1.0)
     hard_probs = hard_x.float().mean(0)
     result = {"num_vars": fsz}
@@ -198,7 +200,7 @@ class CascadedBranch(nn.Module):
         self.vq_temp = vq_temp
         self.sot_token, self.eot_token = sot_token, eot_token
 
-    def forward(self, audio_feat, audio_len, training=True, collect=None):
+    def forward(self, audio_feat, audio_len, training=True, collect=None, force_idx=None):
         B, T = audio_feat.shape[:2]
         K = self.keyword_num
         src = torch.cat([self.cls.expand(B, K, -1), audio_feat], 1)                     # kwClip.py:870-872
@@ -208,7 +210,7 @@ class CascadedBranch(nn.Module):
         kw = self.bn_layer(kw)                                                             # :886-887
         emb = self.clip_model[0].token_embedding.weight
         cos = torch.stack([F.cosine_similarity(kw[:, i, :].unsqueeze(-1), emb.t().unsqueeze(0), dim=1) for i in range(K)], 1)  # :890-900
-        vq = simple_vector_quantizer(cos, self.vq_temp, training)                          # :909
+        vq = simple_vector_quantizer(cos, self.vq_temp, training, force_idx=force_idx)     # :909
         keywords = vq["subword_prob"] @ emb                                                # :911
         feat = self.clip_model[0].encode_keywords(keywords, K, self.sot_token, self.eot_token)  # :914
         if collect is not None:
@@ -292,14 +294,18 @@ class _Criterion(nn.Module):
 class SpeechClipOracle(nn.Module):
     """Parallel SpeechCLIP (KWClip_GeneralTransformer with parallel_objective_weight > 0), eval-mode arithmetic."""
 
-    def __init__(self, hubert_cfg: ohubert.HubertCfg, clip_cfg: oclip.ClipCfg, branch_args: dict,
-                 loss_args: Optional[dict] = None, normalize_hiddenstates: bool = False):
+    def __init__(self, hubert_cfg: ohubert.HubertCfg, clip_cfg: oclip.ClipCfg, branch_args: Optional[dict],
+                 loss_args: Optional[dict] = None, normalize_hiddenstates: bool = False, cascaded_args: Optional[dict] = None):
         super().__init__()
         self.audio_encoder = _AudioEncoder(hubert_cfg)
         self.clip = _Clip(clip_cfg)
         self.criterion = _Criterion(**(loss_args or {}))
-        self.parallel_branch = ParallelBranch(hubert_cfg.embed_dim, clip_cfg.t_width,
-                                              **{k: v for k, v in branch_args.items() if k != "d_model"})
+        self.parallel_branch = self.cascaded_branch = None
+        if branch_args is not None:
+            self.parallel_branch = ParallelBranch(hubert_cfg.embed_dim, clip_cfg.t_width,
+                                                  **{k: v for k, v in branch_args.items() if k != "d_model"})
+        if cascaded_args is not None:   # spchclp_c.yaml: cascaded_objective_weight = 1 (kwClip.py:1125-1137)
+            self.cascaded_branch = CascadedBranch(self.clip.model, hubert_cfg.embed_dim, **cascaded_args)
         self.normalize_hiddenstates = normalize_hiddenstates
         self.max_audio_len = 102400
 
@@ -318,15 +324,25 @@ class SpeechClipOracle(nn.Module):
         """kwClip.py:1385-1478 → dict of L2-normalised features."""
         audio_feat, audio_len = self.forward_audio(wavs)
         image_feat = self.clip.model.encode_image(image)
-        p = self.parallel_branch(audio_feat, audio_len)
         image_feat = image_feat / image_feat.norm(dim=-1, keepdim=True)
-        p = p / p.norm(dim=-1, keepdim=True)
-        return {"id": ids, "image_feat": image_feat, "parallel_audio_feat": p,
-                "audio_feat": audio_feat, "audio_len": audio_len}
+        out = {"id": ids, "image_feat": image_feat, "audio_feat": audio_feat, "audio_len": audio_len}
+        if self.cascaded_branch is not None:
+            collect = {}
+            c, vq, keywords = self.cascaded_branch(audio_feat, audio_len, training=self.cascaded_training, collect=collect,
+                                                   force_idx=self.force_idx)
+            out.update(cascaded_audio_feat=c / c.norm(dim=-1, keepdim=True), vq_results=vq, keywords=keywords, cascaded_collect=collect)
+        if self.parallel_branch is not None:
+            p = self.parallel_branch(audio_feat, audio_len)
+            out["parallel_audio_feat"] = p / p.norm(dim=-1, keepdim=True)
+        return out
+
+    force_idx = None           # test hook, see simple_vector_quantizer
+    cascaded_training = True   # straight-through softmax path of the quantiser (module.training in the reference)
 
     def compute_loss(self, feats: dict, return_logits=False):
-        """kwClip.py:1248-1297 with parallel_objective_weight = 1."""
-        return masked_contrastive_loss(feats["parallel_audio_feat"].float(), feats["image_feat"].float(), feats["id"],
+        """kwClip.py:1248-1297 with the active objective's weight = 1 (cascaded XOR parallel in every shipped config)."""
+        key = "parallel_audio_feat" if self.parallel_branch is not None else "cascaded_audio_feat"
+        return masked_contrastive_loss(feats[key].float(), feats["image_feat"].float(), feats["id"],
                                        self.criterion.multiplier(), return_logits=return_logits)
 
     def encode_speech(self, wavs):

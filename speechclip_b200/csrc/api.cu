@@ -213,4 +213,70 @@ int scb_retrieval_rank(const float* score, int64_t ld, int32_t rows, int32_t col
                              ST);
 }
 
+int scb_mq_attention_fwd(const float* q, const void* kv, int32_t kv_fmt, int64_t kv_ld, int64_t kv_batch_stride, int32_t k_off, int32_t v_off,
+                         const int32_t* kv_len, int32_t batch, int32_t heads, int32_t head_dim, int32_t nq, int32_t Tk, float scale,
+                         float* probs, float* ctx, void* stream) {
+  return scb::mq_attention_fwd(q, kv, kv_fmt, kv_ld, kv_batch_stride, k_off, v_off, kv_len, batch, heads, head_dim, nq, Tk, scale, probs, ctx,
+                               ST);
+}
+int scb_mq_attention_bwd(const float* q, const void* kv, int32_t kv_fmt, int64_t kv_ld, int64_t kv_batch_stride, int32_t k_off, int32_t v_off,
+                         const int32_t* kv_len, int32_t batch, int32_t heads, int32_t head_dim, int32_t nq, int32_t Tk, float scale,
+                         const float* probs, const float* dctx, void* dkv, int32_t dkv_fmt, float* dq, void* stream) {
+  return scb::mq_attention_bwd(q, kv, kv_fmt, kv_ld, kv_batch_stride, k_off, v_off, kv_len, batch, heads, head_dim, nq, Tk, scale, probs, dctx,
+                               dkv, dkv_fmt, dq, ST);
+}
+int scb_batchnorm_fwd(const float* x, float* y, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                      float* save_mean, float* save_rstd, int32_t batch, int32_t n_kw, int32_t d, float eps, float momentum,
+                      int32_t training, void* stream) {
+  return scb::batchnorm_fwd(x, y, gamma, beta, running_mean, running_var, save_mean, save_rstd, batch, n_kw, d, eps, momentum, training, ST);
+}
+int scb_batchnorm_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_rstd, float* dx,
+                      float* dgamma, float* dbeta, int32_t batch, int32_t n_kw, int32_t d, void* stream) {
+  return scb::batchnorm_bwd(dy, x, gamma, save_mean, save_rstd, dx, dgamma, dbeta, batch, n_kw, d, ST);
+}
+int scb_vq_forward(float* dots, const float* kw, const float* emb_norm, int32_t rows, int32_t vocab, int32_t d, int64_t ld,
+                   const int32_t* mask_ids, int32_t n_mask, float temp, int64_t* idx, float* stats, void* stream) {
+  return scb::vq_forward(dots, kw, emb_norm, rows, vocab, d, ld, mask_ids, n_mask, temp, reinterpret_cast<ll*>(idx), stats, ST);
+}
+int scb_vq_backward(float* g, const float* cos, int32_t rows, int32_t vocab, int64_t ld, const float* stats, float temp, float* t2,
+                    void* stream) {
+  return scb::vq_backward(g, cos, rows, vocab, ld, stats, temp, t2, ST);
+}
+int scb_cosine_bwd_rows(const float* t1, const float* t2, const float* kw, const float* stats, float* dkw, int32_t rows, int32_t d,
+                        void* stream) {
+  return scb::cosine_bwd_rows(t1, t2, kw, stats, dkw, rows, d, ST);
+}
+int scb_vq_diagnostics(const float* cos, int32_t rows, int32_t vocab, int64_t ld, const float* stats, const int64_t* idx, float* hist,
+                       float* avg, float* ent, void* stream) {
+  return scb::vq_diagnostics(cos, rows, vocab, ld, stats, reinterpret_cast<const ll*>(idx), hist, avg, ent, ST);
+}
+int scb_keyword_embed(const float* emb, const float* pos, const int64_t* idx, int64_t sot, int64_t eot, int32_t batch, int32_t n_kw, int32_t d,
+                      float* x0, float* keywords, void* stream) {
+  return scb::keyword_embed(emb, pos, reinterpret_cast<const ll*>(idx), sot, eot, batch, n_kw, d, x0, keywords, ST);
+}
+int scb_attention_small_bwd(const void* qkv, int32_t fmt, const float* dctx, float* dqkv, int32_t batch, int32_t L, int32_t heads,
+                            int32_t head_dim, float scale, int32_t causal, void* stream) {
+  return scb::attention_small_bwd(qkv, fmt, dctx, dqkv, batch, L, heads, head_dim, scale, causal, ST);
+}
+int scb_token_embed(const float* emb, const float* pos, const int64_t* tokens, int32_t batch, int32_t L, int32_t d, int64_t vocab, float* x,
+                    void* stream) {
+  return scb::token_embed(emb, pos, reinterpret_cast<const ll*>(tokens), batch, L, d, vocab, x, ST);
+}
+int scb_gather_rows(const float* src, const int64_t* row, int32_t batch, int32_t L, int32_t d, float* out, void* stream) {
+  return scb::gather_rows(src, reinterpret_cast<const ll*>(row), batch, L, d, out, ST);
+}
+int scb_softmax_rows(const float* s, int64_t ld, int64_t rows, int32_t rows_per_batch, const int32_t* len, int32_t cols, void* out, int32_t fmt,
+                     int64_t out_ld, int32_t out_cols, void* stream) {
+  return scb::softmax_rows(s, ld, rows, rows_per_batch, len, cols, out, fmt, out_ld, out_cols, ST);
+}
+int scb_split_tf32(const float* src, int64_t src_ld, float* dst, int64_t rows, int32_t cols, int32_t role, void* stream) {
+  return scb::split_tf32(src, src_ld, dst, rows, cols, role, ST);
+}
+int scb_act16_fwd(const void* pre, int32_t fmt, int32_t act, void* out, int64_t n, void* stream) {
+  return scb::act16_fwd(pre, fmt, act, out, n, ST);
+}
+int scb_act_bwd(const float* dy, const void* pre, int32_t fmt, int32_t act, float* dx, int64_t n, void* stream) {
+  return scb::act_bwd(dy, pre, fmt, act, dx, n, ST);
+}
+
 }  // extern "C"

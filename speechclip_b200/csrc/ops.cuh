@@ -70,4 +70,31 @@ int gelu_bwd(const float* dy, const float* pre, float* dx, long long n, cudaStre
 int column_sum(const void* in, int in_dtype, long long ld, long long rows, int cols, float* out, float beta, cudaStream_t st);
 int retrieval_rank(const float* score, long long ld, int rows, int cols, const long long* cand_ids, const long long* answers, int* rank,
                    int* top1, cudaStream_t st);
+// cascaded.cu
+int mq_attention_fwd(const float* q, const void* kv, int kv_fmt, long long kv_ld, long long kv_bs, int k_off, int v_off, const int* kv_len,
+                     int batch, int heads, int head_dim, int nq, int Tk, float scale, float* probs, float* ctx, cudaStream_t st);
+int mq_attention_bwd(const float* q, const void* kv, int kv_fmt, long long kv_ld, long long kv_bs, int k_off, int v_off, const int* kv_len,
+                     int batch, int heads, int head_dim, int nq, int Tk, float scale, const float* probs, const float* dctx, void* dkv,
+                     int dkv_fmt, float* dq, cudaStream_t st);
+int batchnorm_fwd(const float* x, float* y, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                  float* save_mean, float* save_rstd, int B, int NK, int D, float eps, float momentum, int training, cudaStream_t st);
+int batchnorm_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_rstd, float* dx,
+                  float* dgamma, float* dbeta, int B, int NK, int D, cudaStream_t st);
+int vq_forward(float* dots, const float* kw, const float* emb_norm, int R, int V, int D, long long ld, const int* mask_ids, int n_mask,
+               float temp, long long* idx, float* stats, cudaStream_t st);
+int vq_backward(float* g, const float* cos, int R, int V, long long ld, const float* stats, float temp, float* t2, cudaStream_t st);
+int cosine_bwd_rows(const float* t1, const float* t2, const float* kw, const float* stats, float* dkw, int R, int D, cudaStream_t st);
+int vq_diagnostics(const float* cos, int R, int V, long long ld, const float* stats, const long long* idx, float* hist, float* avg, float* ent,
+                   cudaStream_t st);
+int keyword_embed(const float* emb, const float* pos, const long long* idx, long long sot, long long eot, int B, int K, int D, float* x0,
+                  float* keywords, cudaStream_t st);
+int attention_small_bwd(const void* qkv, int fmt, const float* dctx, float* dqkv, int batch, int L, int heads, int head_dim, float scale,
+                        int causal, cudaStream_t st);
+int token_embed(const float* emb, const float* pos, const long long* tokens, int B, int L, int D, long long vocab, float* x, cudaStream_t st);
+int gather_rows(const float* src, const long long* row, int B, int L, int D, float* out, cudaStream_t st);
+int softmax_rows(const float* s, long long ld, long long rows, int rows_per_batch, const int* len, int cols, void* out, int fmt,
+                 long long out_ld, int out_cols, cudaStream_t st);
+int split_tf32(const float* src, long long src_ld, float* dst, long long rows, int cols, int role, cudaStream_t st);
+int act16_fwd(const void* pre, int fmt, int act, void* out, long long n, cudaStream_t st);
+int act_bwd(const float* dy, const void* pre, int fmt, int act, float* dx, long long n, cudaStream_t st);
 }  // namespace scb

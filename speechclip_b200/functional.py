@@ -133,6 +133,115 @@ class ParallelBranchFn(torch.autograd.Function):
         return (dfeat, None, None, None) + tuple(g[name] if p[name].requires_grad else None for name in PARAM_ORDER)
 
 
+# ---------------------------------------------------------------------------------------------------- cascaded branch
+class CascadedBranchFn(torch.autograd.Function):
+    """kwClip.py:857-916 end to end (see speechclip_b200/cascaded.py).  ``rt`` carries the frozen pieces and switches:
+    dict(vocab, text, bn_buffers, temp, sot, eot, training, need_grad).  Returns (text feature, keywords, cos, idx, stats); only the
+    first output is differentiable."""
+
+    @staticmethod
+    def forward(ctx, audio_feat, kv_len, head, arena, rt, *params):
+        from .cascaded import PARAM_ORDER as ORDER
+        _require_cuda(audio_feat, "KW_CascadedBranch")
+        p = dict(zip(ORDER, params))
+        audio_feat = audio_feat.contiguous()
+        need_grad = rt["need_grad"] and (audio_feat.requires_grad or any(t.requires_grad for t in params))
+        feat, keywords, cos, idx, stats, saved = head.forward(
+            workspace(audio_feat.device), p, audio_feat.detach(), kv_len, rt["bn_buffers"], rt["vocab"], rt["text"], rt["temp"],
+            rt["sot"], rt["eot"], rt["training"], need_grad)
+        ctx.head, ctx.arena, ctx.saved, ctx.params, ctx.rt = head, arena, saved, params, rt
+        ctx.need_dfeat = audio_feat.requires_grad
+        ctx.buf = arena.grad_buffer_index() if arena else 0
+        ctx.mark_non_differentiable(keywords, cos, idx, stats)
+        return feat, keywords, cos, idx, stats
+
+    @staticmethod
+    def backward(ctx, dfeat, *_):
+        from .cascaded import PARAM_ORDER as ORDER
+        head, arena, params, rt = ctx.head, ctx.arena, ctx.params, ctx.rt
+        if ctx.saved.get("text") is None:
+            raise RuntimeError("KW_CascadedBranch: backward through an eval-mode forward (no activations were kept)")
+        p = dict(zip(ORDER, params))
+        g = {name: _grad_like(t, arena, ctx.buf) for name, t in p.items()}
+        dx = head.backward(workspace(dfeat.device), p, ctx.saved, dfeat.contiguous(), g, rt["vocab"], rt["text"], need_dfeat=ctx.need_dfeat)
+        ctx.saved = None
+        return (dx, None, None, None, None) + tuple(g[name] if p[name].requires_grad else None for name in ORDER)
+
+
+class KwBatchNormFn(torch.autograd.Function):
+    """Kw_BatchNorm (eachKw, parallel) as a standalone op: kw_bn.py:96-125."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, training):
+        _require_cuda(x, "Kw_BatchNorm")
+        x = x.contiguous().float()
+        B, K, W = x.shape
+        y = torch.empty_like(x)
+        mean = rstd = None
+        if training:
+            mean, rstd = torch.empty(K * W, device=x.device), torch.empty(K * W, device=x.device)
+        ops.batchnorm_fwd(x, y, weight, bias, running_mean, running_var, mean, rstd, eps, momentum, training)
+        ctx.save_for_backward(x, weight)
+        ctx.stats = (mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        mean, rstd = ctx.stats
+        if mean is None:
+            raise RuntimeError("Kw_BatchNorm: backward through an eval-mode forward is not supported")
+        dx, dg, db = torch.empty_like(x), torch.empty_like(weight), torch.empty_like(weight)
+        ops.batchnorm_bwd(dy.contiguous().float(), x, weight, mean, rstd, dx, dg, db)
+        return dx, dg, db, None, None, None, None, None
+
+
+class VectorQuantizeFn(torch.autograd.Function):
+    """SimpleVectorQuantizer on ready-made scores (my_vector_quantizer.py:66-135): returns (scores with masked ids = -inf,
+    idx, stats); the caller builds the one-hot ``subword_prob``.  The gradient arriving at ``subword_prob`` is routed through
+    softmax(scores / temp) as the hard straight-through estimator prescribes."""
+
+    @staticmethod
+    def forward(ctx, scores, mask_ids, temp):
+        _require_cuda(scores, "SimpleVectorQuantizer")
+        B, K, V = scores.shape
+        Vp = (V + 3) // 4 * 4
+        cos = torch.empty(B * K, Vp, device=scores.device, dtype=torch.float32)[:, :V]
+        cos.copy_(scores.reshape(B * K, V))
+        idx = torch.empty(B, K, device=scores.device, dtype=torch.int64)
+        stats = torch.empty(B * K, 4, device=scores.device, dtype=torch.float32)
+        ops.vq_forward(cos, None, None, mask_ids, temp, idx, stats)
+        ctx.save_for_backward(cos, stats)
+        ctx.temp = temp
+        ctx.mark_non_differentiable(idx, stats)
+        return cos, idx, stats
+
+    @staticmethod
+    def backward(ctx, dcos_unused, *_):
+        raise RuntimeError("SimpleVectorQuantizer: differentiate through subword_prob (OneHotSTFn), not through the masked scores")
+
+
+class OneHotSTFn(torch.autograd.Function):
+    """subword_prob = one_hot(idx) + softmax(cos / temp) - softmax(cos / temp).detach()  (my_vector_quantizer.py:104-110)."""
+
+    @staticmethod
+    def forward(ctx, scores, cos, idx, stats, temp):
+        B, K, V = scores.shape
+        ctx.save_for_backward(cos, stats)
+        ctx.temp, ctx.shape = temp, (B, K, V)
+        return torch.zeros(B * K, V, device=scores.device).scatter_(1, idx.view(-1, 1), 1.0).view(B, K, V)
+
+    @staticmethod
+    def backward(ctx, dprob):
+        cos, stats = ctx.saved_tensors
+        B, K, V = ctx.shape
+        g = torch.empty(B * K, cos.stride(0), device=cos.device, dtype=torch.float32)[:, :V]
+        g.copy_(dprob.reshape(B * K, V))
+        t2 = torch.empty(B * K, device=cos.device, dtype=torch.float32)
+        ops.vq_backward(g, cos, stats, ctx.temp, t2)
+        return g.reshape(B, K, V), None, None, None, None
+
+
 # ---------------------------------------------------------------------------------------------------- L2 normalise
 class L2NormFn(torch.autograd.Function):
     """x / x.norm(dim=-1, keepdim=True)  (kwClip.py:1436,1451-1453)."""

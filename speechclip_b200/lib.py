@@ -123,6 +123,22 @@ def _declare(lib):
         "scb_infonce": [vp, vp, vp, i32, i32, vp, f32, f32, i32, i32, i32, i32, vp, vp, f32, vp, vp, vp, vp, vp, i64, vp],
         "scb_adam_step": [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, f32, f32, i32, vp, vp, vp],
         "scb_retrieval_rank": [vp, i64, i32, i32, vp, vp, vp, vp, vp],
+        "scb_mq_attention_fwd": [vp, vp, i32, i64, i64, i32, i32, vp, i32, i32, i32, i32, i32, f32, vp, vp, vp],
+        "scb_mq_attention_bwd": [vp, vp, i32, i64, i64, i32, i32, vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, i32, vp, vp],
+        "scb_batchnorm_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, i32, vp],
+        "scb_batchnorm_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
+        "scb_vq_forward": [vp, vp, vp, i32, i32, i32, i64, vp, i32, f32, vp, vp, vp],
+        "scb_vq_backward": [vp, vp, i32, i32, i64, vp, f32, vp, vp],
+        "scb_cosine_bwd_rows": [vp, vp, vp, vp, vp, i32, i32, vp],
+        "scb_vq_diagnostics": [vp, i32, i32, i64, vp, vp, vp, vp, vp, vp],
+        "scb_keyword_embed": [vp, vp, vp, i64, i64, i32, i32, i32, vp, vp, vp],
+        "scb_attention_small_bwd": [vp, i32, vp, vp, i32, i32, i32, i32, f32, i32, vp],
+        "scb_token_embed": [vp, vp, vp, i32, i32, i32, i64, vp, vp],
+        "scb_gather_rows": [vp, vp, i32, i32, i32, vp, vp],
+        "scb_softmax_rows": [vp, i64, i64, i32, vp, i32, vp, i32, i64, i32, vp],
+        "scb_split_tf32": [vp, i64, vp, i64, i32, i32, vp],
+        "scb_act16_fwd": [vp, i32, i32, vp, i64, vp],
+        "scb_act_bwd": [vp, vp, i32, i32, vp, i64, vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)
@@ -135,7 +151,9 @@ EXPORTS = ["scb_abi_version", "scb_last_error", "scb_launch_count", "scb_conv0_s
            "scb_lengths_to_i32", "scb_wav_prepare", "scb_conv0_groupnorm_gelu", "scb_conv0_layernorm_gelu", "scb_posconv_pack", "scb_patchify",
            "scb_broadcast_row", "scb_cast_rows", "scb_transpose", "scb_layernorm_fwd", "scb_layernorm_bwd", "scb_l2norm_fwd",
            "scb_l2norm_bwd", "scb_weighted_sum_fwd", "scb_weighted_sum_bwd", "scb_rows_bias_act", "scb_gelu_bwd", "scb_column_sum",
-           "scb_infonce", "scb_adam_step", "scb_retrieval_rank"]
+           "scb_infonce", "scb_adam_step", "scb_retrieval_rank", "scb_mq_attention_fwd", "scb_mq_attention_bwd", "scb_batchnorm_fwd",
+           "scb_batchnorm_bwd", "scb_vq_forward", "scb_vq_backward", "scb_cosine_bwd_rows", "scb_vq_diagnostics", "scb_keyword_embed",
+           "scb_attention_small_bwd", "scb_token_embed", "scb_gather_rows", "scb_softmax_rows", "scb_split_tf32", "scb_act16_fwd", "scb_act_bwd"]
 
 
 def load():

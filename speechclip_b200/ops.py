@@ -296,3 +296,90 @@ def retrieval_rank(score, cand_ids, answers, rank, top1):
     rows, cols = score.shape
     assert score.dtype == torch.float32 and score.stride(1) == 1
     _call("scb_retrieval_rank", _p(score), score.stride(0), rows, cols, _p(cand_ids), _p(answers), _p(rank), _p(top1))
+
+
+# ------------------------------------------------------------------------------------------------ cascaded branch
+def mq_attention_fwd(q, kv, k_off, v_off, kv_len, heads, hd, scale, probs, ctx32):
+    """q fp32 [NQ, heads*hd]; kv 16-bit [B, Tk, ld]; probs fp32 [B, heads, NQ, Tk]; ctx32 fp32 [B, NQ, heads*hd]."""
+    B, Tk = kv.shape[0], kv.shape[1]
+    _call("scb_mq_attention_fwd", _p(q), _p(kv), _DT[kv.dtype], kv.stride(1), kv.stride(0), k_off, v_off, _p(kv_len), B, heads, hd,
+          q.shape[0], Tk, scale, _p(probs), _p(ctx32))
+
+
+def mq_attention_bwd(q, kv, k_off, v_off, kv_len, heads, hd, scale, probs, dctx, dkv, dq):
+    B, Tk = kv.shape[0], kv.shape[1]
+    assert dkv.shape == kv.shape and dkv.stride() == kv.stride()
+    _call("scb_mq_attention_bwd", _p(q), _p(kv), _DT[kv.dtype], kv.stride(1), kv.stride(0), k_off, v_off, _p(kv_len), B, heads, hd,
+          q.shape[0], Tk, scale, _p(probs), _p(dctx), _p(dkv), _DT[dkv.dtype], _p(dq))
+
+
+def batchnorm_fwd(x, y, gamma, beta, running_mean, running_var, save_mean, save_rstd, eps, momentum, training):
+    B, NK, D = x.shape
+    _call("scb_batchnorm_fwd", _p(x), _p(y), _p(gamma), _p(beta), _p(running_mean), _p(running_var), _p(save_mean), _p(save_rstd),
+          B, NK, D, eps, momentum, int(training))
+
+
+def batchnorm_bwd(dy, x, gamma, save_mean, save_rstd, dx, dgamma, dbeta):
+    B, NK, D = x.shape
+    _call("scb_batchnorm_bwd", _p(dy), _p(x), _p(gamma), _p(save_mean), _p(save_rstd), _p(dx), _p(dgamma), _p(dbeta), B, NK, D)
+
+
+def split_tf32(src, dst, role):
+    rows, cols = src.shape
+    assert dst.shape == (rows, 3 * cols) and dst.is_contiguous() and src.stride(1) == 1
+    _call("scb_split_tf32", _p(src), src.stride(0), _p(dst), rows, cols, role)
+    return dst
+
+
+def vq_forward(dots, kw, emb_norm, mask_ids, temp, idx, stats):
+    R, V = dots.shape
+    _call("scb_vq_forward", _p(dots), _p(kw), _p(emb_norm), R, V, kw.shape[1] if kw is not None else 0, dots.stride(0), _p(mask_ids),
+          0 if mask_ids is None else mask_ids.numel(), temp, _p(idx), _p(stats))
+
+
+def vq_backward(g, cos, stats, temp, t2):
+    R, V = g.shape
+    assert g.stride(0) == cos.stride(0)
+    _call("scb_vq_backward", _p(g), _p(cos), R, V, g.stride(0), _p(stats), temp, _p(t2))
+
+
+def cosine_bwd_rows(t1, t2, kw, stats, dkw):
+    R, D = kw.shape
+    _call("scb_cosine_bwd_rows", _p(t1), _p(t2), _p(kw), _p(stats), _p(dkw), R, D)
+
+
+def vq_diagnostics(cos, stats, idx, hist, avg, ent):
+    R, V = cos.shape
+    _call("scb_vq_diagnostics", _p(cos), R, V, cos.stride(0), _p(stats), _p(idx), _p(hist), _p(avg), _p(ent))
+
+
+def keyword_embed(emb, pos, idx, sot, eot, x0, keywords):
+    B, K = idx.shape
+    _call("scb_keyword_embed", _p(emb), _p(pos), _p(idx), sot, eot, B, K, emb.shape[1], _p(x0), _p(keywords))
+
+
+def attention_small_bwd(qkv, dctx, dqkv, B, L, heads, hd, scale, causal):
+    _call("scb_attention_small_bwd", _p(qkv), _DT[qkv.dtype], _p(dctx), _p(dqkv), B, L, heads, hd, scale, int(causal))
+
+
+def act16_fwd(pre, act, out):
+    _call("scb_act16_fwd", _p(pre), _DT[pre.dtype], act, _p(out), pre.numel())
+
+
+def act_bwd(dy, pre, act, dx):
+    _call("scb_act_bwd", _p(dy), _p(pre), _DT[pre.dtype], act, _p(dx), pre.numel())
+
+
+def token_embed(emb, pos, tokens, x):
+    B, L = tokens.shape
+    _call("scb_token_embed", _p(emb), _p(pos), _p(tokens), B, L, emb.shape[1], emb.shape[0], _p(x))
+
+
+def gather_rows(src, row, out):
+    B, L, D = src.shape
+    _call("scb_gather_rows", _p(src), _p(row), B, L, D, _p(out))
+
+
+def softmax_rows(s, rows_per_batch, lens, cols, out, out_cols):
+    """s fp32 [rows, ld]; lens int32 [rows / rows_per_batch] or None; out 16-bit [rows, out_ld]."""
+    _call("scb_softmax_rows", _p(s), s.stride(0), s.shape[0], rows_per_batch, _p(lens), cols, _p(out), _DT[out.dtype], out.stride(0), out_cols)

@@ -121,6 +121,8 @@ class ClipArch:
             return ClipArch(224, 14, 1024, 24, 16, 768, 768, 12, 12)
         if name == "tiny":
             return ClipArch(32, 16, 64, 2, 4, 32, 32, 2, 4, 16, 64)
+        if name == "tiny_c":      # tiny image tower + a text tower the cascaded branch can run (head_dim 16)
+            return ClipArch(32, 16, 64, 2, 4, 32, 64, 2, 4, 16, 96)
         raise KeyError(name)
 
 

@@ -83,8 +83,17 @@ def test_model_builds_with_reference_state_dict_layout():
 
 def test_unsupported_configs_fail_loudly():
     from avssl.model import KWClip_GeneralTransformer
-    cfg = parallel_config("tiny")
-    cfg["model_settings"]["cascaded_objective_weight"] = 1.0
+    from speechclip_b200.configs import cascaded_config
+    cfg = cascaded_config("tiny")
+    cfg["model_settings"]["cascaded_branch"]["transformer_type"] = "TransformerEncoder"
+    with pytest.raises(NotImplementedError):
+        KWClip_GeneralTransformer(OrderedNamespace(cfg))
+    cfg = cascaded_config("tiny")
+    cfg["model_settings"]["cascaded_branch"]["vq"]["args"]["use_gumbel"] = True
+    with pytest.raises(NotImplementedError):
+        KWClip_GeneralTransformer(OrderedNamespace(cfg))
+    cfg = cascaded_config("tiny")
+    cfg["model_settings"]["cascaded_branch"]["keyword"]["batchnorms"]["parallel"] = False
     with pytest.raises(NotImplementedError):
         KWClip_GeneralTransformer(OrderedNamespace(cfg))
     cfg = parallel_config("tiny")
@@ -97,6 +106,34 @@ def test_unsupported_configs_fail_loudly():
         KWClip_GeneralTransformer(OrderedNamespace(cfg))
 
 
+def test_cascaded_model_mirrors_reference_structure(tmp_path):
+    """State-dict keys / parameter counts of the cascaded configuration (kwClip.py:697-826, spchclp_c.yaml)."""
+    from avssl.model import KWClip_GeneralTransformer
+    from speechclip_b200.configs import cascaded_config, write_synthetic_vocab_usage
+    npy = write_synthetic_vocab_usage(str(tmp_path / "usage.npy"))
+    m = KWClip_GeneralTransformer(OrderedNamespace(cascaded_config("base", npy)))
+    assert m.parallel_branch is None and m.cascaded_branch is not None
+    keys = set(m.state_dict().keys())
+    for k in ("cascaded_branch.cls", "cascaded_branch.self_att.multihead_attn_layer.in_proj_weight",
+              "cascaded_branch.self_att.multihead_attn_layer.out_proj.bias", "cascaded_branch.self_att.attentionBlock_Norm.weight",
+              "cascaded_branch.linear_proj.weight", "cascaded_branch.bn_layer.bn_layer.weight", "cascaded_branch.bn_layer.bn_layer.running_var",
+              "cascaded_branch.bn_layer.bn_layer.num_batches_tracked", "cascaded_branch.vector_quantizer.curr_temp",
+              "cascaded_branch.clip.model.token_embedding.weight", "clip.model.token_embedding.weight"):
+        assert k in keys, k
+    cb = m.cascaded_branch
+    assert cb.cls.shape == (1, 8, 768) and m.clip.model.token_embedding.weight.shape == (8112, 512)
+    assert cb.bn_layer.bn_layer.weight.shape == (8 * 512,)
+    emb = m.clip.model.token_embedding.weight
+    torch.testing.assert_close(cb.bn_layer.bn_layer.bias.data, emb.mean(0).repeat(8))
+    torch.testing.assert_close(cb.bn_layer.bn_layer.weight.data, emb.std(0).repeat(8))
+    assert m.clip.special_tokens() == (2, 3) and cb.vector_quantizer.temperature() == pytest.approx(0.1)
+    # trainable: weighted-sum (13) + cls + MHA (4 d^2 + 4 d) + LN (2 d) + linear_proj + BatchNorm affine
+    d = 768
+    want = 13 + 8 * d + 4 * d * d + 4 * d + 2 * d + d * 512 + 512 + 2 * 8 * 512
+    assert sum(p.numel() for p in m.getTrainableParams() if p.requires_grad) == want
+    assert all(not p.requires_grad for p in m.clip.parameters())
+
+
 def test_product_path_has_no_cpu_fallback():
     from avssl.model import KWClip_GeneralTransformer
     from avssl.module import MaskedContrastiveLoss, mutualRetrieval
@@ -104,6 +141,14 @@ def test_product_path_has_no_cpu_fallback():
     b = {"wav": torch.randn(2, 4000), "wav_len": torch.tensor([4000, 3000]), "image": torch.randn(2, 3, 32, 32), "id": torch.arange(2)}
     with pytest.raises(RuntimeError, match="CUDA"):
         m.training_step(b)
+    from speechclip_b200.configs import cascaded_config
+    mc = KWClip_GeneralTransformer(OrderedNamespace(cascaded_config("tiny")))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mc.training_step(b)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mc.clip.encode_text(torch.zeros(2, 8, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mc.cascaded_branch.vector_quantizer(torch.randn(2, 8, 96))
     with pytest.raises(RuntimeError, match="CUDA"):
         MaskedContrastiveLoss()(torch.randn(4, 8), torch.randn(4, 8), torch.arange(4))
     with pytest.raises(RuntimeError, match="CUDA"):
