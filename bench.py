@@ -190,7 +190,12 @@ def run_own(args):
     use_graphs = args.graphs == "on" or (args.graphs == "auto" and per_gpu < 256)
     engine.GRAPHS = use_graphs
 
-    cfg = parallel_config(args.config)
+    if args.config == "cascaded":   # BASELINE.json configs[2]: keyword VQ + CLIP text tower, 8112-entry reduced vocabulary
+        import tempfile
+        from speechclip_b200.configs import cascaded_config, write_synthetic_vocab_usage
+        cfg = cascaded_config("base", write_synthetic_vocab_usage(os.path.join(tempfile.mkdtemp(prefix="scb_bench_"), "vocab_usage.npy")))
+    else:
+        cfg = parallel_config(args.config)
     model = KWClip_GeneralTransformer(OrderedNamespace(cfg)).to(dev)
     model.train()
     opts, scheds = model.configure_optimizers()
@@ -299,7 +304,8 @@ def run_own(args):
             for shp, (ms, fl, n) in sorted(shapes.items(), key=lambda kv: -kv[1][0]):
                 f.write(f"{ms / prof_steps:.4f},{n / prof_steps:.1f},{fl / (ms * 1e-3) / 1e12 if ms > 0 else 0:.1f},{shp}\n")
     pk = peaks()
-    gf_step = GF_PER_PAIR_STEP if args.config == "base" else 427.2  # dense algorithmic GFLOP per pair per step
+    # dense algorithmic GFLOP per pair per step (the cascaded branch's own work is < 1% of the towers')
+    gf_step = 427.2 if args.config == "large" else GF_PER_PAIR_STEP
     g = agg.get("scb_gemm", [0.0, 0.0, 0])
     gemm_ms, gemm_flops, gemm_n = g
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
@@ -317,10 +323,13 @@ def run_own(args):
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f16",
         "data": "synthetic",
-        "config": {"workload": ("Parallel SpeechCLIP-base (HuBERT-base + CLIP ViT-B/32)" if args.config == "base" else
-                                "Parallel SpeechCLIP-large (HuBERT-large + CLIP ViT-L/14)") + " training step, batch 256, 102400-sample utterances",
+        "config": {"workload": {"base": "Parallel SpeechCLIP-base (HuBERT-base + CLIP ViT-B/32)",
+                                "large": "Parallel SpeechCLIP-large (HuBERT-large + CLIP ViT-L/14)",
+                                "cascaded": "Cascaded SpeechCLIP-base (HuBERT-base + keyword VQ over 8112 subwords + CLIP ViT-B/32 text and image towers)"}[args.config]
+                               + " training step, batch 256, 102400-sample utterances",
                    "global_batch": global_batch, "pairs_per_gpu": per_gpu, "frames": 319, "parallelism": f"dp{world}",
-                   "mode": "training step, eval-mode arithmetic (dropout p=0), frozen towers, trainable branch 7.48 M params",
+                   "mode": "training step, eval-mode arithmetic (dropout p=0), frozen towers, trainable branch "
+                           + ("2.77 M params (+ frozen CLIP text tower in the differentiated path)" if args.config == "cascaded" else "7.48 M params"),
                    "l2": "inputs (259 MB) and activations (GBs) larger than the 126 MB L2; no flush needed",
                    "cuda_graphs": use_graphs},
         "e2e": {"value": global_batch / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
@@ -366,7 +375,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--batch", type=int, default=0, help="pairs per GPU (default: 256 / N strong, 256 weak)")
-    ap.add_argument("--config", default="base", choices=["base", "large"],
+    ap.add_argument("--config", default="base", choices=["base", "large", "cascaded"],
                     help="base = BASELINE.json configs[1] (headline); large = HuBERT-large + ViT-L/14 (configs[3])")
     ap.add_argument("--graphs", default="auto", choices=["auto", "on", "off"], help="replay the frozen towers as CUDA graphs")
     ap.add_argument("--no-cpu-baseline", action="store_true")

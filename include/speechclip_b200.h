@@ -112,7 +112,7 @@ int scb_cls_attention_fwd(const float* q, const void* kv, int32_t kv_fmt, int64_
                           float* ctx32, void* ctx16, int32_t ctx16_fmt, void* stream);
 int scb_cls_attention_bwd(const float* q, const void* kv, int32_t kv_fmt, int64_t kv_ld, int64_t kv_bs, int32_t k_off, int32_t v_off,
                           const int32_t* kv_len, int32_t batch, int32_t heads, int32_t head_dim, int32_t Tk, float scale,
-                          const float* probs, const float* dctx, void* dkv, int32_t dkv_fmt, float* dq, void* stream);
+                          const float* probs, const float* dctx, void* dkv, int32_t dkv_fmt, float* dq_part, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Waveform front end.
@@ -234,11 +234,12 @@ int scb_retrieval_rank(const float* score, int64_t ld, int32_t rows, int32_t col
 int scb_mq_attention_fwd(const float* q, const void* kv, int32_t kv_fmt, int64_t kv_ld, int64_t kv_batch_stride, int32_t k_off, int32_t v_off,
                          const int32_t* kv_len, int32_t batch, int32_t heads, int32_t head_dim, int32_t nq, int32_t Tk, float scale,
                          float* probs, float* ctx, void* stream);
-/* Backward: dkv (16-bit, layout of kv; rows >= kv_len zeroed; only the K and V column ranges are written), dq fp32
- * [nq][heads*head_dim] ACCUMULATED with atomics across the batch (zero it first). */
+/* Backward: dkv (16-bit, layout of kv; rows >= kv_len zeroed; only the K and V column ranges are written), dq_part fp32
+ * [batch][nq][heads*head_dim] = every utterance's contribution to dq (sum over the batch with scb_column_sum: no atomics,
+ * bit-reproducible). */
 int scb_mq_attention_bwd(const float* q, const void* kv, int32_t kv_fmt, int64_t kv_ld, int64_t kv_batch_stride, int32_t k_off, int32_t v_off,
                          const int32_t* kv_len, int32_t batch, int32_t heads, int32_t head_dim, int32_t nq, int32_t Tk, float scale,
-                         const float* probs, const float* dctx, void* dkv, int32_t dkv_fmt, float* dq, void* stream);
+                         const float* probs, const float* dctx, void* dkv, int32_t dkv_fmt, float* dq_part, void* stream);
 
 /* Kw_BatchNorm, eachKw + parallel (avssl/module/speechclip_c_modules/kw_bn.py:96-125): x fp32 [batch][n_kw][d] is viewed as
  * BatchNorm1d over d*n_kw features with feature index f = dim * n_kw + kw (the permute/reshape of kw_bn.py:116-118).

@@ -298,9 +298,10 @@ class CascadedHead:
         kv = s["kv"]
         dkv = ws.view("casc_dkv", (B, Tk, 2 * d), BF)
         g_w, g_b = g[A0 + "in_proj_weight"], g[A0 + "in_proj_bias"]
+        dq_part = ws.view("casc_dq_part", (B, K * d), torch.float32)
+        ops.mq_attention_bwd(s["q"], kv, 0, d, s["kv_len"], heads, hd, hd ** -0.5, s["probs"], dctx, dkv, dq_part)
         dq = ws.view("casc_dq", (K, d), torch.float32)
-        dq.zero_()
-        ops.mq_attention_bwd(s["q"], kv, 0, d, s["kv_len"], heads, hd, hd ** -0.5, s["probs"], dctx, dkv, dq)
+        ops.column_sum(dq_part, dq.view(1, K * d))
         ops.sgemm(dq.t(), cls.t(), g_w[:d])                            # dWq[o, i] = sum_k dq[k, o] cls[k, i]
         ops.column_sum(dq, g_b[:d])
         ops.sgemm(dq, w_in[:d].t(), dcls, beta=1.0)                    # dcls += dq Wq

@@ -38,52 +38,88 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 }
 
 // ------------------------------------------------------------------------------------------------ multi-query attention
-// One CTA per (utterance, head).  q fp32 [NQ][heads*hd] (unscaled).  kv 16-bit [B][Tk][ld]: K at k_off + h*hd, V at v_off + h*hd.
-// probs fp32 [B][heads][NQ][Tk]; ctx fp32 [B][NQ][heads*hd].
+// One CTA (8 warps) per (utterance, head).  q fp32 [NQ][heads*hd] (unscaled).  kv 16-bit [B][Tk][ld]: K at k_off + h*hd, V at
+// v_off + h*hd.  probs fp32 [B][heads][NQ][Tk]; ctx fp32 [B][NQ][heads*hd].
+// Row phases (scores = K q, dP = V dctx): a WARP per key row -- the 32 lanes read consecutive 16-byte chunks of the row (one
+// coalesced 512-byte request), each accumulates its slice of all NQ dot products against the query block held in shared
+// memory, then the NQ partials are reduced with shuffles.  Column phases (ctx = P V, dq = dS K): a thread per pair of
+// output dims, looping over the keys, so that every key row is again read as one contiguous segment per warp.
 constexpr int kMaxNQ = 8;
-__global__ void __launch_bounds__(128) mq_attention_fwd_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kv, int kv_fmt,
-                                                               long long kv_ld, long long kv_bs, int k_off, int v_off,
-                                                               const int* __restrict__ kv_len, int Tk, int heads, int hd, int nq,
-                                                               float scale, float* __restrict__ probs, float* __restrict__ ctx) {
-  extern __shared__ float sm[];  // [nq][Tk] scores/probs | [nq][hd] q | [8] scratch
-  float* sc = sm;
-  float* sq = sc + nq * Tk;
-  float* red = sq + nq * hd;
+constexpr int kMqThreads = 256;
+
+// out[k * out_ld + j] = scale_out * <row_j, vec_k> for j in [0, len): rows 16-bit at base + j*ld, vecs fp32 in shared memory [nq][hd]
+__device__ __forceinline__ void mq_row_dots(const uint16_t* __restrict__ base, long long ld, int fmt, int len, int hd, int nq,
+                                            const float* __restrict__ vecs, float* __restrict__ out, int out_ld) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int j = warp; j < len; j += nwarps) {
+    const uint16_t* row = base + (long long)j * ld;
+    float dot[kMaxNQ];
+#pragma unroll
+    for (int k = 0; k < kMaxNQ; ++k) dot[k] = 0.f;
+    for (int c = lane; c < hd / 8; c += 32) {
+      const uint4 u = *reinterpret_cast<const uint4*>(row + c * 8);
+      const float2 a = unpack16(fmt, u.x), b = unpack16(fmt, u.y), cc = unpack16(fmt, u.z), d = unpack16(fmt, u.w);
+#pragma unroll
+      for (int k = 0; k < kMaxNQ; ++k) {
+        if (k < nq) {
+          const float4 q0 = *reinterpret_cast<const float4*>(vecs + k * hd + c * 8);
+          const float4 q1 = *reinterpret_cast<const float4*>(vecs + k * hd + c * 8 + 4);
+          dot[k] += a.x * q0.x + a.y * q0.y + b.x * q0.z + b.y * q0.w + cc.x * q1.x + cc.y * q1.y + d.x * q1.z + d.y * q1.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxNQ; ++k) {
+      if (k < nq) {
+        const float v = warp_sum(dot[k]);
+        if (lane == 0) out[k * out_ld + j] = v;
+      }
+    }
+  }
+}
+
+// acc[k] (a float2 = two adjacent dims) = sum_j w[k * w_ld + j] * row_j[pair]  for the pair of dims owned by this thread
+__device__ __forceinline__ void mq_col_sums(const uint16_t* __restrict__ col, long long ld, int fmt, int len, int nq,
+                                            const float* __restrict__ w, int w_ld, float2* acc) {
+#pragma unroll
+  for (int k = 0; k < kMaxNQ; ++k) acc[k] = make_float2(0.f, 0.f);
+#pragma unroll 4
+  for (int j = 0; j < len; ++j) {
+    const float2 vv = unpack16(fmt, *reinterpret_cast<const uint32_t*>(col + (long long)j * ld));
+#pragma unroll
+    for (int k = 0; k < kMaxNQ; ++k) {
+      if (k < nq) {
+        const float pj = w[k * w_ld + j];
+        acc[k].x += pj * vv.x;
+        acc[k].y += pj * vv.y;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kMqThreads) mq_attention_fwd_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kv, int kv_fmt,
+                                                                      long long kv_ld, long long kv_bs, int k_off, int v_off,
+                                                                      const int* __restrict__ kv_len, int Tk, int heads, int hd, int nq,
+                                                                      float scale, float* __restrict__ probs, float* __restrict__ ctx) {
+  extern __shared__ __align__(16) float sm[];  // [nq][hd] q (scaled) | [nq][Tk] scores/probs | [8] scratch
+  float* sq = sm;
+  float* sc = sq + nq * hd;
+  float* red = sc + nq * Tk;
   const int tid = threadIdx.x;
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int D = heads * hd;
   const int len = kv_len ? min(kv_len[b], Tk) : Tk;
   const uint16_t* base = kv + (long long)b * kv_bs + h * hd;
-  for (int i = tid; i < nq * hd; i += 128) sq[i] = q[(i / hd) * D + h * hd + (i % hd)] * scale;
+  for (int i = tid; i < nq * hd; i += kMqThreads) sq[i] = q[(i / hd) * D + h * hd + (i % hd)] * scale;
   __syncthreads();
-  // scores: a key per thread, all queries at once (each 16-byte chunk of the key row is used NQ times from registers)
-  for (int j = tid; j < len; j += 128) {
-    const uint16_t* kr = base + (long long)j * kv_ld + k_off;
-    float dot[kMaxNQ];
-#pragma unroll
-    for (int k = 0; k < kMaxNQ; ++k) dot[k] = 0.f;
-    for (int c = 0; c < hd / 8; ++c) {
-      const uint4 u = *reinterpret_cast<const uint4*>(kr + c * 8);
-      const float2 a = unpack16(kv_fmt, u.x), bb = unpack16(kv_fmt, u.y), cc = unpack16(kv_fmt, u.z), dd = unpack16(kv_fmt, u.w);
-#pragma unroll
-      for (int k = 0; k < kMaxNQ; ++k) {
-        if (k < nq) {
-          const float* qq = sq + k * hd + c * 8;
-          dot[k] += a.x * qq[0] + a.y * qq[1] + bb.x * qq[2] + bb.y * qq[3] + cc.x * qq[4] + cc.y * qq[5] + dd.x * qq[6] + dd.y * qq[7];
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < kMaxNQ; ++k)
-      if (k < nq) sc[k * Tk + j] = dot[k];
-  }
+  mq_row_dots(base + k_off, kv_ld, kv_fmt, len, hd, nq, sq, sc, Tk);
   __syncthreads();
   for (int k = 0; k < nq; ++k) {
     float mx = -INFINITY;
-    for (int j = tid; j < len; j += 128) mx = fmaxf(mx, sc[k * Tk + j]);
+    for (int j = tid; j < len; j += kMqThreads) mx = fmaxf(mx, sc[k * Tk + j]);
     mx = block_max(mx, red);
     float sum = 0.f;
-    for (int j = tid; j < len; j += 128) {
+    for (int j = tid; j < len; j += kMqThreads) {
       const float e = __expf(sc[k * Tk + j] - mx);
       sc[k * Tk + j] = e;
       sum += e;
@@ -91,94 +127,61 @@ __global__ void __launch_bounds__(128) mq_attention_fwd_kernel(const float* __re
     sum = block_sum(sum, red);
     const float inv = 1.f / sum;
     float* po = probs + (((long long)b * heads + h) * nq + k) * Tk;
-    for (int j = tid; j < Tk; j += 128) {
+    for (int j = tid; j < Tk; j += kMqThreads) {
       const float pj = j < len ? sc[k * Tk + j] * inv : 0.f;
       if (j < len) sc[k * Tk + j] = pj;
       po[j] = pj;
     }
   }
   __syncthreads();
-  // context: a pair of output dims per thread (looped when hd/2 > 128), all queries at once, coalesced V row reads
-  for (int pr = tid; pr < hd / 2; pr += 128) {
+  for (int pr = tid; pr < hd / 2; pr += kMqThreads) {
     float2 acc[kMaxNQ];
-#pragma unroll
-    for (int k = 0; k < kMaxNQ; ++k) acc[k] = make_float2(0.f, 0.f);
-    const uint16_t* vr = base + v_off + pr * 2;
-    for (int j = 0; j < len; ++j) {
-      const float2 vv = unpack16(kv_fmt, *reinterpret_cast<const uint32_t*>(vr + (long long)j * kv_ld));
-#pragma unroll
-      for (int k = 0; k < kMaxNQ; ++k) {
-        if (k < nq) {
-          const float pj = sc[k * Tk + j];
-          acc[k].x += pj * vv.x;
-          acc[k].y += pj * vv.y;
-        }
-      }
-    }
+    mq_col_sums(base + v_off + pr * 2, kv_ld, kv_fmt, len, nq, sc, Tk, acc);
 #pragma unroll
     for (int k = 0; k < kMaxNQ; ++k)
       if (k < nq) *reinterpret_cast<float2*>(ctx + ((long long)b * nq + k) * D + h * hd + pr * 2) = acc[k];
   }
 }
 
-// dctx fp32 [B][NQ][D].  dkv 16-bit (same layout as kv; rows >= len zero).  dq fp32 [NQ][D] accumulated with atomics.
-__global__ void __launch_bounds__(128) mq_attention_bwd_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kv, int kv_fmt,
-                                                               long long kv_ld, long long kv_bs, int k_off, int v_off,
-                                                               const int* __restrict__ kv_len, int Tk, int heads, int hd, int nq,
-                                                               float scale, const float* __restrict__ probs,
-                                                               const float* __restrict__ dctx, uint16_t* __restrict__ dkv, int dkv_fmt,
-                                                               float* __restrict__ dq) {
-  extern __shared__ float sm[];  // [nq][Tk] ds | [nq][Tk] p | [nq][hd] q | [nq][hd] dctx | [8]
-  float* sds = sm;
-  float* sp = sds + nq * Tk;
-  float* sq = sp + nq * Tk;
+// dctx fp32 [B][NQ][D].  dkv 16-bit (same layout as kv; rows >= len zero).  dq_part fp32 [B][NQ][D]: this utterance's
+// contribution to dq (the caller sums over B -- no atomics, deterministic).
+__global__ void __launch_bounds__(kMqThreads) mq_attention_bwd_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kv, int kv_fmt,
+                                                                      long long kv_ld, long long kv_bs, int k_off, int v_off,
+                                                                      const int* __restrict__ kv_len, int Tk, int heads, int hd, int nq,
+                                                                      float scale, const float* __restrict__ probs,
+                                                                      const float* __restrict__ dctx, uint16_t* __restrict__ dkv, int dkv_fmt,
+                                                                      float* __restrict__ dq_part) {
+  extern __shared__ __align__(16) float sm[];  // [nq][hd] q | [nq][hd] dctx | [nq][Tk] ds | [nq][Tk] p | [8]
+  float* sq = sm;
   float* sdc = sq + nq * hd;
-  float* red = sdc + nq * hd;
+  float* sds = sdc + nq * hd;
+  float* sp = sds + nq * Tk;
+  float* red = sp + nq * Tk;
   const int tid = threadIdx.x;
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int D = heads * hd;
   const int len = kv_len ? min(kv_len[b], Tk) : Tk;
   const uint16_t* base = kv + (long long)b * kv_bs + h * hd;
   uint16_t* dbase = dkv + (long long)b * kv_bs + h * hd;
-  for (int i = tid; i < nq * hd; i += 128) {
+  for (int i = tid; i < nq * hd; i += kMqThreads) {
     const int k = i / hd, d = i % hd;
     sq[i] = q[k * D + h * hd + d];
     sdc[i] = dctx[((long long)b * nq + k) * D + h * hd + d];
   }
-  for (int i = tid; i < nq * Tk; i += 128) sp[i] = probs[((long long)b * heads + h) * nq * Tk + i];
+  for (int i = tid; i < nq * Tk; i += kMqThreads) sp[i] = probs[((long long)b * heads + h) * nq * Tk + i];
   __syncthreads();
-  // dp[k][j] = <dctx_k, v_j>
-  for (int j = tid; j < len; j += 128) {
-    const uint16_t* vr = base + (long long)j * kv_ld + v_off;
-    float dp[kMaxNQ];
-#pragma unroll
-    for (int k = 0; k < kMaxNQ; ++k) dp[k] = 0.f;
-    for (int c = 0; c < hd / 8; ++c) {
-      const uint4 u = *reinterpret_cast<const uint4*>(vr + c * 8);
-      const float2 a = unpack16(kv_fmt, u.x), bb = unpack16(kv_fmt, u.y), cc = unpack16(kv_fmt, u.z), dd = unpack16(kv_fmt, u.w);
-#pragma unroll
-      for (int k = 0; k < kMaxNQ; ++k) {
-        if (k < nq) {
-          const float* g = sdc + k * hd + c * 8;
-          dp[k] += a.x * g[0] + a.y * g[1] + bb.x * g[2] + bb.y * g[3] + cc.x * g[4] + cc.y * g[5] + dd.x * g[6] + dd.y * g[7];
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < kMaxNQ; ++k)
-      if (k < nq) sds[k * Tk + j] = dp[k];
-  }
+  mq_row_dots(base + v_off, kv_ld, kv_fmt, len, hd, nq, sdc, sds, Tk);   // dP[k][j] = <dctx_k, v_j>
   __syncthreads();
   for (int k = 0; k < nq; ++k) {
     float dot = 0.f;
-    for (int j = tid; j < len; j += 128) dot += sp[k * Tk + j] * sds[k * Tk + j];
+    for (int j = tid; j < len; j += kMqThreads) dot += sp[k * Tk + j] * sds[k * Tk + j];
     dot = block_sum(dot, red);
-    for (int j = tid; j < len; j += 128) sds[k * Tk + j] = sp[k * Tk + j] * (sds[k * Tk + j] - dot) * scale;
+    for (int j = tid; j < len; j += kMqThreads) sds[k * Tk + j] = sp[k * Tk + j] * (sds[k * Tk + j] - dot) * scale;
   }
   __syncthreads();
   // dK_j = sum_k ds[k][j] q_k ; dV_j = sum_k p[k][j] dctx_k : a 16-byte chunk of one key row per thread per step
   const int CH = hd / 8;
-  for (int idx = tid; idx < Tk * CH; idx += 128) {
+  for (int idx = tid; idx < Tk * CH; idx += kMqThreads) {
     const int j = idx / CH, c = idx % CH;
     float gk[8], gv[8];
 #pragma unroll
@@ -186,13 +189,12 @@ __global__ void __launch_bounds__(128) mq_attention_bwd_kernel(const float* __re
     if (j < len) {
       for (int k = 0; k < nq; ++k) {
         const float ds = sds[k * Tk + j], pj = sp[k * Tk + j];
-        const float* qq = sq + k * hd + c * 8;
-        const float* g = sdc + k * hd + c * 8;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          gk[i] += ds * qq[i];
-          gv[i] += pj * g[i];
-        }
+        const float4 q0 = *reinterpret_cast<const float4*>(sq + k * hd + c * 8), q1 = *reinterpret_cast<const float4*>(sq + k * hd + c * 8 + 4);
+        const float4 g0 = *reinterpret_cast<const float4*>(sdc + k * hd + c * 8), g1 = *reinterpret_cast<const float4*>(sdc + k * hd + c * 8 + 4);
+        gk[0] += ds * q0.x; gk[1] += ds * q0.y; gk[2] += ds * q0.z; gk[3] += ds * q0.w;
+        gk[4] += ds * q1.x; gk[5] += ds * q1.y; gk[6] += ds * q1.z; gk[7] += ds * q1.w;
+        gv[0] += pj * g0.x; gv[1] += pj * g0.y; gv[2] += pj * g0.z; gv[3] += pj * g0.w;
+        gv[4] += pj * g1.x; gv[5] += pj * g1.y; gv[6] += pj * g1.z; gv[7] += pj * g1.w;
       }
     }
     uint4 uk, uv;
@@ -201,30 +203,13 @@ __global__ void __launch_bounds__(128) mq_attention_bwd_kernel(const float* __re
     *reinterpret_cast<uint4*>(dbase + (long long)j * kv_ld + k_off + c * 8) = uk;
     *reinterpret_cast<uint4*>(dbase + (long long)j * kv_ld + v_off + c * 8) = uv;
   }
-  // dq_k += sum_j ds[k][j] k_j
-  for (int pr = tid; pr < hd / 2; pr += 128) {
+  // dq_k (this utterance) = sum_j ds[k][j] k_j
+  for (int pr = tid; pr < hd / 2; pr += kMqThreads) {
     float2 acc[kMaxNQ];
+    mq_col_sums(base + k_off + pr * 2, kv_ld, kv_fmt, len, nq, sds, Tk, acc);
 #pragma unroll
-    for (int k = 0; k < kMaxNQ; ++k) acc[k] = make_float2(0.f, 0.f);
-    const uint16_t* kr = base + k_off + pr * 2;
-    for (int j = 0; j < len; ++j) {
-      const float2 kk = unpack16(kv_fmt, *reinterpret_cast<const uint32_t*>(kr + (long long)j * kv_ld));
-#pragma unroll
-      for (int k = 0; k < kMaxNQ; ++k) {
-        if (k < nq) {
-          const float ds = sds[k * Tk + j];
-          acc[k].x += ds * kk.x;
-          acc[k].y += ds * kk.y;
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < kMaxNQ; ++k) {
-      if (k < nq) {
-        atomicAdd(&dq[k * D + h * hd + pr * 2], acc[k].x);
-        atomicAdd(&dq[k * D + h * hd + pr * 2 + 1], acc[k].y);
-      }
-    }
+    for (int k = 0; k < kMaxNQ; ++k)
+      if (k < nq) *reinterpret_cast<float2*>(dq_part + ((long long)b * nq + k) * D + h * hd + pr * 2) = acc[k];
   }
 }
 
@@ -653,7 +638,7 @@ int mq_attention_fwd(const float* q, const void* kv, int kv_fmt, long long kv_ld
   const size_t smem = (size_t)(nq * Tk + nq * head_dim + 8) * sizeof(float);
   SCB_CHECK(smem <= 200 * 1024, SCB_EUNSUPPORTED, "scb_mq_attention_fwd: nq*Tk + nq*head_dim too large");
   SCB_SMEM_ATTR(mq_attention_fwd_kernel, smem);
-  mq_attention_fwd_kernel<<<batch * heads, 128, smem, st>>>(q, (const uint16_t*)kv, kv_fmt, kv_ld, kv_bs, k_off, v_off, kv_len, Tk, heads,
+  mq_attention_fwd_kernel<<<batch * heads, kMqThreads, smem, st>>>(q, (const uint16_t*)kv, kv_fmt, kv_ld, kv_bs, k_off, v_off, kv_len, Tk, heads,
                                                            head_dim, nq, scale, probs, ctx);
   note_launch();
   SCB_LAUNCH_OK("mq_attention_fwd");
@@ -671,7 +656,7 @@ int mq_attention_bwd(const float* q, const void* kv, int kv_fmt, long long kv_ld
   const size_t smem = (size_t)(2 * nq * Tk + 2 * nq * head_dim + 8) * sizeof(float);
   SCB_CHECK(smem <= 200 * 1024, SCB_EUNSUPPORTED, "scb_mq_attention_bwd: nq*Tk + nq*head_dim too large");
   SCB_SMEM_ATTR(mq_attention_bwd_kernel, smem);
-  mq_attention_bwd_kernel<<<batch * heads, 128, smem, st>>>(q, (const uint16_t*)kv, kv_fmt, kv_ld, kv_bs, k_off, v_off, kv_len, Tk, heads,
+  mq_attention_bwd_kernel<<<batch * heads, kMqThreads, smem, st>>>(q, (const uint16_t*)kv, kv_fmt, kv_ld, kv_bs, k_off, v_off, kv_len, Tk, heads,
                                                            head_dim, nq, scale, probs, dctx, (uint16_t*)dkv, dkv_fmt, dq);
   note_launch();
   SCB_LAUNCH_OK("mq_attention_bwd");

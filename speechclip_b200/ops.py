@@ -306,11 +306,12 @@ def mq_attention_fwd(q, kv, k_off, v_off, kv_len, heads, hd, scale, probs, ctx32
           q.shape[0], Tk, scale, _p(probs), _p(ctx32))
 
 
-def mq_attention_bwd(q, kv, k_off, v_off, kv_len, heads, hd, scale, probs, dctx, dkv, dq):
+def mq_attention_bwd(q, kv, k_off, v_off, kv_len, heads, hd, scale, probs, dctx, dkv, dq_part):
+    """dq_part fp32 [B, NQ * heads*hd]: per-utterance contributions to dq (sum over dim 0 with column_sum)."""
     B, Tk = kv.shape[0], kv.shape[1]
-    assert dkv.shape == kv.shape and dkv.stride() == kv.stride()
+    assert dkv.shape == kv.shape and dkv.stride() == kv.stride() and dq_part.numel() == B * q.numel()
     _call("scb_mq_attention_bwd", _p(q), _p(kv), _DT[kv.dtype], kv.stride(1), kv.stride(0), k_off, v_off, _p(kv_len), B, heads, hd,
-          q.shape[0], Tk, scale, _p(probs), _p(dctx), _p(dkv), _DT[dkv.dtype], _p(dq))
+          q.shape[0], Tk, scale, _p(probs), _p(dctx), _p(dkv), _DT[dkv.dtype], _p(dq_part))
 
 
 def batchnorm_fwd(x, y, gamma, beta, running_mean, running_var, save_mean, save_rstd, eps, momentum, training):
