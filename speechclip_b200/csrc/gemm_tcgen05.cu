@@ -23,7 +23,12 @@ template <int BN> struct EpiCfg {
   static constexpr int WARPS = BN >= 128 ? 16 : 8;          // 4 (or 2) warps per TMEM lane quarter
   static constexpr int COLS = BN / (WARPS / 4);              // accumulator columns per warp: 64 / 32 / 32
   static constexpr int THREADS = (4 + WARPS) * 32;
+  static constexpr int PATCH_BYTES = WARPS * 32 * 16 * 4;   // transpose patches of the register-store epilogue (2 KB per warp)
+  static constexpr int TMA_BYTES = WARPS * 32 * 128;        // TMA-store epilogue: 32 rows x 128 B (64 16-bit columns) per warp
 };
+// Epilogues whose output is 16-bit with no residual (QKV, fc1, the conv stack, CLIP c_fc) leave through TMA stores: see
+// epilogue_tile_tma.  They give up one pipeline stage for the 64 KB of staging.
+__host__ __device__ constexpr bool tma_out(int BN, int ACT, int RES, int ODT) { return BN == 256 && ACT >= 0 && RES == 3 && ODT == SCB_F16; }
 
 struct GemmParams {
   int batch, m_tiles_per_batch, n_tiles, groups, num_tiles;
@@ -181,16 +186,92 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
   }
 }
 
+
+// TMA-store epilogue (16-bit output, bias + activation, no residual).  tcgen05.ld hands lane r ROW r of the accumulator; the
+// lane converts its 64 columns to 16-bit and writes them as eight 16-byte units into row r of a [32 rows][128 B] staging tile
+// in the 128B-swizzle pattern (unit c of row r at slot c ^ (r & 7): the 8 lanes of a quarter-warp hit 8 different slots, so
+// the stores are bank-conflict-free), and one elected lane hands the tile to cp.async.bulk.tensor: no transpose pass, no
+// per-lane global addressing or predicates (the tensor map clips the M / N edges), about half the instructions of the
+// register-store path — which is what bounds the K = 768 shapes (fc1: 22 instructions per output measured, 15 of them GELU).
+template <int ACT>
+__device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUtensorMap* tmO, const TileCoord& t, uint32_t tmem_base,
+                                                  int acc, uint32_t acc_phase, uint64_t* tfull_bar, uint32_t tempty_addr,
+                                                  uint8_t* stage_all, int warp, int lane) {
+  constexpr int BN = 256, COLS = EpiCfg<BN>::COLS;
+  static_assert(COLS == 64, "one 128-byte staging row per accumulator row");
+  const int q = warp & 3;
+  const int part = (warp - 4) >> 2;
+  const int m_base = t.m0 + q * 32;
+  const int col_base = t.n0 + part * COLS;
+  const uint32_t stg = smem_u32(stage_all + (warp - 4) * (32 * 128)) + (uint32_t)lane * 128u;
+  const uint32_t sw = (uint32_t)(lane & 7);
+  const bool live = col_base < p.n && m_base < p.m_per_batch;
+  const bool has_bias = p.bias != nullptr;
+  mbar_wait(tfull_bar, acc_phase);
+  tc_fence_after();
+  if (lane == 0) bulk_wait_read0();  // the previous tile's store has finished reading this warp's staging tile
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t v[32];
+    if (live) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + part * COLS + h * 32), v);
+    tmem_ld_wait();
+    if (h == 1) {  // accumulator fully read by this warp: hand the buffer back to the MMA warp
+      tc_fence_before();
+      if (lane == 0) mbar_arrive_cluster(tempty_addr);
+    }
+    if (live) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {  // 8 columns -> one 16-byte unit
+        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+        if (has_bias) {  // columns past n (clipped by the store) read the last in-range unit instead: n % 8 == 0
+          const float* bp = p.bias + min(col_base + h * 32 + k * 8, p.n - 8);
+          b0 = __ldg(reinterpret_cast<const float4*>(bp));
+          b1 = __ldg(reinterpret_cast<const float4*>(bp + 4));
+        }
+        const uint64_t al2 = pk2(p.alpha, p.alpha);
+        uint64_t x[4] = {fma2(al2, pk2(__uint_as_float(v[8 * k + 0]), __uint_as_float(v[8 * k + 1])), pk2(b0.x, b0.y)),
+                         fma2(al2, pk2(__uint_as_float(v[8 * k + 2]), __uint_as_float(v[8 * k + 3])), pk2(b0.z, b0.w)),
+                         fma2(al2, pk2(__uint_as_float(v[8 * k + 4]), __uint_as_float(v[8 * k + 5])), pk2(b1.x, b1.y)),
+                         fma2(al2, pk2(__uint_as_float(v[8 * k + 6]), __uint_as_float(v[8 * k + 7])), pk2(b1.z, b1.w))};
+        uint32_t h16[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (ACT == SCB_ACT_GELU_ERF) x[i] = gelu_h16_x2(x[i]);
+          else if (ACT == SCB_ACT_QUICK_GELU) x[i] = quick_gelu_x2(x[i]);
+          float lo, hi;
+          upk2(x[i], lo, hi);
+          h16[i] = H16<SCB_F16>::pack(lo, hi);
+        }
+        const uint32_t unit = (uint32_t)(h * 4 + k);
+        st_shared_v4(stg + ((unit ^ sw) << 4), h16[0], h16[1], h16[2], h16[3]);
+      }
+    }
+  }
+  if (live) {
+    fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA engine
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_3d(tmO, stg, col_base, m_base, t.b);
+      bulk_commit();
+    }
+  }
+}
+
 template <int BN, int STAGES, int ACT, int RES, int ODT>
 __global__ void __launch_bounds__(EpiCfg<BN>::THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int B_BYTES = BN * BK * 2;
+  constexpr bool TMAO = tma_out(BN, ACT, RES, ODT);
+  constexpr int EPI_BYTES = TMAO ? EpiCfg<BN>::TMA_BYTES : EpiCfg<BN>::PATCH_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset arithmetic keeps the shared address space
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint8_t* epi = sB + STAGES * B_BYTES;  // 1024-aligned: transpose patches or TMA-store staging tiles
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi + EPI_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -199,7 +280,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + 2);
   constexpr int SLAB_BYTES = 256 * BK * 2;  // 256 rows x 128 B
   static_assert(BN > 64 || STAGES * A_BYTES >= 2 * SLAB_BYTES, "the A ring must hold two slabs");
-  float* stage = reinterpret_cast<float*>(sB + STAGES * B_BYTES + 256);  // [epilogue warp][32 rows x 16 cols] transpose patches
+  float* stage = reinterpret_cast<float*>(epi);  // [epilogue warp][32 rows x 16 cols] transpose patches
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -207,6 +288,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (TMAO) tma_prefetch_desc(&tmO);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -345,10 +427,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile<BN>(p, tile);
-      epilogue_tile<BN, ACT, RES, ODT>(p, t, tmem_base, acc, acc_phase, &tfull[acc], smem_u32(&tempty[acc]), stage, warp, lane);
+      if constexpr (TMAO) epilogue_tile_tma<ACT>(p, &tmO, t, tmem_base, acc, acc_phase, &tfull[acc], smem_u32(&tempty[acc]), epi, warp, lane);
+      else epilogue_tile<BN, ACT, RES, ODT>(p, t, tmem_base, acc, acc_phase, &tfull[acc], smem_u32(&tempty[acc]), stage, warp, lane);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (TMAO && lane == 0) bulk_wait_all();  // the staging tiles must outlive the last store's reads
   }
 
   tc_fence_before();
@@ -369,8 +453,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 //   empty[s]  (each CTA): tcgen05.commit multicast from the leader -> that CTA's producer may refill the stage
 //   tfull[a]  (each CTA): tcgen05.commit multicast -> that CTA's epilogue may read its accumulator half
 //   tempty[a] (leader)  : 2 x 16 epilogue warps (local + remote arrivals) -> the leader may overwrite the accumulators
-constexpr int kStages2 = 6;
 constexpr int BN2 = 256;
+__host__ __device__ constexpr int stages2(bool tma_epilogue) { return tma_epilogue ? 5 : 6; }
 
 __device__ __forceinline__ TileCoord decode_tile2(const GemmParams& p, int tile, int rank) {
   TileCoord t;
@@ -387,20 +471,24 @@ __device__ __forceinline__ TileCoord decode_tile2(const GemmParams& p, int tile,
 
 template <int ACT, int RES, int ODT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<BN2>::THREADS, 1)
-gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int B_BYTES = (BN2 / 2) * BK * 2;
-  constexpr int STAGES = kStages2;
+  constexpr bool TMAO = tma_out(BN2, ACT, RES, ODT);
+  constexpr int STAGES = stages2(TMAO);
+  constexpr int EPI_BYTES = TMAO ? EpiCfg<BN2>::TMA_BYTES : EpiCfg<BN2>::PATCH_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint8_t* epi = sB + STAGES * B_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi + EPI_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* stage = reinterpret_cast<float*>(sB + STAGES * B_BYTES + 256);
+  float* stage = reinterpret_cast<float*>(epi);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -411,6 +499,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (TMAO) tma_prefetch_desc(&tmO);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -488,10 +577,12 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < p.num_tiles; tile += num_pairs) {
       const TileCoord t = decode_tile2(p, tile, (int)rank);
-      epilogue_tile<BN2, ACT, RES, ODT>(p, t, tmem_base, acc, acc_phase, &tfull[acc], mapa_u32(smem_u32(&tempty[acc]), 0), stage, warp, lane);
+      if constexpr (TMAO) epilogue_tile_tma<ACT>(p, &tmO, t, tmem_base, acc, acc_phase, &tfull[acc], mapa_u32(smem_u32(&tempty[acc]), 0), epi, warp, lane);
+      else epilogue_tile<BN2, ACT, RES, ODT>(p, t, tmem_base, acc, acc_phase, &tfull[acc], mapa_u32(smem_u32(&tempty[acc]), 0), stage, warp, lane);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (TMAO && lane == 0) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -503,8 +594,10 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 template <int ACT, int RES, int ODT>
-int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  constexpr int smem_bytes = kStages2 * (BM * BK * 2 + (BN2 / 2) * BK * 2) + 1024 + 256 + EpiCfg<BN2>::WARPS * 32 * 16 * 4;
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p, cudaStream_t stream) {
+  constexpr bool TMAO = tma_out(BN2, ACT, RES, ODT);
+  constexpr int smem_bytes = stages2(TMAO) * (BM * BK * 2 + (BN2 / 2) * BK * 2) + 1024 + 256 +
+                             (TMAO ? EpiCfg<BN2>::TMA_BYTES : EpiCfg<BN2>::PATCH_BYTES);
   static_assert(smem_bytes <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
   static bool configured = false;
   if (!configured) {
@@ -513,15 +606,16 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
   }
   int pairs = num_sms() / 2;
   if (p.num_tiles < pairs) pairs = p.num_tiles;
-  gemm2_tcgen05_kernel<ACT, RES, ODT><<<2 * pairs, EpiCfg<BN2>::THREADS, smem_bytes, stream>>>(tmA, tmB, p);
+  gemm2_tcgen05_kernel<ACT, RES, ODT><<<2 * pairs, EpiCfg<BN2>::THREADS, smem_bytes, stream>>>(tmA, tmB, tmO, p);
   note_launch();
   SCB_LAUNCH_OK("gemm2_tcgen05");
   return SCB_OK;
 }
 
 template <int BN, int STAGES, int ACT = -1, int RES = -1, int ODT = -1>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  constexpr int smem_bytes = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + 256 + EpiCfg<BN>::WARPS * 32 * 16 * 4;
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p, cudaStream_t stream) {
+  constexpr bool TMAO = tma_out(BN, ACT, RES, ODT);
+  constexpr int smem_bytes = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + 256 + (TMAO ? EpiCfg<BN>::TMA_BYTES : EpiCfg<BN>::PATCH_BYTES);
   static_assert(smem_bytes <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
   static bool configured = false;
   if (!configured) {
@@ -529,7 +623,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, 
     configured = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  gemm_tcgen05_kernel<BN, STAGES, ACT, RES, ODT><<<grid, EpiCfg<BN>::THREADS, smem_bytes, stream>>>(tmA, tmB, p);
+  gemm_tcgen05_kernel<BN, STAGES, ACT, RES, ODT><<<grid, EpiCfg<BN>::THREADS, smem_bytes, stream>>>(tmA, tmB, tmO, p);
   note_launch();
   SCB_LAUNCH_OK("gemm_tcgen05");
   return SCB_OK;
@@ -632,27 +726,42 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
     else if (a.act == SCB_ACT_NONE && !nores && a.residual_dtype == SCB_F32 && a.out_dtype == SCB_F32) mode = 2;               // out-proj, fc2
     else if (a.act == SCB_ACT_GELU_ERF && nores && a.out_dtype == SCB_F16) mode = 3;                                            // fc1, conv1..6
     else if (a.act == SCB_ACT_QUICK_GELU && nores && a.out_dtype == SCB_F16) mode = 4;                                          // CLIP c_fc
+    else if (a.act == SCB_ACT_NONE && !nores && a.residual_dtype == SCB_F16 && a.out_dtype == SCB_F32) mode = 5;               // out-proj, fc2 (16-bit residual stream)
+  }
+  // modes 1, 3, 4 store through TMA: [batch][rows][cols] view of the output, 32-row x 64-column boxes in the 128B swizzle
+  static const int tma_env = [] { const char* e = getenv("SCB_GEMM_TMA_STORE"); return e ? atoi(e) : 1; }();
+  if ((mode == 1 || mode == 3 || mode == 4) && (a.groups != 1 || tma_env == 0)) mode = 0;
+  CUtensorMap tmO = tmA;
+  if (mode == 1 || mode == 3 || mode == 4) {
+    const uint64_t dims[3] = {(uint64_t)a.n, (uint64_t)a.m_per_batch, (uint64_t)a.batch};
+    const uint64_t bstride = a.out_batch_stride ? (uint64_t)a.out_batch_stride : (uint64_t)a.m_per_batch * (uint64_t)a.ldc;
+    const uint64_t strides[2] = {(uint64_t)a.ldc * 2, bstride * 2};
+    const uint32_t box[3] = {64, 32, 1};
+    int e = make_tmap(&tmO, a.out, 2, 3, dims, strides, box, 1);
+    if (e) return e;
   }
   if (two) {
     switch (mode) {
-      case 1: return launch2<SCB_ACT_NONE, 3, SCB_F16>(tmA, tmB, p, stream);
-      case 2: return launch2<SCB_ACT_NONE, SCB_F32, SCB_F32>(tmA, tmB, p, stream);
-      case 3: return launch2<SCB_ACT_GELU_ERF, 3, SCB_F16>(tmA, tmB, p, stream);
-      case 4: return launch2<SCB_ACT_QUICK_GELU, 3, SCB_F16>(tmA, tmB, p, stream);
-      default: return launch2<-1, -1, -1>(tmA, tmB, p, stream);
+      case 1: return launch2<SCB_ACT_NONE, 3, SCB_F16>(tmA, tmB, tmO, p, stream);
+      case 2: return launch2<SCB_ACT_NONE, SCB_F32, SCB_F32>(tmA, tmB, tmO, p, stream);
+      case 3: return launch2<SCB_ACT_GELU_ERF, 3, SCB_F16>(tmA, tmB, tmO, p, stream);
+      case 4: return launch2<SCB_ACT_QUICK_GELU, 3, SCB_F16>(tmA, tmB, tmO, p, stream);
+      case 5: return launch2<SCB_ACT_NONE, SCB_F16, SCB_F32>(tmA, tmB, tmO, p, stream);
+      default: return launch2<-1, -1, -1>(tmA, tmB, tmO, p, stream);
     }
   }
   if (bn == 256) {
     switch (mode) {
-      case 1: return launch<256, 4, SCB_ACT_NONE, 3, SCB_F16>(tmA, tmB, p, stream);
-      case 2: return launch<256, 4, SCB_ACT_NONE, SCB_F32, SCB_F32>(tmA, tmB, p, stream);
-      case 3: return launch<256, 4, SCB_ACT_GELU_ERF, 3, SCB_F16>(tmA, tmB, p, stream);
-      case 4: return launch<256, 4, SCB_ACT_QUICK_GELU, 3, SCB_F16>(tmA, tmB, p, stream);
-      default: return launch<256, 4>(tmA, tmB, p, stream);
+      case 1: return launch<256, 3, SCB_ACT_NONE, 3, SCB_F16>(tmA, tmB, tmO, p, stream);
+      case 2: return launch<256, 4, SCB_ACT_NONE, SCB_F32, SCB_F32>(tmA, tmB, tmO, p, stream);
+      case 3: return launch<256, 3, SCB_ACT_GELU_ERF, 3, SCB_F16>(tmA, tmB, tmO, p, stream);
+      case 4: return launch<256, 3, SCB_ACT_QUICK_GELU, 3, SCB_F16>(tmA, tmB, tmO, p, stream);
+      case 5: return launch<256, 4, SCB_ACT_NONE, SCB_F16, SCB_F32>(tmA, tmB, tmO, p, stream);
+      default: return launch<256, 4>(tmA, tmB, tmO, p, stream);
     }
   }
-  if (bn == 128) return launch<128, 6>(tmA, tmB, p, stream);
-  return launch<64, 8>(tmA, tmB, p, stream);
+  if (bn == 128) return launch<128, 6>(tmA, tmB, tmO, p, stream);
+  return launch<64, 8>(tmA, tmB, tmO, p, stream);
 }
 
 }  // namespace scb

@@ -50,3 +50,71 @@ def test_gemm_epilogue(act, out_dtype, res_dtype):
     tol = 2e-3 if out_dtype == torch.float32 else 8e-3
     assert (out.float() - ref).abs().max().item() < tol
     assert (out2.float() - ref).abs().max().item() < 8e-3
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+@pytest.mark.parametrize("M,N,K,bias", [(700, 776, 320, True), (20000, 2304, 768, True), (4097, 3072, 768, False),
+                                        (9000, 264, 128, True)])
+def test_gemm_tma_store_epilogue(act, M, N, K, bias):
+    """16-bit output, no residual, no second output, N > 128: the epilogue leaves through TMA stores (32 x 64 boxes clipped by
+    the tensor map at the M and N edges; single-CTA kernel below 74 tile pairs, CTA pairs above)."""
+    from speechclip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + act)
+    a = torch.randn(M, K, device="cuda", generator=g).half()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).half()
+    b = torch.randn(N, device="cuda", generator=g) if bias else None
+    guard = torch.full((M + 64, N), 7.0, device="cuda", dtype=torch.float16)
+    out = guard[:M]
+    ops.gemm(a, w, bias=b, act=act, out=out, alpha=1.5)
+    torch.cuda.synchronize()
+    ref = _ref(a, w, b, act, None, 1.5)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 8e-3, err
+    assert (guard[M:] == 7.0).all()  # rows past M are clipped, not written
+
+
+@pytest.mark.parametrize("tap", [0, 1])
+def test_gemm_tma_store_batched_ragged_rows(tap):
+    """Batched output whose rows per batch are not a multiple of the 32-row store box (the conv stack: [B][T_out][512]): a box
+    that straddles the end of one batch must not spill into the next one."""
+    from speechclip_b200 import ops
+    B, T, C, N = 5, 333, 256, 512
+    g = torch.Generator(device="cuda").manual_seed(11 + tap)
+    x = torch.randn(B, T, C, device="cuda", generator=g).half()
+    if tap:  # stride-2, k = 2 conv over channel-last rows: pairs of frames are one 2C-wide row
+        T_out = T // 2
+        w = (torch.randn(N, 2 * C, device="cuda", generator=g) / (2 * C) ** 0.5).half()
+        out = torch.zeros(B, T_out, N, device="cuda", dtype=torch.float16)
+        ops.gemm_raw(a=x, a_inner=2 * C, a_rows=(T + 1) // 2, a_row_stride=2 * C, a_batch_stride=T * C, batch=B, m_per_batch=T_out,
+                     w=w, n=N, k=2 * C, kb_per_tap=2 * C // 64, tap_row_shift=1, out=out, ldc=N, out_batch_stride=T_out * N,
+                     act=ops.ACT_GELU)
+        ref = torch.nn.functional.gelu(x[:, :2 * T_out].reshape(B, T_out, 2 * C).float() @ w.float().t())
+    else:
+        w = (torch.randn(N, C, device="cuda", generator=g) / C ** 0.5).half()
+        out = torch.zeros(B, T, N, device="cuda", dtype=torch.float16)
+        ops.gemm_raw(a=x, a_inner=C, a_rows=T, a_row_stride=C, a_batch_stride=T * C, batch=B, m_per_batch=T, w=w, n=N, k=C,
+                     out=out, ldc=N, out_batch_stride=T * N, act=ops.ACT_GELU)
+        ref = torch.nn.functional.gelu(x.float() @ w.float().t())
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    assert err < 8e-3, err
+
+
+def test_gelu_h16_fit_error():
+    """The sigmoid-polynomial erf-GELU of the 16-bit epilogues stays within 3e-5 of erf-GELU before the fp16 rounding: checked
+    through a K = 64 identity contraction so the epilogue sees exactly the probe values."""
+    from speechclip_b200 import ops
+    n = 256
+    xs = torch.linspace(-12.0, 12.0, 1 << 20, device="cuda").half()  # 16384 rows: enough tiles to stay on the 256-wide kernel
+    # out[m, j] = a[m, :] . w[j, :] = probe value (m, j % 64): w = one-hot rows, a carries 64 probes per row
+    rows = xs.numel() // 64
+    a = xs.view(rows, 64).contiguous()
+    w = torch.zeros(n, 64, device="cuda", dtype=torch.float16)
+    w[torch.arange(n), torch.arange(n) % 64] = 1.0
+    out = ops.gemm(a, w, act=ops.ACT_GELU)
+    torch.cuda.synchronize()
+    probe = a.float()[:, torch.arange(n, device="cuda") % 64]
+    ref = torch.nn.functional.gelu(probe.double()).float()
+    err = (out.float() - ref).abs()
+    ulp = ref.abs().clamp_min(2.0 ** -14) * 2.0 ** -11  # half an fp16 ulp, roughly
+    assert (err <= ulp + 3e-5).all(), (err - ulp).max().item()
