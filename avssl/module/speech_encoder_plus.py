@@ -158,19 +158,24 @@ class FairseqSpeechEncoder_Hubert(nn.Module):
         slab = hidden.view(hidden.shape[0], B, T, d)
         if feat_select_idx is None:
             feat_select_idx = self.feat_select_idx
-        if engine.GRAPHS and (feat_select_idx != FEAT_SELECT_IDX_WEIGHTED_SUM_MODE or return_hidden_states):
-            slab = slab.clone()  # hidden states handed to the caller must survive the next forward (the plan reuses its buffers)
+        hand_out = feat_select_idx != FEAT_SELECT_IDX_WEIGHTED_SUM_MODE or return_hidden_states
+        if hand_out and slab.dtype != torch.float32:
+            user = slab.float()  # the post-LN tower keeps fp16 hidden states; callers get fp32 tensors like the reference's
+        elif hand_out and engine.GRAPHS:
+            user = slab.clone()  # hidden states handed to the caller must survive the next forward (the plan reuses its buffers)
+        else:
+            user = slab
 
-        states = lambda: tuple(slab[i] for i in range(slab.shape[0]))
+        states = lambda: tuple(user[i] for i in range(user.shape[0]))
         ret = []
         if feat_select_idx == "all":
-            ret.extend([{"last_hidden_state": slab[-1], "hidden_states": states()}, feat_len])
+            ret.extend([{"last_hidden_state": user[-1], "hidden_states": states()}, feat_len])
         elif feat_select_idx == FEAT_SELECT_IDX_WEIGHTED_SUM_MODE:
             ret.extend([self.weightedsum_layer(slab), feat_len])
         elif isinstance(feat_select_idx, list):
-            ret.extend([[slab[i] for i in feat_select_idx], feat_len])
+            ret.extend([[user[i] for i in feat_select_idx], feat_len])
         elif feat_select_idx == "last_hidden_state":
-            ret.extend([slab[-1], feat_len])
+            ret.extend([user[-1], feat_len])
         elif feat_select_idx == "hidden_states":
             ret.extend([states(), feat_len])
         else:

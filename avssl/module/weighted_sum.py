@@ -26,5 +26,7 @@ class WeightedSumLayer(nn.Module):
         assert slab.shape[0] == self.n_weights, slab.shape
         L, B, T, d = slab.shape
         arena = self._scb_arena_fn() if self._scb_arena_fn is not None else None
-        return WeightedSumFn.apply(self.weights, slab.detach().float().contiguous().view(L, B * T, d), B, T,
-                                   self.normalize_features, arena)
+        slab = slab.detach()
+        if slab.dtype != torch.float16:  # fp16 slabs (post-LN tower) are read as they are; anything else as fp32
+            slab = slab.float()
+        return WeightedSumFn.apply(self.weights, slab.contiguous().view(L, B * T, d), B, T, self.normalize_features, arena)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SCB_ABI_VERSION 1
+#define SCB_ABI_VERSION 2
 
 enum { SCB_OK = 0, SCB_EINVAL = -1, SCB_ECUDA = -2, SCB_EUNSUPPORTED = -3 };
 enum { SCB_F32 = 0, SCB_F16 = 1, SCB_BF16 = 2 };
@@ -168,7 +168,8 @@ int scb_transpose(const void* in, int32_t in_dtype, int64_t in_ld, void* out, in
  * scb_layernorm_bwd: dx, and dgamma/dbeta ACCUMULATED (+=).
  * scb_l2norm_*: x / ||x|| (kwClip.py:1436,1451-1453).
  * scb_weighted_sum_*: softmax(w)-weighted sum of the L hidden states (weighted_sum.py:26-45; normalize != 0 applies the
- *   parameter-free LayerNorm of :41-42 first).  h = [L] slabs of [rows][d] fp32 at layer_stride.  The 16-bit output can be
+ *   parameter-free LayerNorm of :41-42 first).  h = [L] slabs of [rows][d] (h_dtype: SCB_F32, or SCB_F16 for the
+ *   16-bit hidden states of the post-LN tower) at layer_stride (elements).  The 16-bit output can be
  *   scattered into the branch source buffer: row r of utterance b goes to out16 + b*out16_batch_stride + (out16_row0 + r)*d.
  *   bwd reads dout the same way and ACCUMULATES grad_scale * dL/dw into grad_logits.
  * scb_rows_bias_act: y = act(x + bias + res) on [rows][d] fp32 (res row stride res_ld; 0 = one row broadcast);
@@ -182,10 +183,10 @@ int scb_layernorm_bwd(const float* dy, const float* x, const float* stats, const
                       int64_t rows, int32_t d, void* stream);
 int scb_l2norm_fwd(const float* x, float* y, float* norms, int32_t rows, int32_t d, void* stream);
 int scb_l2norm_bwd(const float* dy, const float* y, const float* norms, float* dx, int32_t rows, int32_t d, void* stream);
-int scb_weighted_sum_fwd(const float* h, int64_t layer_stride, const float* w_logits, int32_t L, int32_t normalize, float* out32,
+int scb_weighted_sum_fwd(const void* h, int32_t h_dtype, int64_t layer_stride, const float* w_logits, int32_t L, int32_t normalize, float* out32,
                          void* out16, int32_t out16_fmt, int64_t rows, int32_t d, int32_t rows_per_batch, int64_t out16_batch_stride,
                          int64_t out16_row0, void* stream);
-int scb_weighted_sum_bwd(const float* h, int64_t layer_stride, const float* w_logits, int32_t L, int32_t normalize, const float* dout,
+int scb_weighted_sum_bwd(const void* h, int32_t h_dtype, int64_t layer_stride, const float* w_logits, int32_t L, int32_t normalize, const float* dout,
                          int64_t rows, int32_t d, int32_t rows_per_batch, int64_t dout_batch_stride, int64_t dout_row0,
                          float* scratch_L, float* grad_logits, float grad_scale, void* stream);
 int scb_rows_bias_act(const float* x, int64_t x_ld, const float* bias, const float* res, int64_t res_ld, int32_t act, float* pre, float* y,

@@ -173,16 +173,16 @@ int scb_l2norm_fwd(const float* x, float* y, float* norms, int32_t rows, int32_t
 int scb_l2norm_bwd(const float* dy, const float* y, const float* norms, float* dx, int32_t rows, int32_t d, void* stream) {
   return scb::l2norm_bwd(dy, y, norms, dx, rows, d, ST);
 }
-int scb_weighted_sum_fwd(const float* h, int64_t layer_stride, const float* w_logits, int32_t L, int32_t normalize, float* out32,
+int scb_weighted_sum_fwd(const void* h, int32_t h_dtype, int64_t layer_stride, const float* w_logits, int32_t L, int32_t normalize, float* out32,
                          void* out16, int32_t out16_fmt, int64_t rows, int32_t d, int32_t rows_per_batch, int64_t out16_batch_stride,
                          int64_t out16_row0, void* stream) {
-  return scb::weighted_sum_fwd(h, layer_stride, w_logits, L, normalize, out32, out16, out16_fmt, rows, d, rows_per_batch,
+  return scb::weighted_sum_fwd(h, h_dtype, layer_stride, w_logits, L, normalize, out32, out16, out16_fmt, rows, d, rows_per_batch,
                                out16_batch_stride, out16_row0, ST);
 }
-int scb_weighted_sum_bwd(const float* h, int64_t layer_stride, const float* w_logits, int32_t L, int32_t normalize, const float* dout,
+int scb_weighted_sum_bwd(const void* h, int32_t h_dtype, int64_t layer_stride, const float* w_logits, int32_t L, int32_t normalize, const float* dout,
                          int64_t rows, int32_t d, int32_t rows_per_batch, int64_t dout_batch_stride, int64_t dout_row0,
                          float* scratch_L, float* grad_logits, float grad_scale, void* stream) {
-  return scb::weighted_sum_bwd(h, layer_stride, w_logits, L, normalize, dout, rows, d, rows_per_batch, dout_batch_stride, dout_row0,
+  return scb::weighted_sum_bwd(h, h_dtype, layer_stride, w_logits, L, normalize, dout, rows, d, rows_per_batch, dout_batch_stride, dout_row0,
                                scratch_L, grad_logits, grad_scale, ST);
 }
 int scb_rows_bias_act(const float* x, int64_t x_ld, const float* bias, const float* res, int64_t res_ld, int32_t act, float* pre, float* y,

@@ -94,6 +94,12 @@ __global__ void conv0_finalize_kernel(const double* __restrict__ acc, const floa
 // and walks frame tiles of 16.  The fragment column -> channel map is chosen so that every lane ends up with 32 CONTIGUOUS
 // channels of a frame (64 bytes): column j of n-block n is channel (j/2)*32 + n*2 + (j%2).
 constexpr int kFramesPerBlock = 128;
+template <int FMT>
+__device__ __forceinline__ uint32_t gelu_pack(float a, float b) {  // two activations on the packed-fp32 path, then one 16-bit pair
+  float lo, hi;
+  upk2(gelu_h16_x2(pk2(a, b)), lo, hi);
+  return H16<FMT>::pack(lo, hi);
+}
 __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restrict__ wav, long long wav_ld, const float* __restrict__ w,
                                                           const float2* __restrict__ scale_shift, void* __restrict__ out, int out_fmt,
                                                           int n_frames, long long out_batch_stride, int channels) {
@@ -158,15 +164,15 @@ __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restric
       }
       uint4 ua, ub;
       if (bf) {
-        ua.x = H16<SCB_BF16>::pack(gelu_fast(c[0][0]), gelu_fast(c[0][1])); ua.y = H16<SCB_BF16>::pack(gelu_fast(c[1][0]), gelu_fast(c[1][1]));
-        ua.z = H16<SCB_BF16>::pack(gelu_fast(c[2][0]), gelu_fast(c[2][1])); ua.w = H16<SCB_BF16>::pack(gelu_fast(c[3][0]), gelu_fast(c[3][1]));
-        ub.x = H16<SCB_BF16>::pack(gelu_fast(c[0][2]), gelu_fast(c[0][3])); ub.y = H16<SCB_BF16>::pack(gelu_fast(c[1][2]), gelu_fast(c[1][3]));
-        ub.z = H16<SCB_BF16>::pack(gelu_fast(c[2][2]), gelu_fast(c[2][3])); ub.w = H16<SCB_BF16>::pack(gelu_fast(c[3][2]), gelu_fast(c[3][3]));
+        ua.x = gelu_pack<SCB_BF16>(c[0][0], c[0][1]); ua.y = gelu_pack<SCB_BF16>(c[1][0], c[1][1]);
+        ua.z = gelu_pack<SCB_BF16>(c[2][0], c[2][1]); ua.w = gelu_pack<SCB_BF16>(c[3][0], c[3][1]);
+        ub.x = gelu_pack<SCB_BF16>(c[0][2], c[0][3]); ub.y = gelu_pack<SCB_BF16>(c[1][2], c[1][3]);
+        ub.z = gelu_pack<SCB_BF16>(c[2][2], c[2][3]); ub.w = gelu_pack<SCB_BF16>(c[3][2], c[3][3]);
       } else {
-        ua.x = H16<SCB_F16>::pack(gelu_fast(c[0][0]), gelu_fast(c[0][1])); ua.y = H16<SCB_F16>::pack(gelu_fast(c[1][0]), gelu_fast(c[1][1]));
-        ua.z = H16<SCB_F16>::pack(gelu_fast(c[2][0]), gelu_fast(c[2][1])); ua.w = H16<SCB_F16>::pack(gelu_fast(c[3][0]), gelu_fast(c[3][1]));
-        ub.x = H16<SCB_F16>::pack(gelu_fast(c[0][2]), gelu_fast(c[0][3])); ub.y = H16<SCB_F16>::pack(gelu_fast(c[1][2]), gelu_fast(c[1][3]));
-        ub.z = H16<SCB_F16>::pack(gelu_fast(c[2][2]), gelu_fast(c[2][3])); ub.w = H16<SCB_F16>::pack(gelu_fast(c[3][2]), gelu_fast(c[3][3]));
+        ua.x = gelu_pack<SCB_F16>(c[0][0], c[0][1]); ua.y = gelu_pack<SCB_F16>(c[1][0], c[1][1]);
+        ua.z = gelu_pack<SCB_F16>(c[2][0], c[2][1]); ua.w = gelu_pack<SCB_F16>(c[3][0], c[3][1]);
+        ub.x = gelu_pack<SCB_F16>(c[0][2], c[0][3]); ub.y = gelu_pack<SCB_F16>(c[1][2], c[1][3]);
+        ub.z = gelu_pack<SCB_F16>(c[2][2], c[2][3]); ub.w = gelu_pack<SCB_F16>(c[3][2], c[3][3]);
       }
       if (ok_a) *reinterpret_cast<uint4*>(oa + q4 * 8) = ua;
       if (ok_b) *reinterpret_cast<uint4*>(ob + q4 * 8) = ub;

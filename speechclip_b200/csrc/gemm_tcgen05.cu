@@ -650,18 +650,46 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
   SCB_CHECK(a.kb_per_tap > 0, SCB_EINVAL, "scb_gemm: kb_per_tap must be positive");
   SCB_CHECK(a.groups == 1 || a.out_group_cols >= a.n, SCB_EINVAL, "scb_gemm: out_group_cols < n");
 
-  // Tile width: 256 columns for throughput; when that leaves most of the 148 SMs without a tile (CLIP ViT and the head at small
-  // per-GPU batch: strong scaling at 32 pairs per GPU), narrower tiles trade per-tile efficiency for occupancy.
-  int bn = a.n > 128 ? 256 : (a.n > 64 ? 128 : 64);
-  {
-    const long long mt = (long long)a.batch * a.groups * ((a.m_per_batch + BM - 1) / BM);
-    while (bn > 64 && mt * ((a.n + bn - 1) / bn) < (num_sms() * 3) / 4) bn >>= 1;
-  }
-  // CTA pairs (256 x 256 tiles) for the large shapes; SCB_GEMM_2CTA=0 keeps every problem on the single-CTA kernel
+  // Tile shape.  256-wide tiles (CTA pairs: 256 x 256) carry the large problems.  When M is small (CLIP ViT and the head at 32-64
+  // pairs per GPU: strong scaling) the choice is between few large tiles on part of the SMs and many small tiles on all of
+  // them; small tiles pull (128 + BN) x 128 B per k-block for 128 x BN x 64 MACs, so they are bound by the L2 -> SM path, and
+  // a tile count just above the SM count (156 tiles of 128 x 64 for M = 1600, N = 768) costs a second wave.  pick_tile()
+  // estimates each candidate with a two-term model (MMA clocks vs operand bytes over min(per-SM, chip / active SMs) bandwidth).
   static const int two_env = [] { const char* e = getenv("SCB_GEMM_2CTA"); return e ? atoi(e) : 1; }();
-  // (the tap-walk conv GEMMs measured 7 % faster on single CTAs, the plain linears 2-3 % faster on pairs)
-  const bool two = two_env != 0 && bn == 256 && a.m_per_batch >= 256 && a.tap_row_shift == 0 &&
-                   (long long)a.batch * a.groups * ((a.m_per_batch + 255) / 256) * ((a.n + 255) / 256) >= num_sms() / 2;
+  static const int force_bn = [] { const char* e = getenv("SCB_GEMM_FORCE_BN"); return e ? atoi(e) : 0; }();      // tuning sweeps
+  static const int force_two = [] { const char* e = getenv("SCB_GEMM_FORCE_2CTA"); return e ? atoi(e) : -1; }();
+  const long long mt1 = (long long)a.batch * a.groups * ((a.m_per_batch + BM - 1) / BM);
+  const long long mt2 = (long long)a.batch * a.groups * ((a.m_per_batch + 255) / 256);
+  const bool two_ok = two_env != 0 && a.n > 128 && a.m_per_batch >= 256 && a.tap_row_shift == 0;
+  int bn = a.n > 128 ? 256 : (a.n > 64 ? 128 : 64);
+  bool two = false;
+  {
+    const int kb = (a.k + (BK * 2 / eb) - 1) / (BK * 2 / eb);
+    const int sms = num_sms();
+    double best = 1e30;
+    for (int cand = 0; cand < 4; ++cand) {  // 0..2: single CTA with BN = 64 / 128 / 256; 3: CTA pair 256 x 256
+      const int cbn = cand == 3 ? 256 : (64 << cand);
+      if (cand < 3 && cbn > bn) continue;            // never wider than the padded N
+      if (cand == 3 && !two_ok) continue;
+      const long long tiles = (cand == 3 ? mt2 : mt1) * ((a.n + cbn - 1) / cbn);
+      const int slots = cand == 3 ? sms / 2 : sms;
+      const long long waves = (tiles + slots - 1) / slots;
+      const double active = (double)(tiles < slots ? tiles : slots) * (cand == 3 ? 2 : 1);
+      const double bw = fmin(64.0, 8500.0 / active);                                   // bytes per clock per CTA
+      const double bytes = (cand == 3 ? (BM + 128) : (BM + cbn)) * 128.0;             // per CTA per k-block
+      const double mma = cbn * 2.0;                                                    // 128 x BN x 64 MACs at 4096 MAC / clk
+      const double t = 2000.0 + (double)waves * (kb * fmax(mma, bytes / bw) + 600.0) + cbn * 8.0;  // fill + main loops + last epilogue
+      if (t < best) {
+        best = t;
+        bn = cbn;
+        two = cand == 3;
+      }
+    }
+    // (the tap-walk conv GEMMs measured 7 % faster on single CTAs, the plain linears 2-3 % faster on pairs)
+    if (force_bn) bn = force_bn;
+    if (force_two >= 0) two = force_two != 0 && a.m_per_batch >= 256 && a.tap_row_shift == 0;
+    if (two) bn = 256;
+  }
   GemmParams p{};
   p.batch = a.batch;
   p.m_tiles_per_batch = two ? (a.m_per_batch + 255) / 256 : (a.m_per_batch + BM - 1) / BM;

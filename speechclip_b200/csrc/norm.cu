@@ -180,10 +180,11 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const float* __restrict
     dx[(long long)row * d + c] = (dy[(long long)row * d + c] - y[(long long)row * d + c] * dot) * inv;
 }
 
-// out = sum_l softmax(w)_l * h_l   (weighted_sum.py:38-43), h = [L][rows][d] fp32 with layer stride.
+// out = sum_l softmax(w)_l * h_l   (weighted_sum.py:38-43), h = [L][rows][d] (fp32, or the fp16 hidden states the post-LN
+// tower keeps: half the bytes of the 13-layer read) with layer stride.
 // NORMALIZE: parameter-free LayerNorm over d on every h_l first (weighted_sum.py:41-42).  One warp per row.
-template <bool NORMALIZE>
-__global__ void __launch_bounds__(256) weighted_sum_fwd_kernel(const float* __restrict__ h, long long layer_stride,
+template <bool NORMALIZE, typename TH>
+__global__ void __launch_bounds__(256) weighted_sum_fwd_kernel(const TH* __restrict__ h, long long layer_stride,
                                                                const float* __restrict__ w_logits, int L,
                                                                float* __restrict__ out32, void* __restrict__ out16, int out16_fmt,
                                                                long long rows, int d, int rows_per_batch,
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(256) weighted_sum_fwd_kernel(const float* __re
 #pragma unroll
   for (int i = 0; i < kMaxVec; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int l = 0; l < L; ++l) {
-    const float* hr = h + (long long)l * layer_stride + row * d;
+    const TH* hr = h + (long long)l * layer_stride + row * d;
     const float wl = sw[l];
     float4 v[kMaxVec];
     float s = 0.f;
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(256) weighted_sum_fwd_kernel(const float* __re
     for (int i = 0; i < kMaxVec; ++i) {
       const int c = lane + i * 32;
       if (c < nvec) {
-        v[i] = *reinterpret_cast<const float4*>(hr + c * 4);
+        v[i] = load4<TH>(hr + c * 4);
         if (NORMALIZE) s += v[i].x + v[i].y + v[i].z + v[i].w;
       }
     }
@@ -258,8 +259,8 @@ __global__ void __launch_bounds__(256) weighted_sum_fwd_kernel(const float* __re
 // dw_l = sum_{r,c} dout[r,c] * h_l[r,c]  (h optionally LayerNorm'ed first); then softmax backward into dlogits.
 // dout rows may live inside a larger per-batch buffer (branch input gradient): row r of batch b is at
 // dout + b*dout_batch_stride + (dout_row0 + r)*d.
-template <bool NORMALIZE>
-__global__ void __launch_bounds__(256) weighted_sum_bwd_kernel(const float* __restrict__ h, long long layer_stride, int L,
+template <bool NORMALIZE, typename TH>
+__global__ void __launch_bounds__(256) weighted_sum_bwd_kernel(const TH* __restrict__ h, long long layer_stride, int L,
                                                                const float* __restrict__ dout, long long rows, int d,
                                                                int rows_per_batch, long long dout_batch_stride, long long dout_row0,
                                                                float* __restrict__ dw_raw) {
@@ -284,14 +285,14 @@ __global__ void __launch_bounds__(256) weighted_sum_bwd_kernel(const float* __re
 #pragma unroll
     for (int l = 0; l < 32; ++l) {
       if (l < L) {
-        const float* hr = h + (long long)l * layer_stride + row * d;
+        const TH* hr = h + (long long)l * layer_stride + row * d;
         float4 v[kMaxVec];
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < kMaxVec; ++i) {
           const int c = lane + i * 32;
           if (c < nvec) {
-            v[i] = *reinterpret_cast<const float4*>(hr + c * 4);
+            v[i] = load4<TH>(hr + c * 4);
             if (NORMALIZE) s += v[i].x + v[i].y + v[i].z + v[i].w;
           }
         }
@@ -409,28 +410,35 @@ int l2norm_bwd(const float* dy, const float* y, const float* norms, float* dx, i
   return SCB_OK;
 }
 
-int weighted_sum_fwd(const float* h, long long layer_stride, const float* w_logits, int L, int normalize, float* out32, void* out16,
+int weighted_sum_fwd(const void* h, int h_dtype, long long layer_stride, const float* w_logits, int L, int normalize, float* out32, void* out16,
                      int out16_fmt, long long rows, int d, int rows_per_batch, long long out16_batch_stride, long long out16_row0,
                      cudaStream_t st) {
   SCB_CHECK(h && w_logits && (out32 || out16), SCB_EINVAL, "scb_weighted_sum: null operand");
+  SCB_CHECK(h_dtype == SCB_F32 || h_dtype == SCB_F16, SCB_EUNSUPPORTED, "scb_weighted_sum: hidden states must be fp32 or fp16");
   SCB_CHECK(L >= 1 && L <= 64, SCB_EUNSUPPORTED, "scb_weighted_sum: L=%d out of range [1,64]", L);
   SCB_CHECK(d % 4 == 0 && d <= 32 * 4 * kMaxVec, SCB_EUNSUPPORTED, "scb_weighted_sum: unsupported d=%d", d);
   if (rows == 0) return SCB_OK;
   if (rows_per_batch <= 0) rows_per_batch = (int)rows;
   const unsigned grid = (unsigned)((rows + 7) / 8);
-  if (normalize)
-    weighted_sum_fwd_kernel<true><<<grid, 256, 0, st>>>(h, layer_stride, w_logits, L, out32, out16, out16_fmt, rows, d, rows_per_batch, out16_batch_stride, out16_row0);
-  else
-    weighted_sum_fwd_kernel<false><<<grid, 256, 0, st>>>(h, layer_stride, w_logits, L, out32, out16, out16_fmt, rows, d, rows_per_batch, out16_batch_stride, out16_row0);
+#define SCB_WS_FWD(NORM, TH) \
+  weighted_sum_fwd_kernel<NORM, TH><<<grid, 256, 0, st>>>(static_cast<const TH*>(h), layer_stride, w_logits, L, out32, out16, out16_fmt, \
+                                                          rows, d, rows_per_batch, out16_batch_stride, out16_row0)
+  if (h_dtype == SCB_F16) {
+    if (normalize) SCB_WS_FWD(true, __half); else SCB_WS_FWD(false, __half);
+  } else {
+    if (normalize) SCB_WS_FWD(true, float); else SCB_WS_FWD(false, float);
+  }
+#undef SCB_WS_FWD
   note_launch();
   SCB_LAUNCH_OK("weighted_sum_fwd");
   return SCB_OK;
 }
 
-int weighted_sum_bwd(const float* h, long long layer_stride, const float* w_logits, int L, int normalize, const float* dout,
+int weighted_sum_bwd(const void* h, int h_dtype, long long layer_stride, const float* w_logits, int L, int normalize, const float* dout,
                      long long rows, int d, int rows_per_batch, long long dout_batch_stride, long long dout_row0, float* scratch_L,
                      float* grad_logits, float grad_scale, cudaStream_t st) {
   SCB_CHECK(h && w_logits && dout && scratch_L && grad_logits, SCB_EINVAL, "scb_weighted_sum_bwd: null operand");
+  SCB_CHECK(h_dtype == SCB_F32 || h_dtype == SCB_F16, SCB_EUNSUPPORTED, "scb_weighted_sum_bwd: hidden states must be fp32 or fp16");
   SCB_CHECK(L >= 1 && L <= 32, SCB_EUNSUPPORTED, "scb_weighted_sum_bwd: L=%d out of range [1,32]", L);
   SCB_CHECK(d % 4 == 0 && d <= 32 * 4 * kMaxVec, SCB_EUNSUPPORTED, "scb_weighted_sum_bwd: unsupported d=%d", d);
   if (rows_per_batch <= 0) rows_per_batch = (int)rows;
@@ -438,10 +446,15 @@ int weighted_sum_bwd(const float* h, long long layer_stride, const float* w_logi
   if (rows > 0) {
     long long blocks = (rows + 7) / 8;
     if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
-    if (normalize)
-      weighted_sum_bwd_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(h, layer_stride, L, dout, rows, d, rows_per_batch, dout_batch_stride, dout_row0, scratch_L);
-    else
-      weighted_sum_bwd_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(h, layer_stride, L, dout, rows, d, rows_per_batch, dout_batch_stride, dout_row0, scratch_L);
+#define SCB_WS_BWD(NORM, TH) \
+  weighted_sum_bwd_kernel<NORM, TH><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const TH*>(h), layer_stride, L, dout, rows, d, \
+                                                                      rows_per_batch, dout_batch_stride, dout_row0, scratch_L)
+    if (h_dtype == SCB_F16) {
+      if (normalize) SCB_WS_BWD(true, __half); else SCB_WS_BWD(false, __half);
+    } else {
+      if (normalize) SCB_WS_BWD(true, float); else SCB_WS_BWD(false, float);
+    }
+#undef SCB_WS_BWD
     note_launch();
     SCB_LAUNCH_OK("weighted_sum_bwd");
   }

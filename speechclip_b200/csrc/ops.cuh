@@ -49,10 +49,10 @@ int layernorm_bwd(const float* dy, const float* x, const float* stats, const flo
                   long long rows, int d, cudaStream_t st);
 int l2norm_fwd(const float* x, float* y, float* norms, int rows, int d, cudaStream_t st);
 int l2norm_bwd(const float* dy, const float* y, const float* norms, float* dx, int rows, int d, cudaStream_t st);
-int weighted_sum_fwd(const float* h, long long layer_stride, const float* w_logits, int L, int normalize, float* out32, void* out16,
+int weighted_sum_fwd(const void* h, int h_dtype, long long layer_stride, const float* w_logits, int L, int normalize, float* out32, void* out16,
                      int out16_fmt, long long rows, int d, int rows_per_batch, long long out16_batch_stride, long long out16_row0,
                      cudaStream_t st);
-int weighted_sum_bwd(const float* h, long long layer_stride, const float* w_logits, int L, int normalize, const float* dout,
+int weighted_sum_bwd(const void* h, int h_dtype, long long layer_stride, const float* w_logits, int L, int normalize, const float* dout,
                      long long rows, int d, int rows_per_batch, long long dout_batch_stride, long long dout_row0, float* scratch_L,
                      float* grad_logits, float grad_scale, cudaStream_t st);
 // optim.cu

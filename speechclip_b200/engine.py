@@ -50,6 +50,7 @@ class Workspace:
         return self.get(name, int(math.prod(shape)), dtype, zero).view(*shape)
 
 
+HIDDEN16 = os.environ.get("SCB_HIDDEN_FP32", "0") != "1"   # post-LN towers: fp16 hidden states / residual stream (see HubertPlan._forward)
 LAYER_CHUNKS = int(os.environ.get("SCB_LAYER_CHUNKS", "1"))   # batch slices for the transformer layer stack (L2 residency)
 GRAPHS = os.environ.get("SCB_CUDA_GRAPHS", "1") != "0"   # replay the frozen towers as CUDA graphs (launch-bound at small batch)
 MAX_GRAPHS = 4                                            # per plan; further input shapes run eagerly
@@ -135,11 +136,13 @@ class EncoderLayerPlan:
         self.d = self.wo.shape[0]
         self.ffn = self.w1.shape[0]
 
-    def forward(self, ws: Workspace, x32: torch.Tensor, x16: Optional[torch.Tensor], out32: torch.Tensor, B: int, T: int,
-                kv_len: Optional[torch.Tensor], causal: bool = False, want_x16: bool = True, tag: str = "",
+    def forward(self, ws: Workspace, x32: Optional[torch.Tensor], x16: Optional[torch.Tensor], out32: Optional[torch.Tensor], B: int,
+                T: int, kv_len: Optional[torch.Tensor], causal: bool = False, want_x16: bool = True, tag: str = "",
                 out16: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
         """x32: fp32 [B*T, d] residual stream in; x16: its fp16 copy (post-LN only; None for pre-LN).
-        out32: fp32 [B*T, d] receives the layer output.  Returns the fp16 copy of the output (post-LN) or None."""
+        out32: fp32 [B*T, d] receives the layer output.  Returns the fp16 copy of the output (post-LN) or None.
+        Post-LN layers also run with x32 = out32 = None: the LayerNorm outputs (bounded by gamma / beta, safe in fp16) then exist
+        only as fp16 — GEMM operand, residual and hidden state in one tensor — while the pre-LayerNorm sums stay fp32."""
         d, M = self.d, B * T
         hd = d // self.heads
         qkv = ws.view(tag + "qkv", (B, T, 3 * d), H)
@@ -161,11 +164,11 @@ class EncoderLayerPlan:
             ops.gemm(ffn, self.w2, bias=self.b2, residual=xa, out=out32)
             return None
         y = ws.view(tag + "y", (M, d), torch.float32)
-        x1 = ws.view(tag + "x1", (M, d), torch.float32)
-        ops.gemm(ctx.view(M, d), self.wo, bias=self.bo, residual=x32, out=y)
+        x1 = ws.view(tag + "x1", (M, d), torch.float32) if x32 is not None else None
+        ops.gemm(ctx.view(M, d), self.wo, bias=self.bo, residual=x32 if x32 is not None else x16, out=y)
         ops.layernorm(y, *self.ln1, y32=x1, y16=a16, rows=M, d=d, eps=self.eps)
         ops.gemm(a16, self.w1, bias=self.b1, act=self.act, out=ffn)
-        ops.gemm(ffn, self.w2, bias=self.b2, residual=x1, out=y)
+        ops.gemm(ffn, self.w2, bias=self.b2, residual=x1 if x1 is not None else a16, out=y)
         o16 = out16 if out16 is not None else (ws.view(tag + "o16", (M, d), H) if want_x16 else None)
         ops.layernorm(y, *self.ln2, y32=out32, y16=o16, rows=M, d=d, eps=self.eps)
         return o16
@@ -273,14 +276,19 @@ class HubertPlan:
         rows_pad = T + K
         xpad = ws.view(f"xpad_{B}_{T}", (B, rows_pad, G * 64), H, zero=True)
         ops.posconv_pack(x, valid_frames, xpad, B, T, d, G, K // 2, rows_pad)
-        hidden = torch.empty(self.n_hidden, M, d, device=self.dev, dtype=torch.float32)
+        # Post-LN towers (HuBERT-base) keep the hidden states — LayerNorm outputs — in fp16 only: one tensor is the next GEMM's
+        # operand, the residual and the state the weighted sum reads (HIDDEN16; SCB_HIDDEN_FP32=1 restores fp32 copies).
+        h16 = HIDDEN16 and not self.pre_ln
+        hidden = torch.empty(self.n_hidden, M, d, device=self.dev, dtype=H if h16 else torch.float32)
         tgt = hidden[0] if self.pre_ln else x
         ops.gemm_raw(a=xpad, a_inner=G * 64, a_rows=rows_pad, a_row_stride=G * 64, a_batch_stride=rows_pad * G * 64, batch=B,
                      m_per_batch=T, w=self.pos_w, n=cpg, k=K * 64, groups=G, b_group_stride=cpg * K * 64, kb_per_tap=1,
                      tap_row_shift=1, a_group_cols=64, out=tgt, ldc=d, out_batch_stride=T * d, out_group_cols=cpg,
                      bias=self.pos_b, act=ops.ACT_GELU, residual=x, algo_k=K * cpg)
         x16s = None
-        if not self.pre_ln:
+        if h16:
+            ops.layernorm(x, *self.enc_ln, y16=hidden[0], rows=M, d=d, eps=1e-5)
+        elif not self.pre_ln:
             x16s = [ws.view("hub_x16_a", (M, d), H), ws.view("hub_x16_b", (M, d), H)]
             ops.layernorm(x, *self.enc_ln, y32=hidden[0], y16=x16s[0], rows=M, d=d, eps=1e-5)
         # The layer stack runs over slices of the batch: with all 256 utterances a layer's intermediates (QKV 376 MB, MLP 502 MB,
@@ -295,8 +303,11 @@ class HubertPlan:
             for c in range(chunks):
                 rows = slice(c * Mc, (c + 1) * Mc)
                 vf = valid_frames[c * Bc:(c + 1) * Bc] if valid_frames is not None else None
-                layer.forward(ws, hidden[l][rows], None if self.pre_ln else x16s[cur][rows], hidden[l + 1][rows], Bc, T, vf, tag="hub_",
-                              out16=None if self.pre_ln else x16s[1 - cur][rows])
+                if h16:
+                    layer.forward(ws, None, hidden[l][rows], None, Bc, T, vf, tag="hub_", out16=hidden[l + 1][rows])
+                else:
+                    layer.forward(ws, hidden[l][rows], None if self.pre_ln else x16s[cur][rows], hidden[l + 1][rows], Bc, T, vf, tag="hub_",
+                                  out16=None if self.pre_ln else x16s[1 - cur][rows])
             cur = 1 - cur  # fp16 copies ping-pong: later slices of this layer still read the previous layer's copy
         return hidden, T
 

@@ -81,7 +81,7 @@ def _grad_like(p: torch.Tensor, arena: Optional[GradArena], buf: int) -> torch.T
 
 # ---------------------------------------------------------------------------------------------------- weighted sum
 class WeightedSumFn(torch.autograd.Function):
-    """avssl/module/weighted_sum.py:26-45.  hidden fp32 [L, B*T, d] (frozen tower output, no grad)."""
+    """avssl/module/weighted_sum.py:26-45.  hidden fp32 or fp16 [L, B*T, d] (frozen tower output, no grad)."""
 
     @staticmethod
     def forward(ctx, weights, hidden, B, T, normalize, arena):

@@ -115,8 +115,8 @@ def _declare(lib):
         "scb_layernorm_bwd": [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
         "scb_l2norm_fwd": [vp, vp, vp, i32, i32, vp],
         "scb_l2norm_bwd": [vp, vp, vp, vp, i32, i32, vp],
-        "scb_weighted_sum_fwd": [vp, i64, vp, i32, i32, vp, vp, i32, i64, i32, i32, i64, i64, vp],
-        "scb_weighted_sum_bwd": [vp, i64, vp, i32, i32, vp, i64, i32, i32, i64, i64, vp, vp, f32, vp],
+        "scb_weighted_sum_fwd": [vp, i32, i64, vp, i32, i32, vp, vp, i32, i64, i32, i32, i64, i64, vp],
+        "scb_weighted_sum_bwd": [vp, i32, i64, vp, i32, i32, vp, i64, i32, i32, i64, i64, vp, vp, f32, vp],
         "scb_rows_bias_act": [vp, i64, vp, vp, i64, i32, vp, vp, i64, i64, i32, vp],
         "scb_gelu_bwd": [vp, vp, vp, i64, vp],
         "scb_column_sum": [vp, i32, i64, i64, i32, vp, f32, vp],

@@ -241,15 +241,15 @@ def l2norm_bwd(dy, y, norms, dx):
 
 
 def weighted_sum(h, w_logits, normalize, *, out32=None, out16=None, rows_per_batch=0, out16_batch_stride=0, out16_row0=0):
-    """h: [L, rows, d] fp32 (contiguous)."""
+    """h: [L, rows, d] fp32 or fp16 (contiguous)."""
     L, rows, d = h.shape
-    _call("scb_weighted_sum_fwd", _p(h), h.stride(0), _p(w_logits), L, int(normalize), _p(out32), _p(out16),
+    _call("scb_weighted_sum_fwd", _p(h), _DT[h.dtype], h.stride(0), _p(w_logits), L, int(normalize), _p(out32), _p(out16),
           _DT[out16.dtype] if out16 is not None else 0, rows, d, rows_per_batch, out16_batch_stride, out16_row0)
 
 
 def weighted_sum_bwd(h, w_logits, normalize, dout, rows_per_batch, dout_batch_stride, dout_row0, scratch_L, grad_logits, grad_scale=1.0):
     L, rows, d = h.shape
-    _call("scb_weighted_sum_bwd", _p(h), h.stride(0), _p(w_logits), L, int(normalize), _p(dout), rows, d, rows_per_batch,
+    _call("scb_weighted_sum_bwd", _p(h), _DT[h.dtype], h.stride(0), _p(w_logits), L, int(normalize), _p(dout), rows, d, rows_per_batch,
           dout_batch_stride, dout_row0, _p(scratch_L), _p(grad_logits), grad_scale)
 
 

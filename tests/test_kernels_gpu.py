@@ -87,13 +87,14 @@ def test_l2norm_fwd_bwd():
 
 @pytest.mark.parametrize("normalize", [False, True])
 @pytest.mark.parametrize("L,d", [(13, 768), (25, 1024), (3, 64)])
-def test_weighted_sum_fwd_bwd(normalize, L, d, golden):
+@pytest.mark.parametrize("hdt", [torch.float32, torch.float16])
+def test_weighted_sum_fwd_bwd(normalize, L, d, hdt, golden):
     from oracle import speechclip as osc
     from speechclip_b200 import ops
     B, T = 3, 17
-    h = randn(L, B * T, d, seed=14)
+    h = randn(L, B * T, d, seed=14).to(hdt)  # fp16: the hidden states of the post-LN tower (the oracle sees the same rounded values)
     w = (0.5 * randn(L, seed=15)).requires_grad_()
-    ref = osc.weighted_sum(w, list(h.view(L, B, T, d)), normalize)
+    ref = osc.weighted_sum(w, list(h.float().view(L, B, T, d)), normalize)
     out32 = torch.empty(B * T, d, device=DEV)
     src16 = torch.zeros(B, T + 1, d, device=DEV, dtype=torch.float16)
     ops.weighted_sum(h, w.detach(), normalize, out32=out32, out16=src16, rows_per_batch=T, out16_batch_stride=(T + 1) * d, out16_row0=1)
