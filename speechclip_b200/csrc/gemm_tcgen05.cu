@@ -661,7 +661,8 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
   const long long mt1 = (long long)a.batch * a.groups * ((a.m_per_batch + BM - 1) / BM);
   const long long mt2 = (long long)a.batch * a.groups * ((a.m_per_batch + 255) / 256);
   const bool two_ok = two_env != 0 && a.n > 128 && a.m_per_batch >= 256 && a.tap_row_shift == 0;
-  int bn = a.n > 128 ? 256 : (a.n > 64 ? 128 : 64);
+  const int bn_max = a.n > 128 ? 256 : (a.n > 64 ? 128 : 64);
+  int bn = bn_max;
   bool two = false;
   {
     const int kb = (a.k + (BK * 2 / eb) - 1) / (BK * 2 / eb);
@@ -669,7 +670,7 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
     double best = 1e30;
     for (int cand = 0; cand < 4; ++cand) {  // 0..2: single CTA with BN = 64 / 128 / 256; 3: CTA pair 256 x 256
       const int cbn = cand == 3 ? 256 : (64 << cand);
-      if (cand < 3 && cbn > bn) continue;            // never wider than the padded N
+      if (cand < 3 && cbn > bn_max) continue;        // never wider than the padded N
       if (cand == 3 && !two_ok) continue;
       const long long tiles = (cand == 3 ? mt2 : mt1) * ((a.n + cbn - 1) / cbn);
       const int slots = cand == 3 ? sms / 2 : sms;

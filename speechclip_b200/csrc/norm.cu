@@ -180,6 +180,26 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const float* __restrict
     dx[(long long)row * d + c] = (dy[(long long)row * d + c] - y[(long long)row * d + c] * dot) * inv;
 }
 
+// Hidden-state rows are read in 16-byte units whatever their type: 4 fp32 or 8 fp16 elements per lane per load (with 8-byte
+// fp16 loads the kernels had half the bytes in flight and ran at 3 TB/s instead of the 6.3 TB/s of the fp32 read).
+template <typename TH> struct HVec;
+template <> struct HVec<float> {
+  static constexpr int N = 4;
+  __device__ static __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 f = *reinterpret_cast<const float4*>(p);
+    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+  }
+};
+template <> struct HVec<__half> {
+  static constexpr int N = 8;
+  __device__ static __forceinline__ void load(const __half* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const float2 a = H16<SCB_F16>::unpack(u.x), b = H16<SCB_F16>::unpack(u.y), c = H16<SCB_F16>::unpack(u.z), d = H16<SCB_F16>::unpack(u.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  }
+};
+constexpr int kMaxElems = kMaxVec * 4;  // elements of a row per lane
+
 // out = sum_l softmax(w)_l * h_l   (weighted_sum.py:38-43), h = [L][rows][d] (fp32, or the fp16 hidden states the post-LN
 // tower keeps: half the bytes of the 13-layer read) with layer stride.
 // NORMALIZE: parameter-free LayerNorm over d on every h_l first (weighted_sum.py:41-42).  One warp per row.
@@ -189,6 +209,7 @@ __global__ void __launch_bounds__(256) weighted_sum_fwd_kernel(const TH* __restr
                                                                float* __restrict__ out32, void* __restrict__ out16, int out16_fmt,
                                                                long long rows, int d, int rows_per_batch,
                                                                long long out16_batch_stride, long long out16_row0) {
+  constexpr int V = HVec<TH>::N, NV = kMaxElems / V;
   __shared__ float sw[64];
   if (threadIdx.x < 32) {
     float v = threadIdx.x < L ? w_logits[threadIdx.x] : -INFINITY;
@@ -203,21 +224,27 @@ __global__ void __launch_bounds__(256) weighted_sum_fwd_kernel(const TH* __restr
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const int nvec = d >> 2;
-  float4 acc[kMaxVec];
+  const int nvec = d / V;
+  float acc[NV][V];
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[i][j] = 0.f;
+#pragma unroll 2  // two layers' loads in flight per lane: ~50 KB per SM, what the HBM latency needs
   for (int l = 0; l < L; ++l) {
     const TH* hr = h + (long long)l * layer_stride + row * d;
     const float wl = sw[l];
-    float4 v[kMaxVec];
+    float v[NV][V];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + i * 32;
       if (c < nvec) {
-        v[i] = load4<TH>(hr + c * 4);
-        if (NORMALIZE) s += v[i].x + v[i].y + v[i].z + v[i].w;
+        HVec<TH>::load(hr + c * V, v[i]);
+        if (NORMALIZE) {
+#pragma unroll
+          for (int j = 0; j < V; ++j) s += v[i][j];
+        }
       }
     }
     float mean = 0.f, rstd = 1.f;
@@ -225,33 +252,37 @@ __global__ void __launch_bounds__(256) weighted_sum_fwd_kernel(const TH* __restr
       mean = warp_sum(s) / d;
       float ss = 0.f;
 #pragma unroll
-      for (int i = 0; i < kMaxVec; ++i) {
+      for (int i = 0; i < NV; ++i) {
         const int c = lane + i * 32;
         if (c < nvec) {
-          const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, dd = v[i].w - mean;
-          ss += a * a + b * b + cc * cc + dd * dd;
+#pragma unroll
+          for (int j = 0; j < V; ++j) ss += (v[i][j] - mean) * (v[i][j] - mean);
         }
       }
       rstd = rsqrtf(warp_sum(ss) / d + 1e-5f);
     }
     const float a = wl * rstd, b = -wl * rstd * mean;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + i * 32;
       if (c < nvec) {
-        acc[i].x += a * v[i].x + b; acc[i].y += a * v[i].y + b;
-        acc[i].z += a * v[i].z + b; acc[i].w += a * v[i].w + b;
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[i][j] += a * v[i][j] + b;
       }
     }
   }
   const long long bidx = row / rows_per_batch, r = row % rows_per_batch;
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = lane + i * 32;
     if (c < nvec) {
-      if (out32) *reinterpret_cast<float4*>(out32 + row * d + c * 4) = acc[i];
-      if (out16)
-        store4_16(reinterpret_cast<uint16_t*>(out16) + bidx * out16_batch_stride + (out16_row0 + r) * d + c * 4, out16_fmt, acc[i]);
+#pragma unroll
+      for (int j = 0; j < V; j += 4) {
+        const float4 o = make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
+        if (out32) *reinterpret_cast<float4*>(out32 + row * d + c * V + j) = o;
+        if (out16)
+          store4_16(reinterpret_cast<uint16_t*>(out16) + bidx * out16_batch_stride + (out16_row0 + r) * d + c * V + j, out16_fmt, o);
+      }
     }
   }
 }
@@ -259,41 +290,51 @@ __global__ void __launch_bounds__(256) weighted_sum_fwd_kernel(const TH* __restr
 // dw_l = sum_{r,c} dout[r,c] * h_l[r,c]  (h optionally LayerNorm'ed first); then softmax backward into dlogits.
 // dout rows may live inside a larger per-batch buffer (branch input gradient): row r of batch b is at
 // dout + b*dout_batch_stride + (dout_row0 + r)*d.
-template <bool NORMALIZE, typename TH>
-__global__ void __launch_bounds__(256) weighted_sum_bwd_kernel(const TH* __restrict__ h, long long layer_stride, int L,
+template <bool NORMALIZE, typename TH, int LMAX>
+__global__ void __launch_bounds__(256, 2) weighted_sum_bwd_kernel(const TH* __restrict__ h, long long layer_stride, int L,
                                                                const float* __restrict__ dout, long long rows, int d,
                                                                int rows_per_batch, long long dout_batch_stride, long long dout_row0,
                                                                float* __restrict__ dw_raw) {
+  constexpr int V = HVec<TH>::N, NV = kMaxElems / V;
   __shared__ float sacc[64];
   if (threadIdx.x < 64) sacc[threadIdx.x] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int nvec = d >> 2;
+  const int nvec = d / V;
   const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
-  float part[32];  // L <= 32 handled in registers per warp; larger L unsupported (checked on host)
+  float part[LMAX];  // L <= LMAX (16 or 32) handled in registers per warp; larger L unsupported (checked on host)
 #pragma unroll
-  for (int l = 0; l < 32; ++l) part[l] = 0.f;
+  for (int l = 0; l < LMAX; ++l) part[l] = 0.f;
   for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps_total) {
     const long long bidx = row / rows_per_batch, r = row % rows_per_batch;
     const float* dr = dout + bidx * dout_batch_stride + (dout_row0 + r) * d;
-    float4 g[kMaxVec];
+    float g[NV][V];
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + i * 32;
-      if (c < nvec) g[i] = *reinterpret_cast<const float4*>(dr + c * 4);
+      if (c < nvec) {
+#pragma unroll
+        for (int j = 0; j < V; j += 4) {
+          const float4 f = *reinterpret_cast<const float4*>(dr + c * V + j);
+          g[i][j] = f.x; g[i][j + 1] = f.y; g[i][j + 2] = f.z; g[i][j + 3] = f.w;
+        }
+      }
     }
 #pragma unroll
-    for (int l = 0; l < 32; ++l) {
+    for (int l = 0; l < LMAX; ++l) {
       if (l < L) {
         const TH* hr = h + (long long)l * layer_stride + row * d;
-        float4 v[kMaxVec];
+        float v[NV][V];
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < kMaxVec; ++i) {
+        for (int i = 0; i < NV; ++i) {
           const int c = lane + i * 32;
           if (c < nvec) {
-            v[i] = load4<TH>(hr + c * 4);
-            if (NORMALIZE) s += v[i].x + v[i].y + v[i].z + v[i].w;
+            HVec<TH>::load(hr + c * V, v[i]);
+            if (NORMALIZE) {
+#pragma unroll
+              for (int j = 0; j < V; ++j) s += v[i][j];
+            }
           }
         }
         float mean = 0.f, rstd = 1.f;
@@ -301,28 +342,30 @@ __global__ void __launch_bounds__(256) weighted_sum_bwd_kernel(const TH* __restr
           mean = warp_sum(s) / d;
           float ss = 0.f;
 #pragma unroll
-          for (int i = 0; i < kMaxVec; ++i) {
+          for (int i = 0; i < NV; ++i) {
             const int c = lane + i * 32;
             if (c < nvec) {
-              const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, dd = v[i].w - mean;
-              ss += a * a + b * b + cc * cc + dd * dd;
+#pragma unroll
+              for (int j = 0; j < V; ++j) ss += (v[i][j] - mean) * (v[i][j] - mean);
             }
           }
           rstd = rsqrtf(warp_sum(ss) / d + 1e-5f);
         }
         float dot = 0.f;
 #pragma unroll
-        for (int i = 0; i < kMaxVec; ++i) {
+        for (int i = 0; i < NV; ++i) {
           const int c = lane + i * 32;
-          if (c < nvec)
-            dot += g[i].x * (v[i].x - mean) + g[i].y * (v[i].y - mean) + g[i].z * (v[i].z - mean) + g[i].w * (v[i].w - mean);
+          if (c < nvec) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) dot += g[i][j] * (v[i][j] - mean);
+          }
         }
         part[l] += dot * rstd;
       }
     }
   }
 #pragma unroll
-  for (int l = 0; l < 32; ++l) {
+  for (int l = 0; l < LMAX; ++l) {
     if (l < L) {
       const float s = warp_sum(part[l]);
       if (lane == 0) atomicAdd(&sacc[l], s);
@@ -416,7 +459,7 @@ int weighted_sum_fwd(const void* h, int h_dtype, long long layer_stride, const f
   SCB_CHECK(h && w_logits && (out32 || out16), SCB_EINVAL, "scb_weighted_sum: null operand");
   SCB_CHECK(h_dtype == SCB_F32 || h_dtype == SCB_F16, SCB_EUNSUPPORTED, "scb_weighted_sum: hidden states must be fp32 or fp16");
   SCB_CHECK(L >= 1 && L <= 64, SCB_EUNSUPPORTED, "scb_weighted_sum: L=%d out of range [1,64]", L);
-  SCB_CHECK(d % 4 == 0 && d <= 32 * 4 * kMaxVec, SCB_EUNSUPPORTED, "scb_weighted_sum: unsupported d=%d", d);
+  SCB_CHECK(d % (h_dtype == SCB_F16 ? 8 : 4) == 0 && d <= 32 * 4 * kMaxVec, SCB_EUNSUPPORTED, "scb_weighted_sum: unsupported d=%d", d);
   if (rows == 0) return SCB_OK;
   if (rows_per_batch <= 0) rows_per_batch = (int)rows;
   const unsigned grid = (unsigned)((rows + 7) / 8);
@@ -440,15 +483,21 @@ int weighted_sum_bwd(const void* h, int h_dtype, long long layer_stride, const f
   SCB_CHECK(h && w_logits && dout && scratch_L && grad_logits, SCB_EINVAL, "scb_weighted_sum_bwd: null operand");
   SCB_CHECK(h_dtype == SCB_F32 || h_dtype == SCB_F16, SCB_EUNSUPPORTED, "scb_weighted_sum_bwd: hidden states must be fp32 or fp16");
   SCB_CHECK(L >= 1 && L <= 32, SCB_EUNSUPPORTED, "scb_weighted_sum_bwd: L=%d out of range [1,32]", L);
-  SCB_CHECK(d % 4 == 0 && d <= 32 * 4 * kMaxVec, SCB_EUNSUPPORTED, "scb_weighted_sum_bwd: unsupported d=%d", d);
+  SCB_CHECK(d % (h_dtype == SCB_F16 ? 8 : 4) == 0 && d <= 32 * 4 * kMaxVec, SCB_EUNSUPPORTED, "scb_weighted_sum_bwd: unsupported d=%d", d);
   if (rows_per_batch <= 0) rows_per_batch = (int)rows;
   SCB_CUDA(cudaMemsetAsync(scratch_L, 0, L * sizeof(float), st));
   if (rows > 0) {
     long long blocks = (rows + 7) / 8;
     if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
-#define SCB_WS_BWD(NORM, TH) \
-  weighted_sum_bwd_kernel<NORM, TH><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const TH*>(h), layer_stride, L, dout, rows, d, \
-                                                                      rows_per_batch, dout_batch_stride, dout_row0, scratch_L)
+#define SCB_WS_BWD(NORM, TH)                                                                                                       \
+  do {                                                                                                                             \
+    if (L <= 16)                                                                                                                   \
+      weighted_sum_bwd_kernel<NORM, TH, 16><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const TH*>(h), layer_stride, L, dout, rows, d, \
+                                                                              rows_per_batch, dout_batch_stride, dout_row0, scratch_L); \
+    else                                                                                                                           \
+      weighted_sum_bwd_kernel<NORM, TH, 32><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const TH*>(h), layer_stride, L, dout, rows, d, \
+                                                                              rows_per_batch, dout_batch_stride, dout_row0, scratch_L); \
+  } while (0)
     if (h_dtype == SCB_F16) {
       if (normalize) SCB_WS_BWD(true, __half); else SCB_WS_BWD(false, __half);
     } else {

@@ -169,6 +169,22 @@ def test_sgemm_strided():
     assert (o - torch.outer(v, u)).abs().max() < 1e-6
 
 
+@pytest.mark.parametrize("M", [1, 3, 8])
+def test_sgemm_skinny_rows(M):
+    """M <= 8 takes the dot-product kernels: B contiguous in k (q = cls Wq^T) or in n (dcls += dq Wq), alpha / beta honoured."""
+    from speechclip_b200 import ops
+    K, N = 768, 200
+    a, w = randn(M, K, seed=31), randn(N, K, seed=32, scale=K ** -0.5)
+    c = torch.empty(M, N, device=DEV)
+    ops.sgemm(a, w, c)
+    assert (c - a @ w.t()).abs().max() < 1e-4
+    wt = randn(K, N, seed=33, scale=K ** -0.5)  # b = wt.t(): element (n, k) at k * N + n
+    c0 = randn(M, N, seed=34)
+    c = c0.clone()
+    ops.sgemm(a, wt.t(), c, alpha=2.0, beta=1.0)
+    assert (c - (c0 + 2.0 * a @ wt)).abs().max() < 1e-4
+
+
 # ------------------------------------------------------------------------------------------------ attention
 @pytest.mark.parametrize("hd,heads,T", [(64, 12, 319), (64, 12, 50), (16, 4, 12), (96, 8, 320), (128, 8, 320), (64, 8, 77), (32, 2, 130)])
 @pytest.mark.parametrize("mode", ["full", "keypad", "causal"])

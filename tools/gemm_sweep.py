@@ -25,11 +25,18 @@ def child(ms):
             for i in range(3):
                 ops.gemm(a[i % 4], w, bias=b, act=act, residual=r, out=out)
             torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            # 20 launches captured into one CUDA graph: the replay has no python / ctypes time between kernels (a single launch
+            # from python costs ~20 us of host time, more than these kernels run)
             reps = 20
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for i in range(reps):
+                    ops.gemm(a[i % 4], w, bias=b, act=act, residual=r, out=out)
+            graph.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for i in range(reps):
-                ops.gemm(a[i % 4], w, bias=b, act=act, residual=r, out=out)
+            graph.replay()
             e1.record()
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) / reps * 1e3
