@@ -9,6 +9,7 @@ Lightning's single-process DataParallel gather (``strategy: dp``); here it is on
 the masked InfoNCE on the full matrix and back-propagates its own rows.
 """
 import logging
+import os
 from typing import List, Tuple, Union
 
 import torch
@@ -456,6 +457,17 @@ class KW_ParallelBranch(nn.Module):
         return ParallelBranchFn.apply(audio_feat, kv_len, head, arena, *[p[k] for k in PARAM_ORDER])
 
 
+OVERLAP_TOWERS = os.environ.get("SCB_OVERLAP_TOWERS", "1") != "0"
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = str(device)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 class KWClip_GeneralTransformer(KWClipBase):
     """Main class for SpeechCLIP (kwClip.py:1111-1496)."""
 
@@ -545,8 +557,21 @@ class KWClip_GeneralTransformer(KWClipBase):
     def forward(self, batch) -> tuple:
         wav, wav_len, image, id = batch["wav"], batch["wav_len"], batch["image"], batch["id"]
         self.clip.update_device(self.device)
-        audio_feat, audio_len = self.forward_audio(wav, wav_len)
-        image_feat = l2_normalize(self.forward_image(image))
+        # The two frozen towers are independent until the loss: the image tower runs on a side stream, so its small, latency-bound
+        # kernels (50 tokens per image) fill SMs the speech tower's kernels leave idle at their tails (SCB_OVERLAP_TOWERS=0: serial).
+        if OVERLAP_TOWERS and isinstance(image, torch.Tensor) and image.is_cuda:
+            cur = torch.cuda.current_stream(image.device)
+            side = _side_stream(image.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                image_raw = self.forward_image(image)
+            image_raw.record_stream(cur)
+            audio_feat, audio_len = self.forward_audio(wav, wav_len)
+            cur.wait_stream(side)
+            image_feat = l2_normalize(image_raw)
+        else:
+            audio_feat, audio_len = self.forward_audio(wav, wav_len)
+            image_feat = l2_normalize(self.forward_image(image))
         losses_ = {"id": id, "image_feat": image_feat}
         log_metrics = {}
         cascaded_audio_feat = parallel_audio_feat = vq_results = keywords = None

@@ -73,9 +73,9 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ a,
 // Skinny case M <= 8 (the [CLS] query projection and its gradient: one row against a d x d matrix).  The tiled kernel above
 // walks K in 16-wide steps with two block barriers each on a dozen blocks (~100 us for 1 x 768 x 768); here every output
 // column is a coalesced dot product.  KCONTIG: B rows are contiguous in k (b_cs == 1), a warp per column, lanes stride k.
-// Otherwise B is contiguous in n (b_rs == 1): a block owns 32 columns (lane = column) and its 8 warps split k.
-template <bool KCONTIG>
-__global__ void __launch_bounds__(256) sgemm_skinny_kernel(const float* __restrict__ a, long long a_rs, long long a_cs,
+// Otherwise B is contiguous in n (b_rs == 1): a block owns 32 columns (lane = column) and its 32 warps split k.
+template <bool KCONTIG, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) sgemm_skinny_kernel(const float* __restrict__ a, long long a_rs, long long a_cs,
                                                            const float* __restrict__ b, long long b_rs, long long b_cs,
                                                            float* __restrict__ c, long long ldc, int M, int N, int K, float alpha, float beta) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) sgemm_skinny_kernel(const float* __restri
 #pragma unroll
   for (int m = 0; m < 8; ++m) acc[m] = 0.f;
   if (KCONTIG) {
-    const int n = blockIdx.x * 8 + warp;
+    const int n = blockIdx.x * WARPS + warp;
     if (n >= N) return;
     const float* br = b + (long long)n * b_rs;
 #pragma unroll 4
@@ -104,11 +104,11 @@ __global__ void __launch_bounds__(256) sgemm_skinny_kernel(const float* __restri
       }
     }
   } else {
-    __shared__ float red[8][8][33];
+    __shared__ float red[WARPS][8][33];
     const int n = blockIdx.x * 32 + lane;
     if (n < N) {
 #pragma unroll 4
-      for (int k = warp; k < K; k += 8) {
+      for (int k = warp; k < K; k += WARPS) {
         const float bv = b[(long long)k * b_cs + n];
 #pragma unroll
         for (int m = 0; m < 8; ++m)
@@ -118,10 +118,10 @@ __global__ void __launch_bounds__(256) sgemm_skinny_kernel(const float* __restri
 #pragma unroll
     for (int m = 0; m < 8; ++m) red[warp][m][lane] = acc[m];
     __syncthreads();
-    if (warp < M && n < N) {  // warp m sums the 8 partials of row m
+    if (warp < M && n < N) {  // warp m sums the WARPS partials of row m
       float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) s += red[w][warp][lane];
+      for (int w = 0; w < WARPS; ++w) s += red[w][warp][lane];
       float* p = c + (long long)warp * ldc + n;
       *p = alpha * s + (beta != 0.f ? beta * *p : 0.f);
     }
@@ -241,9 +241,9 @@ int sgemm(const float* a, long long a_rs, long long a_cs, const float* b, long l
   SCB_CHECK(a && b && c, SCB_EINVAL, "scb_sgemm: null operand");
   if (M == 0 || N == 0) return SCB_OK;
   if (M <= 8 && K >= 64 && b_cs == 1)
-    sgemm_skinny_kernel<true><<<(N + 7) / 8, 256, 0, st>>>(a, a_rs, a_cs, b, b_rs, b_cs, c, ldc, M, N, K, alpha, beta);
+    sgemm_skinny_kernel<true, 8><<<(N + 7) / 8, 256, 0, st>>>(a, a_rs, a_cs, b, b_rs, b_cs, c, ldc, M, N, K, alpha, beta);
   else if (M <= 8 && K >= 64 && b_rs == 1)
-    sgemm_skinny_kernel<false><<<(N + 31) / 32, 256, 0, st>>>(a, a_rs, a_cs, b, b_rs, b_cs, c, ldc, M, N, K, alpha, beta);
+    sgemm_skinny_kernel<false, 32><<<(N + 31) / 32, 1024, 0, st>>>(a, a_rs, a_cs, b, b_rs, b_cs, c, ldc, M, N, K, alpha, beta);
   else
     sgemm_kernel<<<dim3((N + TN - 1) / TN, (M + TM - 1) / TM), 256, 0, st>>>(a, a_rs, a_cs, b, b_rs, b_cs, c, ldc, M, N, K, alpha, beta);
   note_launch();
