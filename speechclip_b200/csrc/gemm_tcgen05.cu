@@ -26,9 +26,14 @@ template <int BN> struct EpiCfg {
   static constexpr int PATCH_BYTES = WARPS * 32 * 16 * 4;   // transpose patches of the register-store epilogue (2 KB per warp)
   static constexpr int TMA_BYTES = WARPS * 32 * 128;        // TMA-store epilogue: 32 rows x 128 B (64 16-bit columns) per warp
 };
-// Epilogues whose output is 16-bit with no residual (QKV, fc1, the conv stack, CLIP c_fc) leave through TMA stores: see
-// epilogue_tile_tma.  They give up one pipeline stage for the 64 KB of staging.
-__host__ __device__ constexpr bool tma_out(int BN, int ACT, int RES, int ODT) { return BN == 256 && ACT >= 0 && RES == 3 && ODT == SCB_F16; }
+// Epilogues whose output is 16-bit with no residual (QKV, fc1, the conv stack, CLIP c_fc), and the fp32 + residual epilogues
+// of the CTA-pair kernel (out-proj, fc2), leave through TMA stores: see epilogue_tile_tma / epilogue_tile_tma_res.  They give
+// up one pipeline stage for the 64 KB of staging.
+// (fp32 output + 16-bit residual only on CTA pairs, where it measured 137 -> 127 us on the HuBERT out-proj; with an fp32
+// residual the row-per-lane residual reads cost more L1 wavefronts than the transpose patch they replace: 156 -> 182 us.)
+__host__ __device__ constexpr bool tma_out(bool pair, int BN, int ACT, int RES, int ODT) {
+  return BN == 256 && ACT >= 0 && ((RES == 3 && ODT == SCB_F16) || (pair && ODT == SCB_F32 && RES == SCB_F16));
+}
 
 struct GemmParams {
   int batch, m_tiles_per_batch, n_tiles, groups, num_tiles;
@@ -258,13 +263,96 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
   }
 }
 
+// TMA-store epilogue for fp32 output = alpha * acc + bias + residual (out-proj, fc2).  The register-store path above spends a
+// 128 x 256 tile's epilogue in serial shared-memory round trips (transpose patch: STS -> LDS, ~1 instruction per cycle per SM
+// measured, 10 us per tile against 4 us of MMAs at K = 768).  Here lane r keeps ROW r: it reads its own residual row segment
+// (32 columns: 64 contiguous bytes of fp16 or 128 of fp32, issued before the accumulator wait), adds, writes the 32 fp32
+// columns as eight swizzled 16-byte units of a [32 rows][128 B] staging tile and one lane issues the TMA store; a warp's 64
+// columns are two such rounds through the same 4 KB tile (the second waits for the first store's shared-memory reads).
+template <int RES>
+__device__ __forceinline__ void epilogue_tile_tma_res(const GemmParams& p, const CUtensorMap* tmO, const TileCoord& t, uint32_t tmem_base,
+                                                      int acc, uint32_t acc_phase, uint64_t* tfull_bar, uint32_t tempty_addr,
+                                                      uint8_t* stage_all, int warp, int lane) {
+  constexpr int BN = 256, COLS = EpiCfg<BN>::COLS;
+  static_assert(COLS == 64, "two 32-column rounds per warp");
+  constexpr int RW = RES == SCB_F32 ? 8 : 4;  // 16-byte units of residual per lane per round
+  const int q = warp & 3;
+  const int part = (warp - 4) >> 2;
+  const int m_base = t.m0 + q * 32;
+  const int col_base = t.n0 + part * COLS;
+  const int row = m_base + lane;
+  const uint32_t stg = smem_u32(stage_all + (warp - 4) * (32 * 128)) + (uint32_t)lane * 128u;
+  const uint32_t sw = (uint32_t)(lane & 7);
+  const bool live = col_base < p.n && m_base < p.m_per_batch;
+  const bool row_ok = row < p.m_per_batch;
+  const bool has_bias = p.bias != nullptr;
+  const long long res_row = (long long)t.b * p.res_batch_stride + (long long)row * p.res_ld;
+  uint4 rr[RW];
+  auto load_res = [&](int h) {  // n % 8 == 0: an 8-column group is entirely inside or outside (outside is clipped by the store)
+#pragma unroll
+    for (int i = 0; i < RW; ++i) {
+      const int col = col_base + h * 32 + i * (32 / RW);
+      rr[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (row_ok && col < p.n) {
+        if (RES == SCB_F32) rr[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.residual) + res_row + col));
+        else rr[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.residual) + res_row + col));
+      }
+    }
+  };
+  if (live) load_res(0);
+  mbar_wait(tfull_bar, acc_phase);
+  tc_fence_after();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t v[32];
+    if (live) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + part * COLS + h * 32), v);
+    tmem_ld_wait();
+    if (h == 1) {  // accumulator fully read by this warp: hand the buffer back to the MMA warp
+      tc_fence_before();
+      if (lane == 0) mbar_arrive_cluster(tempty_addr);
+    }
+    if (lane == 0) bulk_wait_read0();  // the previous store (last tile / first round) has finished reading the staging tile
+    __syncwarp();
+    if (live) {
+      const uint64_t al2 = pk2(p.alpha, p.alpha);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {  // 4 columns -> one 16-byte unit of fp32
+        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_bias) b0 = __ldg(reinterpret_cast<const float4*>(p.bias + min(col_base + h * 32 + k * 4, p.n - 4)));
+        float r0, r1, r2, r3;
+        if (RES == SCB_F32) {
+          r0 = __uint_as_float(rr[k].x); r1 = __uint_as_float(rr[k].y); r2 = __uint_as_float(rr[k].z); r3 = __uint_as_float(rr[k].w);
+        } else {
+          const uint4 u4 = rr[k >> 1];
+          const float2 f0 = H16<RES == SCB_BF16 ? SCB_BF16 : SCB_F16>::unpack((k & 1) ? u4.z : u4.x);
+          const float2 f1 = H16<RES == SCB_BF16 ? SCB_BF16 : SCB_F16>::unpack((k & 1) ? u4.w : u4.y);
+          r0 = f0.x; r1 = f0.y; r2 = f1.x; r3 = f1.y;
+        }
+        const uint64_t x0 = add2(fma2(al2, pk2(__uint_as_float(v[4 * k + 0]), __uint_as_float(v[4 * k + 1])), pk2(b0.x, b0.y)), pk2(r0, r1));
+        const uint64_t x1 = add2(fma2(al2, pk2(__uint_as_float(v[4 * k + 2]), __uint_as_float(v[4 * k + 3])), pk2(b0.z, b0.w)), pk2(r2, r3));
+        float o0, o1, o2, o3;
+        upk2(x0, o0, o1);
+        upk2(x1, o2, o3);
+        st_shared_v4(stg + (((uint32_t)k ^ sw) << 4), __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2), __float_as_uint(o3));
+      }
+      if (h == 0) load_res(1);  // the second round's residual is in flight during the first round's store
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(tmO, stg - (uint32_t)lane * 128u, col_base + h * 32, m_base, t.b);
+        bulk_commit();
+      }
+    }
+  }
+}
+
 template <int BN, int STAGES, int ACT, int RES, int ODT>
 __global__ void __launch_bounds__(EpiCfg<BN>::THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int B_BYTES = BN * BK * 2;
-  constexpr bool TMAO = tma_out(BN, ACT, RES, ODT);
+  constexpr bool TMAO = tma_out(false, BN, ACT, RES, ODT);
   constexpr int EPI_BYTES = TMAO ? EpiCfg<BN>::TMA_BYTES : EpiCfg<BN>::PATCH_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset arithmetic keeps the shared address space
@@ -427,7 +515,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile<BN>(p, tile);
-      if constexpr (TMAO) epilogue_tile_tma<ACT>(p, &tmO, t, tmem_base, acc, acc_phase, &tfull[acc], smem_u32(&tempty[acc]), epi, warp, lane);
+      if constexpr (TMAO && ODT == SCB_F32) epilogue_tile_tma_res<RES>(p, &tmO, t, tmem_base, acc, acc_phase, &tfull[acc], smem_u32(&tempty[acc]), epi, warp, lane);
+      else if constexpr (TMAO) epilogue_tile_tma<ACT>(p, &tmO, t, tmem_base, acc, acc_phase, &tfull[acc], smem_u32(&tempty[acc]), epi, warp, lane);
       else epilogue_tile<BN, ACT, RES, ODT>(p, t, tmem_base, acc, acc_phase, &tfull[acc], smem_u32(&tempty[acc]), stage, warp, lane);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
@@ -475,7 +564,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                      const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int B_BYTES = (BN2 / 2) * BK * 2;
-  constexpr bool TMAO = tma_out(BN2, ACT, RES, ODT);
+  constexpr bool TMAO = tma_out(true, BN2, ACT, RES, ODT);
   constexpr int STAGES = stages2(TMAO);
   constexpr int EPI_BYTES = TMAO ? EpiCfg<BN2>::TMA_BYTES : EpiCfg<BN2>::PATCH_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -577,7 +666,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < p.num_tiles; tile += num_pairs) {
       const TileCoord t = decode_tile2(p, tile, (int)rank);
-      if constexpr (TMAO) epilogue_tile_tma<ACT>(p, &tmO, t, tmem_base, acc, acc_phase, &tfull[acc], mapa_u32(smem_u32(&tempty[acc]), 0), epi, warp, lane);
+      if constexpr (TMAO && ODT == SCB_F32) epilogue_tile_tma_res<RES>(p, &tmO, t, tmem_base, acc, acc_phase, &tfull[acc], mapa_u32(smem_u32(&tempty[acc]), 0), epi, warp, lane);
+      else if constexpr (TMAO) epilogue_tile_tma<ACT>(p, &tmO, t, tmem_base, acc, acc_phase, &tfull[acc], mapa_u32(smem_u32(&tempty[acc]), 0), epi, warp, lane);
       else epilogue_tile<BN2, ACT, RES, ODT>(p, t, tmem_base, acc, acc_phase, &tfull[acc], mapa_u32(smem_u32(&tempty[acc]), 0), stage, warp, lane);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
@@ -595,7 +685,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
 template <int ACT, int RES, int ODT>
 int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p, cudaStream_t stream) {
-  constexpr bool TMAO = tma_out(BN2, ACT, RES, ODT);
+  constexpr bool TMAO = tma_out(true, BN2, ACT, RES, ODT);
   constexpr int smem_bytes = stages2(TMAO) * (BM * BK * 2 + (BN2 / 2) * BK * 2) + 1024 + 256 +
                              (TMAO ? EpiCfg<BN2>::TMA_BYTES : EpiCfg<BN2>::PATCH_BYTES);
   static_assert(smem_bytes <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
@@ -614,7 +704,7 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& t
 
 template <int BN, int STAGES, int ACT = -1, int RES = -1, int ODT = -1>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p, cudaStream_t stream) {
-  constexpr bool TMAO = tma_out(BN, ACT, RES, ODT);
+  constexpr bool TMAO = tma_out(false, BN, ACT, RES, ODT);
   constexpr int smem_bytes = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + 256 + (TMAO ? EpiCfg<BN>::TMA_BYTES : EpiCfg<BN>::PATCH_BYTES);
   static_assert(smem_bytes <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
   static bool configured = false;
@@ -679,7 +769,8 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
       const double bw = fmin(64.0, 8500.0 / active);                                   // bytes per clock per CTA
       const double bytes = (cand == 3 ? (BM + 128) : (BM + cbn)) * 128.0;             // per CTA per k-block
       const double mma = cbn * 2.0;                                                    // 128 x BN x 64 MACs at 4096 MAC / clk
-      const double t = 2000.0 + (double)waves * (kb * fmax(mma, bytes / bw) + 600.0) + cbn * 8.0;  // fill + main loops + last epilogue
+      // (64-wide tiles measured ~1.6x slower per k-block than their byte count predicts)
+      const double t = 2000.0 + (double)waves * (kb * fmax(mma, (cbn == 64 ? 1.6 : 1.0) * bytes / bw) + 600.0) + cbn * 8.0;  // fill + main loops + last epilogue
       if (t < best) {
         best = t;
         bn = cbn;
@@ -759,14 +850,15 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
   }
   // modes 1, 3, 4 store through TMA: [batch][rows][cols] view of the output, 32-row x 64-column boxes in the 128B swizzle
   static const int tma_env = [] { const char* e = getenv("SCB_GEMM_TMA_STORE"); return e ? atoi(e) : 1; }();
-  if ((mode == 1 || mode == 3 || mode == 4) && (a.groups != 1 || tma_env == 0)) mode = 0;
+  if (mode != 0 && (a.groups != 1 || tma_env == 0)) mode = 0;   // (the generic register-store epilogue handles everything)
   CUtensorMap tmO = tmA;
-  if (mode == 1 || mode == 3 || mode == 4) {
+  if (mode == 1 || mode == 3 || mode == 4 || (mode == 5 && two)) {  // 32-row boxes of 128 bytes: 64 16-bit or 32 fp32 columns
+    const int ob = a.out_dtype == SCB_F32 ? 4 : 2;
     const uint64_t dims[3] = {(uint64_t)a.n, (uint64_t)a.m_per_batch, (uint64_t)a.batch};
     const uint64_t bstride = a.out_batch_stride ? (uint64_t)a.out_batch_stride : (uint64_t)a.m_per_batch * (uint64_t)a.ldc;
-    const uint64_t strides[2] = {(uint64_t)a.ldc * 2, bstride * 2};
-    const uint32_t box[3] = {64, 32, 1};
-    int e = make_tmap(&tmO, a.out, 2, 3, dims, strides, box, 1);
+    const uint64_t strides[2] = {(uint64_t)a.ldc * ob, bstride * ob};
+    const uint32_t box[3] = {(uint32_t)(128 / ob), 32, 1};
+    int e = make_tmap(&tmO, a.out, ob, 3, dims, strides, box, 1);
     if (e) return e;
   }
   if (two) {

@@ -118,3 +118,29 @@ def test_gelu_h16_fit_error():
     err = (out.float() - ref).abs()
     ulp = ref.abs().clamp_min(2.0 ** -14) * 2.0 ** -11  # half an fp16 ulp, roughly
     assert (err <= ulp + 3e-5).all(), (err - ulp).max().item()
+
+
+@pytest.mark.parametrize("res_dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("M,N,K,bias", [(700, 776, 320, True), (20000, 768, 768, True), (4097, 3072, 256, False), (12800, 768, 3072, True)])
+def test_gemm_tma_store_residual_epilogue(res_dtype, M, N, K, bias):
+    """fp32 output = alpha * acc + bias + residual (out-proj / fc2), residual fp32 (pre-LN towers) or fp16 (post-LN hidden
+    states): row-per-lane residual reads + TMA stores of 32 x 32 fp32 boxes, on single CTAs and on CTA pairs; also in place."""
+    from speechclip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).half()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).half()
+    b = torch.randn(N, device="cuda", generator=g) if bias else None
+    res = torch.randn(M, N, device="cuda", generator=g).to(res_dtype)
+    guard = torch.full((M + 64, N), 7.0, device="cuda", dtype=torch.float32)
+    out = guard[:M]
+    ops.gemm(a, w, bias=b, residual=res, out=out, alpha=0.5)
+    torch.cuda.synchronize()
+    ref = _ref(a, w, b, 0, res, 0.5)
+    err = (out - ref).abs().max().item()
+    assert err < 2e-3, err
+    assert (guard[M:] == 7.0).all()
+    if res_dtype == torch.float32:  # in place: out aliases the residual
+        buf = res.clone()
+        ops.gemm(a, w, bias=b, residual=buf, out=buf, alpha=0.5)
+        torch.cuda.synchronize()
+        assert (buf - ref).abs().max().item() < 2e-3
