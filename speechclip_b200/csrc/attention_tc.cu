@@ -31,7 +31,7 @@ constexpr int K_BYTES = MAX_NK * 128;           // 40 KB
 constexpr int V_BYTES = MAX_NK * 128;           // 40 KB (5 key blocks of 64 rows x 128 B)
 constexpr int Q_BYTES = MAX_QT * BQ * 128;      // 48 KB
 constexpr int P_BYTES = (MAX_NK / 64) * BQ * 128;  // 80 KB (5 k-blocks of [128 x 64])
-constexpr int SMEM_BYTES = K_BYTES + V_BYTES + Q_BYTES + P_BYTES + 2 * 4 * BQ * 4 + 256 + 1024;
+constexpr int SMEM_BYTES = K_BYTES + V_BYTES + Q_BYTES + P_BYTES + 2 * 4 * BQ * 4 + 256 + 1024;  // 256: mbarriers + TMEM slot
 
 struct AttnTcParams {
   uint16_t* o;
@@ -61,13 +61,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   float* red_max = reinterpret_cast<float*>(sP + P_BYTES);  // [4 column parts][128 rows]
   float* red_sum = red_max + 4 * BQ;
   uint64_t* bars = reinterpret_cast<uint64_t*>(red_sum + 4 * BQ);
-  uint64_t* kv_full = bars + 0;
-  uint64_t* item_empty = bars + 1;
+  uint64_t* kq_full = bars + 0;    // K and every Q tile of the item have landed
+  uint64_t* item_empty = bars + 1; // every PV MMA of the item has retired: V may be overwritten
   uint64_t* s_full = bars + 2;
   uint64_t* p_full = bars + 3;
   uint64_t* o_full = bars + 4;
   uint64_t* o_empty = bars + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* v_full = bars + 6;     // V of the item has landed
+  uint64_t* kq_empty = bars + 7;   // every S MMA of the item has retired: K and Q may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -76,8 +78,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tma_prefetch_desc(&tmV);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(kv_full, 1);
+    mbar_init(kq_full, 1);
     mbar_init(item_empty, 1);
+    mbar_init(v_full, 1);
+    mbar_init(kq_empty, 1);
     mbar_init(s_full, 1);
     mbar_init(p_full, kSoftmaxWarps);
     mbar_init(o_full, 1);
@@ -95,19 +99,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ producer
+    // K and Q of the NEXT item are loaded as soon as the last S = Q K^T of the current item has retired (kq_empty), i.e. while
+    // its last query tile is still in the softmax / P V / drain phases; V follows once the last P V has retired (item_empty).
+    // Without this split every item started with a ~2 us load bubble (14 % of the kernel at 319 frames).
     uint32_t ph = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / p.heads, h = item % p.heads;
-      mbar_wait(item_empty, ph ^ 1u);
-      mbar_expect_tx(kv_full, (uint32_t)(2 * NK * 128 + p.n_qt * BQ * 128));
+      mbar_wait(kq_empty, ph ^ 1u);
+      mbar_expect_tx(kq_full, (uint32_t)(NK * 128 + p.n_qt * BQ * 128));
       if (NK <= 256) {
-        tma_load_3d(sK, &tmK, kv_full, h * HD, 0, b);
+        tma_load_3d(sK, &tmK, kq_full, h * HD, 0, b);
       } else {
-        tma_load_3d(sK, &tmK, kv_full, h * HD, 0, b);
-        tma_load_3d(sK + (NK / 2) * 128, &tmK, kv_full, h * HD, NK / 2, b);
+        tma_load_3d(sK, &tmK, kq_full, h * HD, 0, b);
+        tma_load_3d(sK + (NK / 2) * 128, &tmK, kq_full, h * HD, NK / 2, b);
       }
-      for (int kb = 0; kb < nkb; ++kb) tma_load_3d(sV + kb * 64 * 128, &tmV, kv_full, h * HD, kb * 64, b);
-      for (int qt = 0; qt < p.n_qt; ++qt) tma_load_3d(sQ + qt * BQ * 128, &tmQ, kv_full, h * HD, qt * BQ, b);
+      for (int qt = 0; qt < p.n_qt; ++qt) tma_load_3d(sQ + qt * BQ * 128, &tmQ, kq_full, h * HD, qt * BQ, b);
+      mbar_wait(item_empty, ph ^ 1u);
+      mbar_expect_tx(v_full, (uint32_t)(NK * 128));
+      for (int kb = 0; kb < nkb; ++kb) tma_load_3d(sV + kb * 64 * 128, &tmV, v_full, h * HD, kb * 64, b);
       ph ^= 1u;
     }
   } else if (warp == 1 && lane == 0) {
@@ -128,16 +137,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       tc_commit(s_full);
     };
+    // S(0) of an item is issued as soon as its K / Q have landed AND the S columns are free, i.e. right behind the P V MMAs of
+    // the previous item's last tile (same slot S(qt+1) takes inside an item).
+    bool first = true;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      mbar_wait(kv_full, ph_item);
-      tc_fence_after();
-      issue_s(0);
+      if (first) {
+        mbar_wait(kq_full, ph_item);
+        tc_fence_after();
+        issue_s(0);
+        if (p.n_qt == 1) tc_commit(kq_empty);
+        first = false;
+      }
+      const bool has_next = item + (int)gridDim.x < n_items;
       for (int qt = 0; qt < p.n_qt; ++qt) {
         mbar_wait(p_full, ph_p);       // P(qt) is in shared memory and S(qt) has been read
         ph_p ^= 1u;
         tc_fence_after();
         // S of the next tile goes first: the softmax warps start on it while the PV MMAs below are still running
-        if (qt + 1 < p.n_qt) issue_s(qt + 1);
+        if (qt + 1 < p.n_qt) {
+          issue_s(qt + 1);
+          if (qt + 2 == p.n_qt) tc_commit(kq_empty);  // the item's last S: K / Q are free once it retires
+        }
+        if (qt == 0) {
+          mbar_wait(v_full, ph_item);
+          tc_fence_after();
+        }
         mbar_wait(o_empty, ph_oe ^ 1u);  // O of the previous tile has been read out of TMEM
         ph_oe ^= 1u;
         tc_fence_after();
@@ -150,8 +174,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                        (uint32_t)((kb | k) != 0));
         }
         tc_commit(o_full);
+        if (qt + 1 == p.n_qt) {
+          tc_commit(item_empty);
+          if (has_next) {  // next item's first S behind this item's last P V
+            mbar_wait(kq_full, ph_item ^ 1u);
+            tc_fence_after();
+            issue_s(0);
+            if (p.n_qt == 1) tc_commit(kq_empty);
+          }
+        }
       }
-      tc_commit(item_empty);
       ph_item ^= 1u;
     }
   } else if (warp >= 2) {
