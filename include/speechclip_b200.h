@@ -129,7 +129,8 @@ int scb_cls_attention_bwd(const float* q, const void* kv, int32_t kv_fmt, int64_
  *   GroupNorm(512 groups = per channel over time, eps) -> GELU(erf); out is channel-last 16-bit [batch][n_frames][512].
  *   scratch >= scb_conv0_scratch_bytes(batch).
  * scb_conv0_layernorm_gelu: HuBERT-large variant (extractor_mode=layer_norm): conv -> LayerNorm over the 512 channels
- *   of each frame -> GELU.
+ *   of each frame -> GELU (statistics from the Gram matrix of the weights, normalisation folded into the tensor-core operands);
+ *   scratch >= scb_conv0_scratch_bytes(batch) as well (only the first 512 bytes are used).
  * ---------------------------------------------------------------------------------------------- */
 int scb_frame_lengths(const int64_t* wav_len, int32_t batch, int64_t tw_out, int32_t max_audio_len, int32_t n_frames, int32_t rate,
                       const float* u, int32_t* crop_off, int32_t* crop_len, int32_t* valid_frames, int32_t* feat_len,
@@ -145,7 +146,7 @@ int scb_conv0_groupnorm_gelu(const float* wav, int64_t wav_ld, int32_t batch, in
                              void* scratch, int64_t scratch_bytes, void* stream);
 int scb_conv0_layernorm_gelu(const float* wav, int64_t wav_ld, int32_t batch, int32_t n_samples, const float* w, const float* conv_bias,
                              const float* gamma, const float* beta, float eps, void* out, int32_t out_fmt, int64_t out_batch_stride,
-                             void* stream);
+                             void* scratch, int64_t scratch_bytes, void* stream);
 /* Zero padded frames of x in place (speech_encoder_plus.py:32-33) and write the 16-bit, group-padded (channels per group ->
  * 64), time-padded copy that the positional-conv GEMM walks tap by tap (speech_encoder_plus.py:35). */
 int scb_posconv_pack(float* x, const int32_t* valid_frames, void* xpad, int32_t fmt, int32_t batch, int32_t T, int32_t D, int32_t groups,

@@ -135,8 +135,9 @@ int scb_conv0_groupnorm_gelu(const float* wav, int64_t wav_ld, int32_t batch, in
 }
 int scb_conv0_layernorm_gelu(const float* wav, int64_t wav_ld, int32_t batch, int32_t n_samples, const float* w, const float* conv_bias,
                              const float* gamma, const float* beta, float eps, void* out, int32_t out_fmt, int64_t out_batch_stride,
-                             void* stream) {
-  return scb::conv0_layernorm_gelu(wav, wav_ld, batch, n_samples, w, conv_bias, gamma, beta, eps, out, out_fmt, out_batch_stride, ST);
+                             void* scratch, int64_t scratch_bytes, void* stream) {
+  return scb::conv0_layernorm_gelu(wav, wav_ld, batch, n_samples, w, conv_bias, gamma, beta, eps, out, out_fmt, out_batch_stride, scratch,
+                                   scratch_bytes, ST);
 }
 int scb_posconv_pack(float* x, const int32_t* valid_frames, void* xpad, int32_t fmt, int32_t batch, int32_t T, int32_t D, int32_t groups,
                      int32_t pad_left, int32_t rows_pad, void* stream) {

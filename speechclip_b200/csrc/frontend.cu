@@ -180,58 +180,144 @@ __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restric
   }
 }
 
-// HuBERT-large conv0 block: conv (C_in = 1) -> LayerNorm over the 512 channels of each frame (affine, fp32) -> GELU.
-// One warp per frame; lane owns channels {lane*4 + 128*i .. +3}, i < 4 (coalesced 8-byte 16-bit stores).
-__global__ void __launch_bounds__(256) conv0_ln_kernel(const float* __restrict__ wav, long long wav_ld, const float* __restrict__ w,
-                                                       const float* __restrict__ conv_bias, const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, float eps, void* __restrict__ out, int out_fmt,
-                                                       int n_frames, long long out_batch_stride) {
-  constexpr int C = 512;
-  __shared__ float ws[C * kTaps];
-  for (int i = threadIdx.x; i < C * kTaps; i += blockDim.x) ws[i] = w[i];
-  __syncthreads();
+// ---- HuBERT-large conv0 block (conv -> LayerNorm over the 512 channels of each frame -> GELU) on the tensor cores.
+// The LayerNorm statistics of a frame need no pass over its 512 conv outputs: with o[f,c] = sum_k w[c,k] x[f,k] + b[c],
+//   mean_f = wbar . x_f + mean(b),   E_c[o^2] = x_f^T G x_f + 2 (W^T b / C) . x_f + mean(b^2),   G = W^T W / C  (10 x 10),
+// so 77 channel sums of the weights (conv0_ln_gram_kernel, once per call) turn them into ~75 FMAs per frame.  The normalisation
+// then folds into the MMA operands like the GroupNorm variant above — here the per-FRAME factors ride on the A rows and the
+// per-CHANNEL factors on the B columns:
+//   A row f    = [ rstd_f x[f,0..9] | m_hi, m_lo | 1, 1 | rstd_f, rstd_f ]          m = -mean_f rstd_f (fp16 hi/lo pair)
+//   B column c = [ g_c w[c,0..9]    | g_c,  g_c  | beta_c hi, lo | (g_c b_c) hi, lo ]
+// and the accumulator is g_c (o - mean_f) rstd_f + beta_c: the epilogue is GELU + pack + store, 16 bytes per lane per store.
+constexpr int kGramVals = kPairs + 2 * kTaps + 2;  // G (55 upper-triangular), wbar (10), W^T b / C (10), mean(b), mean(b^2)
+__global__ void __launch_bounds__(32) conv0_ln_gram_kernel(const float* __restrict__ w, const float* __restrict__ conv_bias, int channels,
+                                                           float* __restrict__ gram) {
+  const int i = blockIdx.x, lane = threadIdx.x;
+  int k = 0, k2 = 0, kind = 0;  // kind 0: G[k][k2], 1: wbar[k], 2: (W^T b)[k], 3: mean b, 4: mean b^2
+  if (i < kPairs) {
+    int idx = i;
+    while (idx >= kTaps - k) { idx -= kTaps - k; ++k; }
+    k2 = k + idx;
+  } else if (i < kPairs + kTaps) { kind = 1; k = i - kPairs; }
+  else if (i < kPairs + 2 * kTaps) { kind = 2; k = i - kPairs - kTaps; }
+  else kind = 3 + (i - kPairs - 2 * kTaps);
+  float s = 0.f;
+  for (int c = lane; c < channels; c += 32) {
+    const float b = conv_bias ? conv_bias[c] : 0.f;
+    const float wk = w[c * kTaps + k];
+    s += kind == 0 ? wk * w[c * kTaps + k2] : kind == 1 ? wk : kind == 2 ? wk * b : kind == 3 ? b : b * b;
+  }
+  s = warp_sum(s);
+  if (lane == 0) gram[i] = s / channels;
+}
+
+__global__ void __launch_bounds__(256) conv0_ln_apply_kernel(const float* __restrict__ wav, long long wav_ld, const float* __restrict__ w,
+                                                             const float* __restrict__ conv_bias, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, const float* __restrict__ gram, float eps,
+                                                             void* __restrict__ out, int out_fmt, int n_frames,
+                                                             long long out_batch_stride, int channels) {
+  __shared__ float xs[kFramesPerBlock * kStride + kTaps + 6];
+  __shared__ float sg[kGramVals];
+  __shared__ float2 fstat[kFramesPerBlock];  // (rstd_f, -mean_f rstd_f)
   const int b = blockIdx.y;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int warps = blockDim.x >> 5;
-  for (int t = blockIdx.x * warps + warp; t < n_frames; t += gridDim.x * warps) {
-    const float* x = wav + (long long)b * wav_ld + (long long)t * kStride;
+  const int t0 = blockIdx.x * kFramesPerBlock;
+  const int nt = min(kFramesPerBlock, n_frames - t0);
+  const int nsamp = (nt - 1) * kStride + kTaps;
+  const float* x = wav + (long long)b * wav_ld + (long long)t0 * kStride;
+  for (int i = threadIdx.x; i < kFramesPerBlock * kStride + kTaps + 6; i += blockDim.x) xs[i] = i < nsamp ? __ldg(x + i) : 0.f;
+  if (threadIdx.x < kGramVals) sg[threadIdx.x] = gram[threadIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int cgrp = warp & 3, fhalf = warp >> 2;
+  const bool bf = out_fmt == SCB_BF16;
+  // ---- B fragments: 16 n-blocks x {k = t4*2, t4*2+1 | k = t4*2+8, t4*2+9} of channel ch(nb, g)
+  uint32_t bfrag[16][2];
+#pragma unroll
+  for (int nb = 0; nb < 16; ++nb) {
+    const int ch = cgrp * 128 + (g >> 1) * 32 + nb * 2 + (g & 1);
+    const float gm = gamma ? gamma[ch] : 1.f;
+    const float* wc = w + ch * kTaps;
+    bfrag[nb][0] = H16<SCB_F16>::pack(wc[t4 * 2] * gm, wc[t4 * 2 + 1] * gm);
+    if (t4 == 0) {
+      bfrag[nb][1] = H16<SCB_F16>::pack(wc[8] * gm, wc[9] * gm);
+    } else if (t4 == 1) {
+      bfrag[nb][1] = H16<SCB_F16>::pack(gm, gm);
+    } else {
+      const float v = t4 == 2 ? (beta ? beta[ch] : 0.f) : (conv_bias ? gm * conv_bias[ch] : 0.f);
+      const float hi = __half2float(__float2half_rn(v));
+      bfrag[nb][1] = H16<SCB_F16>::pack(hi, v - hi);
+    }
+  }
+  __syncthreads();
+  // ---- per-frame LayerNorm statistics from the 10 samples of the frame
+  if (threadIdx.x < kFramesPerBlock) {
+    const float* xf = xs + threadIdx.x * kStride;
     float xv[kTaps];
 #pragma unroll
-    for (int k = 0; k < kTaps; ++k) xv[k] = __ldg(x + k);
-    float v[16];
-    float s = 0.f;
+    for (int k = 0; k < kTaps; ++k) xv[k] = xf[k];
+    float mean = sg[kPairs + 2 * kTaps], e2 = sg[kPairs + 2 * kTaps + 1];
+    int idx = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int k = 0; k < kTaps; ++k) {
+      mean = fmaf(sg[kPairs + k], xv[k], mean);
+      e2 = fmaf(2.f * sg[kPairs + kTaps + k], xv[k], e2);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = lane * 4 + 128 * i + j;
-        float a = conv_bias ? conv_bias[c] : 0.f;
-#pragma unroll
-        for (int k = 0; k < kTaps; ++k) a = fmaf(ws[c * kTaps + k], xv[k], a);
-        v[i * 4 + j] = a;
-        s += a;
-      }
-    const float mean = warp_sum(s) / C;
-    float ss = 0.f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float d = v[i] - mean;
-      ss += d * d;
+      for (int k2 = k; k2 < kTaps; ++k2) e2 = fmaf((k == k2 ? 1.f : 2.f) * sg[idx++], xv[k] * xv[k2], e2);
     }
-    const float rstd = rsqrtf(warp_sum(ss) / C + eps);
-    uint16_t* o = reinterpret_cast<uint16_t*>(out) + (long long)b * out_batch_stride + (long long)t * C;
+    const float rstd = rsqrtf(fmaxf(e2 - mean * mean, 0.f) + eps);
+    fstat[threadIdx.x] = make_float2(rstd, -mean * rstd);
+  }
+  __syncthreads();
+  uint16_t* obase = reinterpret_cast<uint16_t*>(out) + (long long)b * out_batch_stride + (long long)t0 * channels + cgrp * 128 + t4 * 32;
+  for (int ft = fhalf; ft * 16 < nt; ft += 2) {
+    const int f0 = ft * 16;
+    // ---- A fragment: rows g / g+8 of the tile, columns (t4*2, +1) and (t4*2+8, +9)
+    const float2 sa = fstat[f0 + g], sb = fstat[f0 + g + 8];
+    const float* xa = xs + (f0 + g) * kStride + t4 * 2;
+    const float* xb = xa + 8 * kStride;
+    uint32_t a[4];
+    a[0] = H16<SCB_F16>::pack(xa[0] * sa.x, xa[1] * sa.x);
+    a[1] = H16<SCB_F16>::pack(xb[0] * sb.x, xb[1] * sb.x);
+    if (t4 == 0) {
+      a[2] = H16<SCB_F16>::pack(xa[8] * sa.x, xa[9] * sa.x);
+      a[3] = H16<SCB_F16>::pack(xb[8] * sb.x, xb[9] * sb.x);
+    } else if (t4 == 1) {
+      const float ha = __half2float(__float2half_rn(sa.y)), hb = __half2float(__float2half_rn(sb.y));
+      a[2] = H16<SCB_F16>::pack(ha, sa.y - ha);
+      a[3] = H16<SCB_F16>::pack(hb, sb.y - hb);
+    } else if (t4 == 2) {
+      a[2] = a[3] = 0x3C003C00u;  // (1.0, 1.0)
+    } else {
+      a[2] = H16<SCB_F16>::pack(sa.x, sa.x);
+      a[3] = H16<SCB_F16>::pack(sb.x, sb.x);
+    }
+    const bool ok_a = f0 + g < nt, ok_b = f0 + g + 8 < nt;
+    uint16_t* oa = obase + (long long)(f0 + g) * channels;
+    uint16_t* ob = oa + 8LL * channels;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float y[4];
+    for (int q4 = 0; q4 < 4; ++q4) {  // 4 n-blocks -> 8 channels (16 bytes) per row
+      float c[4][4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int c = lane * 4 + 128 * i + j;
-        y[j] = gelu_erf((v[i * 4 + j] - mean) * rstd * (gamma ? gamma[c] : 1.f) + (beta ? beta[c] : 0.f));
+        c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[j][0]), "+f"(c[j][1]), "+f"(c[j][2]), "+f"(c[j][3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(bfrag[q4 * 4 + j][0]), "r"(bfrag[q4 * 4 + j][1]));
       }
-      uint2 u;
-      u.x = pack16(out_fmt, y[0], y[1]);
-      u.y = pack16(out_fmt, y[2], y[3]);
-      *reinterpret_cast<uint2*>(o + lane * 4 + 128 * i) = u;
+      uint4 ua, ub;
+      if (bf) {
+        ua.x = gelu_pack<SCB_BF16>(c[0][0], c[0][1]); ua.y = gelu_pack<SCB_BF16>(c[1][0], c[1][1]);
+        ua.z = gelu_pack<SCB_BF16>(c[2][0], c[2][1]); ua.w = gelu_pack<SCB_BF16>(c[3][0], c[3][1]);
+        ub.x = gelu_pack<SCB_BF16>(c[0][2], c[0][3]); ub.y = gelu_pack<SCB_BF16>(c[1][2], c[1][3]);
+        ub.z = gelu_pack<SCB_BF16>(c[2][2], c[2][3]); ub.w = gelu_pack<SCB_BF16>(c[3][2], c[3][3]);
+      } else {
+        ua.x = gelu_pack<SCB_F16>(c[0][0], c[0][1]); ua.y = gelu_pack<SCB_F16>(c[1][0], c[1][1]);
+        ua.z = gelu_pack<SCB_F16>(c[2][0], c[2][1]); ua.w = gelu_pack<SCB_F16>(c[3][0], c[3][1]);
+        ub.x = gelu_pack<SCB_F16>(c[0][2], c[0][3]); ub.y = gelu_pack<SCB_F16>(c[1][2], c[1][3]);
+        ub.z = gelu_pack<SCB_F16>(c[2][2], c[2][3]); ub.w = gelu_pack<SCB_F16>(c[3][2], c[3][3]);
+      }
+      if (ok_a) *reinterpret_cast<uint4*>(oa + q4 * 8) = ua;
+      if (ok_b) *reinterpret_cast<uint4*>(ob + q4 * 8) = ub;
     }
   }
 }
@@ -373,16 +459,21 @@ long long conv0_scratch_bytes(int batch) {
 
 int conv0_layernorm_gelu(const float* wav, long long wav_ld, int batch, int n_samples, const float* w, const float* conv_bias,
                          const float* gamma, const float* beta, float eps, void* out, int out_fmt, long long out_batch_stride,
-                         cudaStream_t st) {
-  SCB_CHECK(wav && w && out, SCB_EINVAL, "scb_conv0_layernorm_gelu: null operand");
+                         void* scratch, long long scratch_bytes, cudaStream_t st) {
+  SCB_CHECK(wav && w && out && scratch, SCB_EINVAL, "scb_conv0_layernorm_gelu: null operand");
   SCB_CHECK(out_fmt == SCB_F16 || out_fmt == SCB_BF16, SCB_EINVAL, "scb_conv0_layernorm_gelu: 16-bit output required");
   SCB_CHECK(n_samples >= kTaps, SCB_EINVAL, "scb_conv0_layernorm_gelu: utterance shorter than the conv kernel");
   SCB_CHECK(batch <= 65535, SCB_EUNSUPPORTED, "scb_conv0_layernorm_gelu: batch exceeds grid limits");
+  SCB_CHECK(scratch_bytes >= (long long)(kGramVals * sizeof(float)), SCB_EINVAL, "scb_conv0_layernorm_gelu: scratch too small (%lld < %d)",
+            scratch_bytes, (int)(kGramVals * sizeof(float)));
   if (batch == 0) return SCB_OK;
   const int n_frames = (n_samples - kTaps) / kStride + 1;
-  int gx = (n_frames + 63) / 64;  // 8 frames per pass, ~8 passes per block amortise the weight staging
-  if (gx < 1) gx = 1;
-  conv0_ln_kernel<<<dim3(gx, batch), 256, 0, st>>>(wav, wav_ld, w, conv_bias, gamma, beta, eps, out, out_fmt, n_frames, out_batch_stride);
+  float* gram = reinterpret_cast<float*>(scratch);
+  conv0_ln_gram_kernel<<<kGramVals, 32, 0, st>>>(w, conv_bias, 512, gram);
+  note_launch();
+  SCB_LAUNCH_OK("conv0_ln_gram");
+  conv0_ln_apply_kernel<<<dim3((n_frames + kFramesPerBlock - 1) / kFramesPerBlock, batch), 256, 0, st>>>(
+      wav, wav_ld, w, conv_bias, gamma, beta, gram, eps, out, out_fmt, n_frames, out_batch_stride, 512);
   note_launch();
   SCB_LAUNCH_OK("conv0_layernorm_gelu");
   return SCB_OK;

@@ -81,7 +81,12 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const TIn* __restric
         o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
       }
       if (act == SCB_ACT_GELU_ERF) {
-        o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w);
+        if (y32) {  // fp32 consumers get the erff form; 16-bit-only outputs (HuBERT-large conv blocks) the fit of gelu_h16
+          o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w);
+        } else {
+          upk2(gelu_h16_x2(pk2(o.x, o.y)), o.x, o.y);
+          upk2(gelu_h16_x2(pk2(o.z, o.w)), o.z, o.w);
+        }
       } else if (act == SCB_ACT_QUICK_GELU) {
         o.x = quick_gelu(o.x); o.y = quick_gelu(o.y); o.z = quick_gelu(o.z); o.w = quick_gelu(o.w);
       }

@@ -33,7 +33,7 @@ int conv0_groupnorm_gelu(const float* wav, long long wav_ld, int batch, int n_sa
                          void* scratch, long long scratch_bytes, cudaStream_t st);
 int conv0_layernorm_gelu(const float* wav, long long wav_ld, int batch, int n_samples, const float* w, const float* conv_bias,
                          const float* gamma, const float* beta, float eps, void* out, int out_fmt, long long out_batch_stride,
-                         cudaStream_t st);
+                         void* scratch, long long scratch_bytes, cudaStream_t st);
 int posconv_pack(float* x, const int* valid_frames, void* xpad, int fmt, int batch, int T, int D, int groups, int pad_left, int rows_pad,
                  cudaStream_t st);
 int patchify(const float* img, void* out, int fmt, int batch, int C, int H, int W, int P, int ldk, cudaStream_t st);

@@ -239,10 +239,10 @@ class HubertPlan:
         B, Tw = wav.shape
         T = (Tw - 10) // 5 + 1
         cur = ws.get("conv_a", B * T * 512 + SLACK, H)
+        scratch = ws.get("conv0_scratch", ops.conv0_scratch_bytes(B), torch.uint8)
         if self.ext_ln:
-            ops.conv0_layernorm_gelu(wav, Tw, self.c0_w, self.c0_b, self.c0_gamma, self.c0_beta, 1e-5, cur, T * 512)
+            ops.conv0_layernorm_gelu(wav, Tw, self.c0_w, self.c0_b, self.c0_gamma, self.c0_beta, 1e-5, cur, T * 512, scratch)
         else:
-            scratch = ws.get("conv0_scratch", ops.conv0_scratch_bytes(B), torch.uint8)
             ops.conv0_groupnorm_gelu(wav, Tw, self.c0_w, self.c0_b, self.c0_gamma, self.c0_beta, 1e-5, cur, T * 512, scratch)
         names = ("conv_b", "conv_a")
         for i, (wk, b, ln, k) in enumerate(self.convs):

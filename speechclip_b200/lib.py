@@ -105,7 +105,7 @@ def _declare(lib):
         "scb_lengths_to_i32": [vp, i32, i32, i32, vp, vp],
         "scb_wav_prepare": [vp, i64, i32, vp, vp, i64, i32, vp, vp, i64, vp],
         "scb_conv0_groupnorm_gelu": [vp, i64, i32, i32, vp, vp, vp, vp, f32, vp, i32, i64, vp, i64, vp],
-        "scb_conv0_layernorm_gelu": [vp, i64, i32, i32, vp, vp, vp, vp, f32, vp, i32, i64, vp],
+        "scb_conv0_layernorm_gelu": [vp, i64, i32, i32, vp, vp, vp, vp, f32, vp, i32, i64, vp, i64, vp],
         "scb_posconv_pack": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
         "scb_patchify": [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
         "scb_broadcast_row": [vp, vp, vp, i32, i64, i32, i32, vp],

@@ -179,9 +179,9 @@ def conv0_groupnorm_gelu(wav, n_samples, w, conv_bias, gamma, beta, eps, out, ou
           _p(out), _DT[out.dtype], out_batch_stride, _p(scratch), scratch.numel() * scratch.element_size())
 
 
-def conv0_layernorm_gelu(wav, n_samples, w, conv_bias, gamma, beta, eps, out, out_batch_stride):
+def conv0_layernorm_gelu(wav, n_samples, w, conv_bias, gamma, beta, eps, out, out_batch_stride, scratch):
     _call("scb_conv0_layernorm_gelu", _p(wav), wav.stride(0), wav.shape[0], n_samples, _p(w), _p(conv_bias), _p(gamma), _p(beta), eps,
-          _p(out), _DT[out.dtype], out_batch_stride)
+          _p(out), _DT[out.dtype], out_batch_stride, _p(scratch), scratch.numel() * scratch.element_size())
 
 
 def posconv_pack(x, valid_frames, xpad, batch, T, D, groups, pad_left, rows_pad):

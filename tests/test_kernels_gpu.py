@@ -335,17 +335,22 @@ def test_conv0_groupnorm_gelu(n_samples):
     assert err < 6e-3, err
 
 
-def test_conv0_layernorm_gelu():
+@pytest.mark.parametrize("with_bias", [False, True])
+@pytest.mark.parametrize("n", [4000, 10 + 5 * 130])
+def test_conv0_layernorm_gelu(with_bias, n):
     from speechclip_b200 import ops
-    B, n = 2, 4000
+    B = 2
     wav = randn(B, n, seed=40)
+    bias = 0.3 * randn(512, seed=44) if with_bias else None
     w = randn(512, 10, seed=41, scale=math.sqrt(2 / 10))
     gamma, beta = 1 + 0.1 * randn(512, seed=42), 0.1 * randn(512, seed=43)
     T = (n - 10) // 5 + 1
     out = torch.empty(B, T, 512, device=DEV, dtype=torch.float16)
-    ops.conv0_layernorm_gelu(wav, n, w, None, gamma, beta, 1e-5, out, T * 512)
-    ref = F.gelu(F.layer_norm(F.conv1d(wav[:, None], w[:, None], stride=5).transpose(1, 2), (512,), gamma, beta, 1e-5))
-    assert (out.float() - ref).abs().max() < 6e-3
+    scratch = torch.empty(ops.conv0_scratch_bytes(B), device=DEV, dtype=torch.uint8)
+    ops.conv0_layernorm_gelu(wav, n, w, bias, gamma, beta, 1e-5, out, T * 512, scratch)
+    ref = F.gelu(F.layer_norm(F.conv1d(wav[:, None], w[:, None], bias, stride=5).transpose(1, 2), (512,), gamma, beta, 1e-5))
+    err = (out.float() - ref).abs().max().item()
+    assert err < 6e-3, err
 
 
 @pytest.mark.parametrize("k,T_in", [(3, 799), (3, 400), (2, 159), (2, 80)])
