@@ -201,6 +201,8 @@ def run_own(args):
     opts, scheds = model.configure_optimizers()
     opt, sched = opts[0], scheds[0]["scheduler"]
 
+    from speechclip_b200.runtime import DevicePrefetcher, bind_to_gpu_numa_node
+    numa_node = bind_to_gpu_numa_node(local)  # pinned staging buffers local to the GPU's PCIe root (None: topology not visible)
     host = synth_batch(per_gpu, 7122 + rank, True)
     host["id"] += rank * per_gpu
     resident = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
@@ -268,9 +270,19 @@ def run_own(args):
 
     # ---- end to end through the public API with host buffers: every step's inputs are copied from pinned host memory
     # (double-buffered on a copy stream by speechclip_b200.runtime.DevicePrefetcher) and its loss is read back to the host
-    from speechclip_b200.runtime import DevicePrefetcher
-
     host_times = []
+    prefetcher = DevicePrefetcher(None, dev)  # one object for the warm-up and the timed pass: its two device slots are allocated once
+    # host->device bandwidth of this process's pinned buffers (diagnostic: the copy must hide behind one step)
+    probe = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    c0.record()
+    for k, v in host.items():
+        probe[k].copy_(v, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = h2d_bytes / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    del probe
 
     loss_slots = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
 
@@ -278,9 +290,16 @@ def run_own(args):
         # Every step's loss is copied to pinned host memory and read by the host — one step late (after step i+1 has been
         # enqueued), the way a training loop logs without draining the GPU between steps.
         last, pending = None, None
-        for i, batch in enumerate(DevicePrefetcher((host for _ in range(n)), dev)):
+        for i, batch in enumerate(prefetcher.iterate(host for _ in range(n))):
             t_h = time.perf_counter()
+            if dbg is not None:
+                e_a = torch.cuda.Event(enable_timing=True)
+                e_a.record()
             loss = step(batch)
+            if dbg is not None:
+                e_b = torch.cuda.Event(enable_timing=True)
+                e_b.record()
+                dbg.append((e_a, e_b, time.perf_counter()))
             host_times.append((time.perf_counter() - t_h) * 1e3)
             slot = loss_slots[i % 2]
             slot.copy_(loss.detach(), non_blocking=True)
@@ -294,9 +313,17 @@ def run_own(args):
         last = float(pending[1])
         return last
 
+    dbg = [] if os.environ.get("SCB_E2E_DEBUG") else None   # per-step device spans / gaps of the end-to-end loop, to stderr
     e2e_run(2)
+    if dbg is not None:
+        dbg.clear()
     ms_e2e = timed(lambda: e2e_run(args.steps), 1) / args.steps
     clocks = sampler.stop() if sampler else None
+    if dbg:
+        torch.cuda.synchronize()
+        for j, (ea, eb, th) in enumerate(dbg):
+            gap = dbg[j - 1][1].elapsed_time(ea) if j else 0.0
+            sys.stderr.write(f"e2e step {j}: device span {ea.elapsed_time(eb):.2f} ms, gap before {gap:.2f} ms, host t {1e3 * (th - dbg[0][2]):.1f} ms\n")
 
     # ---- per-entry-point breakdown and roofline of the dominant kernel
     agg = {}
@@ -347,7 +374,7 @@ def run_own(args):
                    "l2": "inputs (259 MB) and activations (GBs) larger than the 126 MB L2; no flush needed",
                    "cuda_graphs": use_graphs, "tower_streams": 2 if kwclip_mod.OVERLAP_TOWERS else 1},
         "e2e": {"value": global_batch / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": 4,
+                "d2h_bytes_per_step": 4, "h2d_gb_per_s_measured": h2d_gbs, "numa_node_bound": numa_node,
                 "loss_read": "every step's loss is copied to pinned host memory and read by the host one step late (after the next step is enqueued)"},
         "gpu_launches": int(launches), "host_enqueue_ms_per_step": sorted(host_times)[len(host_times) // 2],
         "host_enqueue_ms_per_step_timed": host_ms,

@@ -6,21 +6,61 @@ two device-side slots while the previous step computes.
 """
 from __future__ import annotations
 
-from typing import Dict, Iterable, Iterator
+import os
+from typing import Dict, Iterable, Iterator, Optional
 
 import torch
+
+
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """Restrict the calling thread to the CPUs of the NUMA node the GPU hangs off (sysfs; no libnuma needed) and return the node.
+
+    Pinned staging buffers are then allocated (first touch) in memory local to the GPU's PCIe root: on a two-socket 8-GPU box a
+    batch pinned on the far socket crosses the inter-socket link on every host->device copy, which was measured as an
+    intermittent 1.2-1.5x slowdown of the end-to-end step (the 259 MB copy no longer hides behind a 38 ms step).  Returns None
+    and changes nothing when the topology is not visible (containers without sysfs, single-node hosts)."""
+    try:
+        prop = torch.cuda.get_device_properties(device_index)
+        bdf = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError):
+        return None
 
 
 class DevicePrefetcher:
     """Iterates device-resident copies of pinned host batches (dicts of tensors), double-buffered on a side stream."""
 
-    def __init__(self, batches: Iterable[Dict[str, torch.Tensor]], device: torch.device):
+    _streams: Dict[str, "torch.cuda.Stream"] = {}  # one copy stream per device for the life of the process: the caching
+    # allocator keeps freed blocks per stream, so a fresh stream per epoch would cudaMalloc (and synchronise) its slots again
+
+    def __init__(self, batches: Optional[Iterable[Dict[str, torch.Tensor]]], device: torch.device):
         self.batches = batches
         self.device = device
-        self.copy_stream = torch.cuda.Stream(device=device)
+        key = str(device)
+        if key not in DevicePrefetcher._streams:
+            DevicePrefetcher._streams[key] = torch.cuda.Stream(device=device)
+        self.copy_stream = DevicePrefetcher._streams[key]
         self.slots = [None, None]
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]
         self.released = [None, None]
+
+    def iterate(self, batches: Iterable[Dict[str, torch.Tensor]]) -> Iterator[Dict[str, torch.Tensor]]:
+        """Another pass (epoch) over new host batches through the same two device slots."""
+        self.batches = batches
+        return iter(self)
 
     def _stage(self, slot: int, host: Dict[str, torch.Tensor]):
         with torch.cuda.stream(self.copy_stream):

@@ -1,20 +1,33 @@
 #!/bin/bash
-# Runs on the GPU box (under gpurun): ncu evidence for the round's bench command.  Outputs land in gpurun_out/.
+# Runs on the GPU box (under gpurun): the evidence set of the round for the bench command.  Outputs land in gpurun_out/ and are
+# copied (summarised where large) into profiles/ by hand.  TAG names the set (r1c = end of round 1).
 set -x
 cd "$(dirname "$0")/.."
+TAG=${TAG:-r1c}
 mkdir -p gpurun_out
-# 1. every launch of the bench command with its device time (cold-cache, serialised: compare SHARES)
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r1_launches.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --graphs off > gpurun_out/r1_launches_bench.json 2> gpurun_out/r1_launches.err
-# 2. DRAM traffic of every GEMM launch of the same command (one metric pass per kernel)
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:gemm --csv \
-    --log-file gpurun_out/r1_gemm_dram.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --graphs off > /dev/null 2> gpurun_out/r1_gemm_dram.err
-# 3. full capture of the top GEMM shapes (fc1 with the GELU epilogue, fc2 with the fp32 residual epilogue)
-ncu --set full --clock-control none --import-source on -k regex:gemm -s 4 -c 1 -o gpurun_out/r1_full_fc1 python tools/gemm_bench.py fc1 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:gemm -s 4 -c 1 -o gpurun_out/r1_full_fc2 python tools/gemm_bench.py fc2 > /dev/null 2>&1
-# 4. clocks during a plain bench run
-nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 200 > gpurun_out/r1_clocks.csv &
+# 0. parity + smoke
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/${TAG}_pytest_gpu.txt
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -1 > gpurun_out/${TAG}_smoke.txt
+# 1. plain bench runs (never under a profiler), clocks sampled beside the headline run
+nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 200 > gpurun_out/${TAG}_clocks.csv &
 SMI=$!
-python bench.py --steps 20 --warmup 5 > gpurun_out/r1_bench.json 2> gpurun_out/r1_bench.err
+python bench.py --steps 20 --warmup 5 --dump-profile gpurun_out/${TAG}_gemm_shapes_base.csv > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err
 kill $SMI
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r1_bench_reference.json 2> /dev/null
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_n1_reference_arm.json 2> /dev/null
+python bench.py --config large --steps 10 --warmup 3 --no-cpu-baseline --dump-profile gpurun_out/${TAG}_gemm_shapes_large.csv > gpurun_out/${TAG}_bench_n1_large.json 2> /dev/null
+python bench.py --config cascaded --steps 20 --warmup 3 --no-cpu-baseline --dump-profile gpurun_out/${TAG}_gemm_shapes_cascaded.csv > gpurun_out/${TAG}_bench_n1_cascaded.json 2> /dev/null
+# 2. every launch of the bench command with its device time (cold-cache, serialised: compare SHARES)
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --graphs off > gpurun_out/${TAG}_launches_bench.json 2> gpurun_out/${TAG}_launches.err
+# 3. DRAM traffic of every GEMM launch of the same command
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:gemm --csv \
+    --log-file gpurun_out/${TAG}_gemm_dram.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --graphs off > /dev/null 2> gpurun_out/${TAG}_gemm_dram.err
+# 4. full captures: the heaviest GEMM shapes and the attention kernel
+for s in fc1 fc2_16 out16 qkv; do
+  ncu --set full --clock-control none --import-source on -k regex:gemm -s 4 -c 1 -o gpurun_out/${TAG}_full_$s python tools/gemm_bench.py $s > /dev/null 2>&1
+done
+ncu --set full --clock-control none --import-source on -k regex:attention_tc -s 2 -c 1 -o gpurun_out/${TAG}_full_attention python tools/attn_bench.py > /dev/null 2>&1
+python tools/gemm_bench.py > gpurun_out/${TAG}_gemm_bench.txt 2>&1
+python tools/attn_bench.py >> gpurun_out/${TAG}_gemm_bench.txt 2>&1
+cat gpurun_out/${TAG}_pytest_gpu.txt gpurun_out/${TAG}_smoke.txt gpurun_out/${TAG}_gemm_bench.txt
+for f in n1 n1_large n1_cascaded; do cut -c1-260 gpurun_out/${TAG}_bench_$f.json; done
