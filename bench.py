@@ -313,17 +313,21 @@ def run_own(args):
         last = float(pending[1])
         return last
 
-    dbg = [] if os.environ.get("SCB_E2E_DEBUG") else None   # per-step device spans / gaps of the end-to-end loop, to stderr
+    dbg = []   # per-step device spans / gaps of the end-to-end loop (2 events per step): reported beside the end-to-end value
     e2e_run(2)
     if dbg is not None:
         dbg.clear()
     ms_e2e = timed(lambda: e2e_run(args.steps), 1) / args.steps
     clocks = sampler.stop() if sampler else None
-    if dbg:
-        torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    spans = sorted(ea.elapsed_time(eb) for ea, eb, _ in dbg)
+    gaps = [dbg[j - 1][1].elapsed_time(dbg[j][0]) for j in range(1, len(dbg))]
+    e2e_diag = {"step_span_ms_median": spans[len(spans) // 2], "step_span_ms_max": spans[-1], "gap_ms_max": max(gaps) if gaps else 0.0,
+                "outside_steps_ms": ms_e2e * args.steps - sum(spans) - sum(gaps)}
+    if os.environ.get("SCB_E2E_DEBUG"):
         for j, (ea, eb, th) in enumerate(dbg):
-            gap = dbg[j - 1][1].elapsed_time(ea) if j else 0.0
-            sys.stderr.write(f"e2e step {j}: device span {ea.elapsed_time(eb):.2f} ms, gap before {gap:.2f} ms, host t {1e3 * (th - dbg[0][2]):.1f} ms\n")
+            sys.stderr.write(f"e2e step {j}: device span {ea.elapsed_time(eb):.2f} ms, gap before {gaps[j - 1] if j else 0.0:.2f} ms, "
+                             f"host t {1e3 * (th - dbg[0][2]):.1f} ms\n")
 
     # ---- per-entry-point breakdown and roofline of the dominant kernel
     agg = {}
@@ -374,7 +378,7 @@ def run_own(args):
                    "l2": "inputs (259 MB) and activations (GBs) larger than the 126 MB L2; no flush needed",
                    "cuda_graphs": use_graphs, "tower_streams": 2 if kwclip_mod.OVERLAP_TOWERS else 1},
         "e2e": {"value": global_batch / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": 4, "h2d_gb_per_s_measured": h2d_gbs, "numa_node_bound": numa_node,
+                "d2h_bytes_per_step": 4, "h2d_gb_per_s_measured": h2d_gbs, "numa_node_bound": numa_node, "diagnostics": e2e_diag,
                 "loss_read": "every step's loss is copied to pinned host memory and read by the host one step late (after the next step is enqueued)"},
         "gpu_launches": int(launches), "host_enqueue_ms_per_step": sorted(host_times)[len(host_times) // 2],
         "host_enqueue_ms_per_step_timed": host_ms,
