@@ -750,7 +750,9 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
   static const int force_two = [] { const char* e = getenv("SCB_GEMM_FORCE_2CTA"); return e ? atoi(e) : -1; }();
   const long long mt1 = (long long)a.batch * a.groups * ((a.m_per_batch + BM - 1) / BM);
   const long long mt2 = (long long)a.batch * a.groups * ((a.m_per_batch + 255) / 256);
-  const bool two_ok = two_env != 0 && a.n > 128 && a.m_per_batch >= 256 && a.tap_row_shift == 0;
+  // (tap-walk conv GEMMs: pairs measured +5 % on the long layers (10239 / 5119 rows per utterance), -5 % at 639 rows, where the
+  // 256-row super tiles pad 17 %)
+  const bool two_ok = two_env != 0 && a.n > 128 && a.m_per_batch >= 256 && (a.tap_row_shift == 0 || a.m_per_batch >= 2048);
   const int bn_max = a.n > 128 ? 256 : (a.n > 64 ? 128 : 64);
   int bn = bn_max;
   bool two = false;
@@ -777,9 +779,8 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
         two = cand == 3;
       }
     }
-    // (the tap-walk conv GEMMs measured 7 % faster on single CTAs, the plain linears 2-3 % faster on pairs)
     if (force_bn) bn = force_bn;
-    if (force_two >= 0) two = force_two != 0 && a.m_per_batch >= 256 && a.tap_row_shift == 0;
+    if (force_two >= 0) two = force_two != 0 && a.m_per_batch >= 256 && (a.tap_row_shift == 0 || force_two == 2);
     if (two) bn = 256;
   }
   GemmParams p{};
