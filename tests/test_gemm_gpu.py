@@ -73,12 +73,12 @@ def test_gemm_tma_store_epilogue(act, M, N, K, bias):
     assert (guard[M:] == 7.0).all()  # rows past M are clipped, not written
 
 
-@pytest.mark.parametrize("tap", [0, 1])
+@pytest.mark.parametrize("tap", [0, 1, 2])
 def test_gemm_tma_store_batched_ragged_rows(tap):
     """Batched output whose rows per batch are not a multiple of the 32-row store box (the conv stack: [B][T_out][512]): a box
     that straddles the end of one batch must not spill into the next one."""
     from speechclip_b200 import ops
-    B, T, C, N = 5, 333, 256, 512
+    B, T, C, N = (3, 4301, 256, 512) if tap == 2 else (5, 333, 256, 512)  # tap 2: >= 2048 rows per batch -> the tap walk runs on CTA pairs
     g = torch.Generator(device="cuda").manual_seed(11 + tap)
     x = torch.randn(B, T, C, device="cuda", generator=g).half()
     if tap:  # stride-2, k = 2 conv over channel-last rows: pairs of frames are one 2C-wide row
