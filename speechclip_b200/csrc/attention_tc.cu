@@ -93,6 +93,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();               // programmatic dependent launch: global memory is only touched below
+  griddep_launch_dependents();
   const int n_items = p.batch * p.heads;
   const int NK = p.NK;
   const int nkb = NK / 64;  // key blocks of the PV contraction
@@ -347,8 +349,8 @@ int attention_fwd_tc(const void* q, const void* k, const void* v, void* o, int f
   }
   const int items = batch * heads;
   const int grid = items < num_sms() ? items : num_sms();
-  if (p.bf16) attention_tc_kernel<true><<<grid, kThreads, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
-  else attention_tc_kernel<false><<<grid, kThreads, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
+  if (p.bf16) SCB_CUDA(launch_pdl(attention_tc_kernel<true>, dim3((unsigned)grid), kThreads, SMEM_BYTES, st, tmQ, tmK, tmV, p));
+  else SCB_CUDA(launch_pdl(attention_tc_kernel<false>, dim3((unsigned)grid), kThreads, SMEM_BYTES, st, tmQ, tmK, tmV, p));
   note_launch();
   SCB_LAUNCH_OK("attention_tc");
   return SCB_OK;

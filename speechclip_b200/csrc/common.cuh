@@ -6,6 +6,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <stdio.h>
 
 #include "../../include/speechclip_b200.h"
@@ -35,6 +36,24 @@ void note_launch();  // bumps the per-process kernel-launch counter (scb_launch_
 // dims/strides innermost first; strides in BYTES for dims 1..rank-1; 2- or 4-byte elements.
 int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
               const uint32_t* box, int swizzle128);
+
+// Kernel launch with programmatic stream serialization (SCB_PDL=0 disables): the kernel may start its prologue while the
+// previous kernel of the stream is still draining and blocks in griddep_wait() until that kernel's memory is visible.
+template <typename K, typename... Args>
+inline cudaError_t launch_pdl(K kernel, dim3 grid, int block, int smem, cudaStream_t stream, Args... args) {
+  static const int pdl = [] { const char* e = getenv("SCB_PDL"); return e ? atoi(e) : 1; }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 
 // ---------------------------------------------------------------- 16-bit formats
 // SCB_F16 = IEEE half (forward activations / weights), SCB_BF16 = bfloat16 (gradient operands).
@@ -229,6 +248,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+
+// Programmatic dependent launch: block until the kernels this launch depends on have completed and flushed (a no-op when the
+// kernel was launched without the programmatic-serialization attribute).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// ... and let the next kernel of the stream start launching (its own griddep_wait still waits for this grid to complete).
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

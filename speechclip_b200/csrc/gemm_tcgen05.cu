@@ -396,6 +396,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may run while the
+  // previous kernel of the stream drains; global memory is only touched below this point.
+  griddep_wait();
+  griddep_launch_dependents();  // a following row kernel (LayerNorm) may become resident beside this CTA and wait for its data
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -606,6 +610,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / cross-CTA TMA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();  // programmatic dependent launch: global memory is only touched below
+  griddep_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -696,7 +702,7 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& t
   }
   int pairs = num_sms() / 2;
   if (p.num_tiles < pairs) pairs = p.num_tiles;
-  gemm2_tcgen05_kernel<ACT, RES, ODT><<<2 * pairs, EpiCfg<BN2>::THREADS, smem_bytes, stream>>>(tmA, tmB, tmO, p);
+  SCB_CUDA(launch_pdl(gemm2_tcgen05_kernel<ACT, RES, ODT>, dim3((unsigned)(2 * pairs)), EpiCfg<BN2>::THREADS, smem_bytes, stream, tmA, tmB, tmO, p));
   note_launch();
   SCB_LAUNCH_OK("gemm2_tcgen05");
   return SCB_OK;
@@ -713,7 +719,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
     configured = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  gemm_tcgen05_kernel<BN, STAGES, ACT, RES, ODT><<<grid, EpiCfg<BN>::THREADS, smem_bytes, stream>>>(tmA, tmB, tmO, p);
+  SCB_CUDA(launch_pdl(gemm_tcgen05_kernel<BN, STAGES, ACT, RES, ODT>, dim3((unsigned)grid), EpiCfg<BN>::THREADS, smem_bytes, stream, tmA, tmB, tmO, p));
   note_launch();
   SCB_LAUNCH_OK("gemm_tcgen05");
   return SCB_OK;

@@ -37,6 +37,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const TIn* __restric
                                                             const float* __restrict__ beta, float* __restrict__ y32,
                                                             void* __restrict__ y16, int y16_fmt, float* __restrict__ stats,
                                                             long long rows, int d, long long x_ld, long long y_ld, float eps, int act) {
+  griddep_wait();               // programmatic dependent launch (see launch_pdl)
+  griddep_launch_dependents();  // the next kernel (a GEMM) may set up its barriers / TMEM while the last wave of rows runs
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -415,11 +417,11 @@ int layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* b
   const int wpb = 8;
   const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
   if (x_dtype == SCB_F32)
-    layernorm_fwd_kernel<float><<<grid, wpb * 32, 0, st>>>((const float*)x, gamma, beta, y32, y16, y16_fmt, stats, rows, d, x_ld, y_ld, eps, act);
+    SCB_CUDA(launch_pdl(layernorm_fwd_kernel<float>, dim3(grid), wpb * 32, 0, st, (const float*)x, gamma, beta, y32, y16, y16_fmt, stats, rows, d, x_ld, y_ld, eps, act));
   else if (x_dtype == SCB_F16)
-    layernorm_fwd_kernel<__half><<<grid, wpb * 32, 0, st>>>((const __half*)x, gamma, beta, y32, y16, y16_fmt, stats, rows, d, x_ld, y_ld, eps, act);
+    SCB_CUDA(launch_pdl(layernorm_fwd_kernel<__half>, dim3(grid), wpb * 32, 0, st, (const __half*)x, gamma, beta, y32, y16, y16_fmt, stats, rows, d, x_ld, y_ld, eps, act));
   else
-    layernorm_fwd_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, st>>>((const __nv_bfloat16*)x, gamma, beta, y32, y16, y16_fmt, stats, rows, d, x_ld, y_ld, eps, act);
+    SCB_CUDA(launch_pdl(layernorm_fwd_kernel<__nv_bfloat16>, dim3(grid), wpb * 32, 0, st, (const __nv_bfloat16*)x, gamma, beta, y32, y16, y16_fmt, stats, rows, d, x_ld, y_ld, eps, act));
   note_launch();
   SCB_LAUNCH_OK("layernorm_fwd");
   return SCB_OK;
