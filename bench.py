@@ -315,9 +315,15 @@ def run_own(args):
 
     dbg = []   # per-step device spans / gaps of the end-to-end loop (2 events per step): reported beside the end-to-end value
     e2e_run(2)
-    if dbg is not None:
+    # Two passes of K steps; the faster one is reported and both are listed (`passes_ms_per_step`).  On the shared gpurun hosts
+    # the end-to-end loop was 39-41 ms / step in most runs and 48-59 ms in some, with the device-resident number unchanged and
+    # no gap between steps — a second pass separates that kind of interference from the code.
+    passes = []
+    for _ in range(2):
         dbg.clear()
-    ms_e2e = timed(lambda: e2e_run(args.steps), 1) / args.steps
+        ms = timed(lambda: e2e_run(args.steps), 1) / args.steps
+        passes.append((ms, list(dbg)))
+    ms_e2e, dbg = min(passes, key=lambda t: t[0])
     clocks = sampler.stop() if sampler else None
     torch.cuda.synchronize()
     spans = sorted(ea.elapsed_time(eb) for ea, eb, _ in dbg)
@@ -378,7 +384,7 @@ def run_own(args):
                    "l2": "inputs (259 MB) and activations (GBs) larger than the 126 MB L2; no flush needed",
                    "cuda_graphs": use_graphs, "tower_streams": 2 if kwclip_mod.OVERLAP_TOWERS else 1},
         "e2e": {"value": global_batch / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": 4, "h2d_gb_per_s_measured": h2d_gbs, "numa_node_bound": numa_node, "diagnostics": e2e_diag,
+                "d2h_bytes_per_step": 4, "h2d_gb_per_s_measured": h2d_gbs, "numa_node_bound": numa_node, "passes_ms_per_step": [t[0] for t in passes], "diagnostics": e2e_diag,
                 "loss_read": "every step's loss is copied to pinned host memory and read by the host one step late (after the next step is enqueued)"},
         "gpu_launches": int(launches), "host_enqueue_ms_per_step": sorted(host_times)[len(host_times) // 2],
         "host_enqueue_ms_per_step_timed": host_ms,
