@@ -749,7 +749,7 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
   // Tile shape.  256-wide tiles (CTA pairs: 256 x 256) carry the large problems.  When M is small (CLIP ViT and the head at 32-64
   // pairs per GPU: strong scaling) the choice is between few large tiles on part of the SMs and many small tiles on all of
   // them; small tiles pull (128 + BN) x 128 B per k-block for 128 x BN x 64 MACs, so they are bound by the L2 -> SM path, and
-  // a tile count just above the SM count (156 tiles of 128 x 64 for M = 1600, N = 768) costs a second wave.  pick_tile()
+  // a tile count just above the SM count (156 tiles of 128 x 64 for M = 1600, N = 768) costs a second wave.  The loop below
   // estimates each candidate with a two-term model (MMA clocks vs operand bytes over min(per-SM, chip / active SMs) bandwidth).
   static const int two_env = [] { const char* e = getenv("SCB_GEMM_2CTA"); return e ? atoi(e) : 1; }();
   static const int force_bn = [] { const char* e = getenv("SCB_GEMM_FORCE_BN"); return e ? atoi(e) : 0; }();      // tuning sweeps
