@@ -191,3 +191,39 @@ def test_gather_features_world_size_2_gloo():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert torch.equal(got[0], got[1])  # identical global feature matrix on both ranks
+
+
+def test_gelu_h16_fit_constants_in_the_cuda_header():
+    """The sigmoid-polynomial erf-GELU of the 16-bit GEMM / conv0 epilogues (csrc/common.cuh: gelu_h16): the constants compiled
+    into the kernels keep |error| <= 3e-5 on the GELU value over the whole real line, including beyond the clamp."""
+    import math
+    import os
+    import re
+    import numpy as np
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "speechclip_b200", "csrc", "common.cuh")).read()
+    body = src[src.index("__device__ __forceinline__ float gelu_h16(float x)"):]
+    body = body[:body.index("}")]
+    c2, c1, c0 = (float(v) for v in re.findall(r"(-?\d+\.\d+)f \* -1\.4426950408889634f", body))
+    clamp = float(re.search(r"fminf\(x \* x, (\d+\.\d+)f\)", body).group(1))
+    x = np.linspace(-40.0, 40.0, 400001)
+    s = np.minimum(x * x, clamp)
+    approx = x / (1.0 + np.exp(-x * (c0 + c1 * s + c2 * s * s)))
+    ref = np.array([0.5 * v * (1.0 + math.erf(v / math.sqrt(2.0))) for v in x])
+    assert np.abs(approx - ref).max() < 3e-5
+    assert c0 + c1 * clamp + c2 * clamp * clamp > 3.0  # beyond the clamp the argument keeps growing with |x|: Phi saturates at 0 / 1
+
+
+def test_conv0_layernorm_statistics_from_the_gram_matrix():
+    """The identity behind the HuBERT-large conv0 kernel (csrc/frontend.cu: conv0_ln_apply_kernel): the LayerNorm mean and
+    variance of a frame's 512 conv outputs follow from its 10 samples and 77 channel sums of the weights."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    C, K = 512, 10
+    w, b = rng.normal(0, 0.45, (C, K)), rng.normal(0, 0.3, C)
+    x = rng.normal(0, 1.0, (200, K))
+    o = x @ w.T + b
+    gram, wbar, wb = w.T @ w / C, w.mean(0), w.T @ b / C
+    mean = x @ wbar + b.mean()
+    e2 = np.einsum("fk,kj,fj->f", x, gram, x) + 2.0 * x @ wb + (b * b).mean()
+    assert np.abs(mean - o.mean(1)).max() < 1e-12
+    assert np.abs((e2 - mean * mean) - o.var(1)).max() < 1e-10
