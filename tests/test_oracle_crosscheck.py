@@ -69,3 +69,30 @@ def test_clip_oracle_vs_hf_live_vitb32():
     with torch.no_grad():
         a, b = om.encode_image(img), hv(pixel_values=img).image_embeds
     assert a.shape == (2, 512) and torch.allclose(a, b, atol=5e-4), (a - b).abs().max()
+
+
+@pytest.mark.parametrize("name,atol", [("hubert", 2e-5), ("hubert_large_ll60k", 1e-4)])
+def test_hubert_oracle_vs_torchaudio_through_its_fairseq_key_map(name, atol):
+    """torchaudio's wav2vec2 / HuBERT is a re-implementation made to load fairseq checkpoints: `import_fairseq._convert_state_dict`
+    is ITS map from fairseq's state-dict keys to its own.  The oracle's state dict (fairseq key names, as the reference's
+    checkpoints have them: speech_encoder_plus.py:387,499-504) must pass through that map with nothing left over, load into
+    torchaudio's model of the same architecture, and give the same hidden states — base (GroupNorm extractor, post-LN) and
+    large (LayerNorm extractor, pre-LN, conv_bias False; the states are collected before the encoder's final LayerNorm)."""
+    torchaudio = pytest.importorskip("torchaudio")
+    from torchaudio.models.wav2vec2.utils.import_fairseq import _map_key
+    om = seeded_init_(oh.HubertModel(oh.HubertCfg.named(name)), 7122).eval()
+    mapped = {}
+    for k, v in om.state_dict().items():
+        nk = _map_key(k)  # raises ValueError on a key fairseq's HubertModel would not have
+        if nk is not None:
+            mapped[nk] = v
+    ta = (torchaudio.models.hubert_base() if name == "hubert" else torchaudio.models.hubert_large()).eval()
+    missing, unexpected = ta.load_state_dict(mapped, strict=False)
+    assert not missing and set(unexpected) <= {"label_embs_concat"}, (missing, unexpected)
+    wav = (0.1 if name == "hubert" else 1.0) * torch.randn(1, 8000, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        mine = om.custom_forward(wav, None)["layer_results"]
+        theirs, _ = ta.extract_features(wav)
+    assert len(mine) == len(theirs) + 1  # the oracle also returns the encoder input (hidden state 0)
+    for a, b in zip(mine[1:], theirs):
+        assert torch.allclose(a, b, atol=atol), (a - b).abs().max()
