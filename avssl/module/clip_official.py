@@ -25,6 +25,21 @@ _clip_models = {"RN50", "RN101", "RN50x4", "RN50x16", "RN50x64", "ViT-B/32", "Vi
 SOT_TOKEN, EOT_TOKEN = 49406, 49407  # openai BPE ids of <|startoftext|> / <|endoftext|>
 
 
+def _load_clip_state(path: str) -> dict:
+    """State dict of an openai CLIP checkpoint: the released files (``ViT-B-32.pt`` ...) are TorchScript archives with fp16
+    weights and three extra scalars (clip.load, clip_official.py:50); a plain ``state_dict`` / ``{"state_dict": ...}`` pickle
+    also loads."""
+    try:
+        return torch.jit.load(path, map_location="cpu").state_dict()
+    except RuntimeError:
+        obj = torch.load(path, map_location="cpu", weights_only=False)
+        if isinstance(obj, dict) and isinstance(obj.get("state_dict"), dict):
+            obj = obj["state_dict"]
+        if hasattr(obj, "state_dict"):
+            obj = obj.state_dict()
+        return obj
+
+
 class ClipModel(nn.Module):
     def __init__(self, name: str, device: str = "cpu", image_encoder_trainable: bool = False, text_encoder_trainable: bool = False,
                  reduce_subword_embbedding: str = None, **kwargs):
@@ -43,7 +58,7 @@ class ClipModel(nn.Module):
             self.model.logit_scale.fill_(float(np.log(1 / 0.07)))
         ckpt = kwargs.get("ckpt_path") or os.environ.get("SPEECHCLIP_CLIP_CKPT")
         if ckpt:
-            state = torch.load(ckpt, map_location="cpu")
+            state = _load_clip_state(ckpt)
             self.model.load_state_dict({k: v.float() for k, v in state.items() if k in dict(self.model.named_parameters())}, strict=True)
         self.image_encoder_trainable = image_encoder_trainable
         self.text_encoder_trainable = text_encoder_trainable

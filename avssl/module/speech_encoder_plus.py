@@ -7,6 +7,8 @@ are replaced by one bookkeeping kernel (``scb_frame_lengths``) + one crop/pad ke
 """
 import logging
 import os
+import pickle
+import types
 from typing import List, Tuple, Union
 
 import torch
@@ -25,6 +27,46 @@ from .weighted_sum import WeightedSumLayer
 logger = logging.getLogger(__name__)
 
 FEAT_SELECT_IDX_WEIGHTED_SUM_MODE = "weighted_sum"
+
+
+class _MissingClass(dict):
+    """Stand-in for classes of packages that are not installed (omegaconf / fairseq / argparse namespaces inside the ``cfg`` and
+    ``task_state`` entries of a fairseq checkpoint): only the ``model`` state dict of such a file is read.  It accepts whatever
+    the pickle stream does to the object it replaces (constructor arguments, state, dict items, list appends)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+
+    def __setstate__(self, state):
+        self["__state__"] = state
+
+    def append(self, item):
+        self.setdefault("__items__", []).append(item)
+
+    def extend(self, items):
+        self.setdefault("__items__", []).extend(items)
+
+    add = append
+
+
+class _LenientUnpickler(pickle.Unpickler):
+    def find_class(self, module, name):
+        try:
+            return super().find_class(module, name)
+        except (ModuleNotFoundError, AttributeError):
+            return _MissingClass
+
+
+def load_checkpoint_lenient(path: str):
+    """``torch.load`` that survives pickled objects of absent packages (fairseq checkpoints carry omegaconf configs)."""
+    try:
+        return torch.load(path, map_location="cpu", weights_only=False)
+    except (ModuleNotFoundError, AttributeError):
+        lenient = types.ModuleType("scb_lenient_pickle")
+        lenient.Unpickler = _LenientUnpickler
+        lenient.load = lambda f, **kw: _LenientUnpickler(f, **kw).load()
+        lenient.__name__ = "pickle"
+        return torch.load(path, map_location="cpu", weights_only=False, pickle_module=lenient)
 
 
 class FairseqSpeechEncoder_Hubert(nn.Module):
@@ -69,7 +111,7 @@ class FairseqSpeechEncoder_Hubert(nn.Module):
                 raise FileNotFoundError(
                     f"pretrained=True needs the fairseq checkpoint ({self.MODEL2URL.get(name)}) on local disk: pass "
                     "audio_encoder.ckpt_path or set SPEECHCLIP_HUBERT_CKPT (this build has no network access)")
-            state = torch.load(ckpt, map_location="cpu", weights_only=False)
+            state = load_checkpoint_lenient(ckpt)
             state = state.get("model", state)
             missing, unexpected = self.encoder.load_state_dict(state, strict=False)
             if missing:

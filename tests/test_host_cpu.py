@@ -227,3 +227,76 @@ def test_conv0_layernorm_statistics_from_the_gram_matrix():
     e2 = np.einsum("fk,kj,fj->f", x, gram, x) + 2.0 * x @ wb + (b * b).mean()
     assert np.abs(mean - o.mean(1)).max() < 1e-12
     assert np.abs((e2 - mean * mean) - o.var(1)).max() < 1e-10
+
+
+def _holder_from(state):
+    """nn.Module tree with exactly these (dotted) parameter names — what a TorchScript archive of a model carries."""
+    from torch import nn
+
+    class Holder(nn.Module):
+        pass
+    root = Holder()
+    for name, v in state.items():
+        m = root
+        parts = name.split(".")
+        for p in parts[:-1]:
+            if not hasattr(m, p):
+                setattr(m, p, Holder())
+            m = getattr(m, p)
+        setattr(m, parts[-1], nn.Parameter(v.clone(), requires_grad=False))
+    return root
+
+
+def test_clip_checkpoint_formats(tmp_path):
+    """`ClipModel(ckpt_path=...)` takes openai's released format (a TorchScript archive, fp16 weights, extra scalars) and a plain
+    state-dict pickle; every parameter arrives (strict load over the module's own openai-named keys)."""
+    from avssl.module import ClipModel
+    from oracle import clip as oc
+    from speechclip_b200.init import seeded_init_
+    src = seeded_init_(oc.CLIP(oc.ClipCfg.named("tiny")), 99).state_dict()  # openai key names
+    fp16 = {k: v.half() if v.is_floating_point() and v.dim() > 0 else v for k, v in src.items()}
+    jit_path, sd_path = str(tmp_path / "clip_jit.pt"), str(tmp_path / "clip_sd.pt")
+    torch.jit.script(_holder_from(fp16)).save(jit_path)
+    torch.save({"state_dict": dict(fp16, input_resolution=torch.tensor(32), context_length=torch.tensor(77))}, sd_path)
+    for path in (jit_path, sd_path):
+        m = ClipModel("tiny", ckpt_path=path)
+        got = m.model.state_dict()
+        assert set(got) <= set(src)
+        for k, v in got.items():
+            assert v.dtype == torch.float32 and torch.equal(v, fp16[k].float()), k
+
+
+def test_hubert_checkpoint_fairseq_layout(tmp_path):
+    """`FairseqSpeechEncoder_Hubert(pretrained=True, ckpt_path=...)` reads fairseq's checkpoint layout ({"model": state_dict, "cfg": ...},
+    fairseq key names — the layout torchaudio's fairseq importer pins in tests/test_oracle_crosscheck.py) and refuses a missing file."""
+    from avssl.module import FairseqSpeechEncoder_Hubert
+    from oracle import hubert as oh
+    from speechclip_b200.init import seeded_init_
+    src = seeded_init_(oh.HubertModel(oh.HubertCfg.named("tiny")), 5).state_dict()
+    path = str(tmp_path / "hubert_tiny.pt")
+    torch.save({"model": src, "cfg": {"model": {"_name": "hubert"}}, "args": None}, path)
+    enc = FairseqSpeechEncoder_Hubert("tiny", pretrained=True, ckpt_path=path, feat_select_idx="weighted_sum")
+    got = enc.encoder.state_dict()
+    assert set(got) <= set(src)
+    for k, v in got.items():
+        assert torch.equal(v, src[k].float()), k
+    with pytest.raises(FileNotFoundError):
+        FairseqSpeechEncoder_Hubert("tiny", pretrained=True, ckpt_path=str(tmp_path / "absent.pt"))
+    # a real fairseq file pickles omegaconf / fairseq objects in "cfg": the model weights must load without those packages
+    import sys
+    import types
+    fake = types.ModuleType("scb_fake_omegaconf")
+
+    class DictConfig(dict):
+        pass
+    DictConfig.__module__, DictConfig.__qualname__ = "scb_fake_omegaconf", "DictConfig"
+    fake.DictConfig = DictConfig
+    sys.modules["scb_fake_omegaconf"] = fake
+    path2 = str(tmp_path / "hubert_tiny_cfg.pt")
+    try:
+        torch.save({"model": src, "cfg": DictConfig(model="hubert")}, path2)
+    finally:
+        del sys.modules["scb_fake_omegaconf"]
+    enc2 = FairseqSpeechEncoder_Hubert("tiny", pretrained=True, ckpt_path=path2)
+    for k, v in enc2.encoder.state_dict().items():
+        assert torch.equal(v, src[k].float()), k
