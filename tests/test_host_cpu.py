@@ -300,3 +300,27 @@ def test_hubert_checkpoint_fairseq_layout(tmp_path):
     enc2 = FairseqSpeechEncoder_Hubert("tiny", pretrained=True, ckpt_path=path2)
     for k, v in enc2.encoder.state_dict().items():
         assert torch.equal(v, src[k].float()), k
+
+
+def test_lightning_checkpoint_roundtrip(tmp_path):
+    """`KWClip_GeneralTransformer.load_from_checkpoint` (example.py:10; base_task.py:60-77): a Lightning-style file
+    ({"state_dict", "hyper_parameters": {"config": OrderedNamespace}}) rebuilds the model from the pickled config and restores
+    every tensor; the tower keys carry the fairseq / openai names under `audio_encoder.encoder.` / `clip.model.`."""
+    from avssl.base import OrderedNamespace
+    from avssl.model import KWClip_GeneralTransformer
+    from speechclip_b200.configs import parallel_config
+    torch.manual_seed(3)
+    model = KWClip_GeneralTransformer(OrderedNamespace(parallel_config("tiny")))
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.01 * torch.randn_like(p))
+    sd = model.state_dict()
+    assert any(k.startswith("audio_encoder.encoder.feature_extractor.conv_layers.0.0.weight") for k in sd)
+    assert any(k.startswith("clip.model.visual.transformer.resblocks.0.attn.in_proj_weight") for k in sd)
+    path = str(tmp_path / "model.ckpt")
+    torch.save({"state_dict": sd, "hyper_parameters": {"config": model.config}, "epoch": 3, "global_step": 120}, path)
+    again = KWClip_GeneralTransformer.load_from_checkpoint(path)
+    sd2 = again.state_dict()
+    assert list(sd2) == list(sd)
+    for k in sd:
+        assert torch.equal(sd[k], sd2[k]), k
