@@ -182,16 +182,26 @@ class KWClipBase(BaseLightningModel):
         self.allreduce_gradients()
 
     def allreduce_gradients(self):
-        """Sum the per-rank gradients of the trainable head (one NCCL all-reduce over the flat gradient buffer)."""
+        """Sum the per-rank gradients of the trainable head (one NCCL all-reduce over the flat gradient buffer).
+
+        Every rank back-propagates the same GLOBAL loss through its own rows of the gathered embeddings, so the gradients of the
+        branch / weighted-sum parameters are partial sums (-> SUM).  The criterion's own parameters (the learnable temperature of
+        ``model_large``) are different: each rank already holds their full gradient, exactly what the reference's single-process
+        DataParallel computes once on the master (kwClip.py:184-191).  Only rank 0's copy enters the sum."""
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
             return
+        if dist.get_rank() != 0:
+            for p in self.criterion.parameters():
+                if p.grad is not None:
+                    p.grad.zero_()
         arena = self.arena()
-        g0 = arena.params[0].grad
-        for k in (0, 1):
-            if g0 is not None and g0.data_ptr() == arena.flat_g[k].data_ptr() + 4 * arena.offsets[0]:
-                dist.all_reduce(arena.flat_g[k])
-                return
-        for p in arena.params:  # gradients that autograd did not adopt in place
+        if arena is not None:
+            for k in (0, 1):
+                base = arena.flat_g[k].data_ptr()
+                if all(p.grad is not None and p.grad.data_ptr() == base + 4 * off for p, off in zip(arena.params, arena.offsets)):
+                    dist.all_reduce(arena.flat_g[k])
+                    return
+        for p in (arena.params if arena is not None else self.getTrainableParams()):  # gradients that autograd did not adopt in place
             if p.grad is not None:
                 dist.all_reduce(p.grad)
 

@@ -17,7 +17,7 @@ from speechclip_b200.cascaded import TextTowerPlan, Vocabulary
 from speechclip_b200.engine import VitPlan
 from speechclip_b200.functional import workspace
 from speechclip_b200.init import seeded_init_
-from speechclip_b200.params import ClipArch, ParamTree, clip_param_shapes
+from speechclip_b200.params import ClipArch, ParamTree, clip_param_shapes, restoring
 
 logger = logging.getLogger(__name__)
 
@@ -57,7 +57,7 @@ class ClipModel(nn.Module):
         with torch.no_grad():
             self.model.logit_scale.fill_(float(np.log(1 / 0.07)))
         ckpt = kwargs.get("ckpt_path") or os.environ.get("SPEECHCLIP_CLIP_CKPT")
-        if ckpt:
+        if ckpt and not restoring():  # load_from_checkpoint: the .ckpt's state_dict fills clip.model.* itself
             state = _load_clip_state(ckpt)
             self.model.load_state_dict({k: v.float() for k, v in state.items() if k in dict(self.model.named_parameters())}, strict=True)
         self.image_encoder_trainable = image_encoder_trainable
@@ -82,8 +82,9 @@ class ClipModel(nn.Module):
             self.model.token_embedding = holder
             self.original2Reduced = {int(old): new for new, old in enumerate(self.selected_text_emb_ids)}
             self.reducedl2Original = {new: int(old) for new, old in enumerate(self.selected_text_emb_ids)}
-            self.startOfTxt_reduced = self.original2Reduced[SOT_TOKEN]
-            self.endOfTxt_reduced = self.original2Reduced[EOT_TOKEN]
+            # openai's BPE ids; the test miniatures ("tiny_c", 96-entry vocabulary) keep them as the last two rows
+            self.startOfTxt_reduced = self.original2Reduced[min(SOT_TOKEN, self.arch.vocab - 2)]
+            self.endOfTxt_reduced = self.original2Reduced[min(EOT_TOKEN, self.arch.vocab - 1)]
         self._vit = None
         self._vit_key = None
         self._text = None

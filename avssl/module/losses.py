@@ -46,3 +46,29 @@ class MaskedContrastiveLoss(nn.Module):
         if self.temperature_trainable:
             return InfoNCEFn.apply(feat_A, feat_B, index, self.temperature, 0.0, self.margin, self.dcl, self.a2b, self.b2a, arena)
         return InfoNCEFn.apply(feat_A, feat_B, index, None, self.temperature, self.margin, self.dcl, self.a2b, self.b2a, arena)
+
+
+class SupConLoss(nn.Module):
+    """Reference: avssl/module/losses.py:8-123 (supervised-contrastive / SimCLR loss).  Every shipped config selects
+    ``MaskedContrastiveLoss`` (``cl_loss.type``, spchclp_*.yaml:71; ``SupConLoss`` appears there only as a comment), and the
+    reference's own ``compute_loss`` calls the criterion as ``criterion(feat_A=, feat_B=, index=)`` (kwClip.py:1274-1290), which
+    this class's ``forward(features, labels, mask)`` cannot accept — it is unreachable from the hot path.  The name and the
+    constructor are kept so ``avssl.module`` imports and ``getattr(losses, ...)`` resolve; evaluating it raises."""
+
+    def __init__(self, temperature=0.07, contrast_mode="all", base_temperature=0.07, learnable_temperature=True):
+        super().__init__()
+        self.learnable_temperature = learnable_temperature
+        if learnable_temperature:
+            self.temperature = nn.Parameter(torch.tensor([float(temperature)]))
+        else:
+            self.temperature = temperature
+        self.contrast_mode = contrast_mode
+        self.base_temperature = base_temperature
+
+    @property
+    def current_temperature(self):
+        return self.temperature.item() if self.learnable_temperature else self.temperature
+
+    def forward(self, features, labels=None, mask=None):
+        raise NotImplementedError("SupConLoss has no sm_100a kernel: it is outside the SpeechCLIP hot path (no shipped config or "
+                                  "call site of the reference can reach it); use MaskedContrastiveLoss")

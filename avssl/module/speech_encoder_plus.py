@@ -19,7 +19,7 @@ from speechclip_b200 import engine, ops
 from speechclip_b200.engine import HubertPlan, conv_out_len
 from speechclip_b200.functional import workspace
 from speechclip_b200.init import seeded_init_
-from speechclip_b200.params import HubertArch, ParamTree, hubert_param_shapes
+from speechclip_b200.params import HubertArch, ParamTree, hubert_param_shapes, restoring
 
 from ..util import freeze_model
 from .weighted_sum import WeightedSumLayer
@@ -105,7 +105,7 @@ class FairseqSpeechEncoder_Hubert(nn.Module):
         self.arch = HubertArch.named(name)
         self.encoder = ParamTree.from_shapes(hubert_param_shapes(self.arch))
         seeded_init_(self.encoder, int(kwargs.get("init_seed", 7122)))
-        if pretrained:
+        if pretrained and not restoring():  # load_from_checkpoint: the .ckpt's state_dict fills audio_encoder.encoder.* itself
             ckpt = kwargs.get("ckpt_path") or os.environ.get("SPEECHCLIP_HUBERT_CKPT")
             if not ckpt or not os.path.exists(ckpt):
                 raise FileNotFoundError(
@@ -198,6 +198,7 @@ class FairseqSpeechEncoder_Hubert(nn.Module):
             hidden, T = self.plan(dev).forward(ws, wav_p, valid_frames if lens is not None else None)
         d = self.out_dim
         slab = hidden.view(hidden.shape[0], B, T, d)
+        slab._scb_graph_output = hidden if hasattr(hidden, "_scb_generation") else None
         if feat_select_idx is None:
             feat_select_idx = self.feat_select_idx
         hand_out = feat_select_idx != FEAT_SELECT_IDX_WEIGHTED_SUM_MODE or return_hidden_states
@@ -225,3 +226,17 @@ class FairseqSpeechEncoder_Hubert(nn.Module):
         if return_hidden_states:
             ret.append(states())
         return tuple(ret)
+
+
+class S3prlSpeechEncoderPlus(nn.Module):
+    """Reference: avssl/module/speech_encoder_plus.py:110-336 (speech encoders loaded through the s3prl hub).  Every shipped
+    config uses ``audio_encoder.type: FairseqHubert``; the s3prl package and its hub checkpoints are not available offline and
+    the upstreams it can load are arbitrary torch models with no B200 plan.  The class keeps the name and constructor
+    signature so ``avssl.module`` / ``kwClip.py:61`` resolve, and fails at construction with the reason."""
+
+    def __init__(self, name: str, pretrained: bool = False, trainable: bool = False, device: str = "cpu",
+                 feat_select_idx: Union[str, list] = "all", layer_drop: Union[str, float] = 0.0, max_audio_len: int = -1,
+                 reinit_layers: List[int] = [], unfreeze_layers: List[int] = [], **kwargs):
+        super().__init__()
+        raise NotImplementedError(f"S3prlSpeechEncoderPlus({name!r}): s3prl upstreams are outside the B200 hot path; use "
+                                  "audio_encoder.type: FairseqHubert (hubert / hubert_large_ll60k), as every shipped config does")

@@ -26,7 +26,8 @@ class WeightedSumLayer(nn.Module):
         assert slab.shape[0] == self.n_weights, slab.shape
         L, B, T, d = slab.shape
         arena = self._scb_arena_fn() if self._scb_arena_fn is not None else None
+        guard = getattr(x, "_scb_graph_output", None)  # set by the HuBERT wrapper when the slab is a CUDA-graph output buffer
         slab = slab.detach()
         if slab.dtype != torch.float16:  # fp16 slabs (post-LN tower) are read as they are; anything else as fp32
             slab = slab.float()
-        return WeightedSumFn.apply(self.weights, slab.contiguous().view(L, B * T, d), B, T, self.normalize_features, arena)
+        return WeightedSumFn.apply(self.weights, slab.contiguous().view(L, B * T, d), B, T, self.normalize_features, arena, guard)

@@ -148,7 +148,9 @@ int scb_conv0_layernorm_gelu(const float* wav, int64_t wav_ld, int32_t batch, in
                              const float* gamma, const float* beta, float eps, void* out, int32_t out_fmt, int64_t out_batch_stride,
                              void* scratch, int64_t scratch_bytes, void* stream);
 /* Zero padded frames of x in place (speech_encoder_plus.py:32-33) and write the 16-bit, group-padded (channels per group ->
- * 64), time-padded copy that the positional-conv GEMM walks tap by tap (speech_encoder_plus.py:35). */
+ * 64), time-padded copy that the positional-conv GEMM walks tap by tap (speech_encoder_plus.py:35).  EVERY element of
+ * xpad[batch][rows_pad][groups * 64] is written (zero rows before pad_left and after pad_left + T, zero channels cpg..63 of each
+ * group), so the caller's buffer needs no initialisation. */
 int scb_posconv_pack(float* x, const int32_t* valid_frames, void* xpad, int32_t fmt, int32_t batch, int32_t T, int32_t D, int32_t groups,
                      int32_t pad_left, int32_t rows_pad, void* stream);
 /* CLIP visual.conv1 input (kernel = stride = P, clip_official.py:209): patches[b*G*G + gy*G + gx][c*P*P + py*P + px]. */

@@ -328,13 +328,20 @@ __global__ void __launch_bounds__(256) conv0_ln_apply_kernel(const float* __rest
 __global__ void __launch_bounds__(256) posconv_pack_kernel(float* __restrict__ x, const int* __restrict__ valid, void* __restrict__ xpad,
                                                            int fmt, long long rows, int T, int D, int groups, int cpg, int pad_left,
                                                            int rows_pad) {
+  // One warp per row of the PADDED buffer: the kernel writes every element of xpad (frame rows, the zero rows on both sides and the
+  // zero channels cpg..63 of each group), so the buffer needs no zero-initialisation and can be shared by every (batch, T).
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const int b = (int)(row / T), t = (int)(row % T);
-  float* xr = x + row * D;
+  const int b = (int)(row / rows_pad), tp = (int)(row % rows_pad);
+  const int t = tp - pad_left;
+  uint16_t* pr = reinterpret_cast<uint16_t*>(xpad) + row * (groups * 64);
+  if (t < 0 || t >= T) {
+    for (int c8 = lane; c8 * 8 < groups * 64; c8 += 32) *reinterpret_cast<uint4*>(pr + c8 * 8) = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  float* xr = x + ((long long)b * T + t) * D;
   const bool keep = valid == nullptr || t < valid[b];
-  uint16_t* pr = reinterpret_cast<uint16_t*>(xpad) + ((long long)b * rows_pad + pad_left + t) * (groups * 64);
   for (int c2 = lane; c2 * 2 < D; c2 += 32) {
     const int c = c2 * 2;
     float2 v = *reinterpret_cast<float2*>(xr + c);
@@ -344,6 +351,10 @@ __global__ void __launch_bounds__(256) posconv_pack_kernel(float* __restrict__ x
     }
     const int g = c / cpg, ci = c % cpg;  // cpg is even, so the pair stays inside one group
     *reinterpret_cast<uint32_t*>(pr + g * 64 + ci) = pack16(fmt, v.x, v.y);
+  }
+  if (cpg < 64) {
+    const int padc = (64 - cpg) / 2;  // zero channel pairs per group
+    for (int i = lane; i < groups * padc; i += 32) *reinterpret_cast<uint32_t*>(pr + (i / padc) * 64 + cpg + (i % padc) * 2) = 0u;
   }
 }
 
@@ -485,7 +496,7 @@ int posconv_pack(float* x, const int* valid_frames, void* xpad, int fmt, int bat
   SCB_CHECK(D % groups == 0 && (D / groups) % 2 == 0 && D / groups <= 64, SCB_EUNSUPPORTED,
             "scb_posconv_pack: channels per group (%d) must be even and <= 64", D / groups);
   SCB_CHECK(rows_pad >= pad_left + T, SCB_EINVAL, "scb_posconv_pack: rows_pad too small");
-  const long long rows = (long long)batch * T;
+  const long long rows = (long long)batch * rows_pad;
   if (rows == 0) return SCB_OK;
   posconv_pack_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, valid_frames, xpad, fmt, rows, T, D, groups, D / groups, pad_left,
                                                                  rows_pad);

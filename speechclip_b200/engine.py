@@ -71,6 +71,7 @@ class GraphCache:
         self.device = device
         self.entries: Dict[tuple, object] = {}
         self.kernels_replayed = 0
+        self.replays = 0
 
     def run(self, key: tuple, eager_ws: "Workspace", fn):
         from . import lib as _l
@@ -96,6 +97,10 @@ class GraphCache:
         graph, out, _, n_kernels = ent
         graph.replay()
         self.kernels_replayed += n_kernels
+        self.replays += 1
+        for t in (out if isinstance(out, (tuple, list)) else (out,)):
+            if isinstance(t, torch.Tensor):
+                t._scb_generation = self.replays  # consumers that keep the slab for a backward pass check it (functional.WeightedSumFn)
         return out
 
 
@@ -274,7 +279,7 @@ class HubertPlan:
         # masked zero + grouped positional conv (k taps, SamePad drops the last output frame) + GELU + residual
         K, G, cpg = self.pos_k, self.pos_g, self.pos_cpg
         rows_pad = T + K
-        xpad = ws.view(f"xpad_{B}_{T}", (B, rows_pad, G * 64), H, zero=True)
+        xpad = ws.view("xpad", (B, rows_pad, G * 64), H)  # ONE buffer for every (B, T): the pack kernel writes the zero rows / channels too
         ops.posconv_pack(x, valid_frames, xpad, B, T, d, G, K // 2, rows_pad)
         # Post-LN towers (HuBERT-base) keep the hidden states — LayerNorm outputs — in fp16 only: one tensor is the next GEMM's
         # operand, the residual and the state the weighted sum reads (HIDDEN16; SCB_HIDDEN_FP32=1 restores fp32 copies).

@@ -60,10 +60,20 @@ class GradArena:
 
     def grad_buffer_index(self) -> int:
         """The flat gradient buffer that does NOT alias the live .grad tensors (so autograd's ``grad += new`` is safe)."""
-        g = self.params[0].grad
-        if g is not None and g.data_ptr() == self.flat_g[0].data_ptr() + 4 * self.offsets[0]:
-            return 1
+        base = self.flat_g[0].data_ptr()
+        for p, off in zip(self.params, self.offsets):
+            if p.grad is not None and p.grad.data_ptr() == base + 4 * off:
+                return 1
         return 0
+
+    def backward_buffer(self) -> int:
+        """Buffer index for the backward pass that is executing NOW: chosen when the first of our Functions runs in an autograd
+        graph task and kept for the rest of that task (parameters adopt their views as .grad while the pass is still running,
+        which must not flip the choice), so it never depends on how many forwards preceded this backward."""
+        task = torch._C._current_graph_task_id()
+        if task < 0 or task != getattr(self, "_task", None):
+            self._task, self._task_buf = task, self.grad_buffer_index()
+        return self._task_buf
 
     def grad_view(self, p: torch.nn.Parameter, buf: int) -> torch.Tensor:
         off = self.offsets[self._slot[id(p)]]
@@ -84,19 +94,26 @@ class WeightedSumFn(torch.autograd.Function):
     """avssl/module/weighted_sum.py:26-45.  hidden fp32 or fp16 [L, B*T, d] (frozen tower output, no grad)."""
 
     @staticmethod
-    def forward(ctx, weights, hidden, B, T, normalize, arena):
+    def forward(ctx, weights, hidden, B, T, normalize, arena, guard=None):
+        """guard: the tower's graph-output tensor object that ``hidden`` views (its ``_scb_generation`` moves with every replay)."""
         _require_cuda(hidden, "WeightedSumLayer")
         d = hidden.shape[-1]
         out = torch.empty(B, T, d, device=hidden.device, dtype=torch.float32)
         ops.weighted_sum(hidden, weights, normalize, out32=out)
         ctx.save_for_backward(weights, hidden)
-        ctx.meta = (B, T, normalize, arena, arena.grad_buffer_index() if arena else 0)
+        ctx.meta = (B, T, normalize, arena)
+        # under CUDA-graph replay ``hidden`` is the graph's output slab, overwritten by the tower's next replay (engine.GraphCache)
+        ctx.hidden_obj, ctx.hidden_gen = guard, getattr(guard, "_scb_generation", None)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         weights, hidden = ctx.saved_tensors
-        B, T, normalize, arena, buf = ctx.meta
+        B, T, normalize, arena = ctx.meta
+        if getattr(ctx.hidden_obj, "_scb_generation", None) != ctx.hidden_gen:
+            raise RuntimeError("WeightedSumLayer.backward: the speech tower ran again (CUDA-graph replay) before this backward and "
+                               "overwrote the hidden states it needs; run backward before the next forward or set SCB_CUDA_GRAPHS=0")
+        buf = arena.backward_buffer() if arena else 0
         d = hidden.shape[-1]
         if dout.stride(2) != 1 or dout.stride(1) != d:
             dout = dout.contiguous()
@@ -104,7 +121,7 @@ class WeightedSumFn(torch.autograd.Function):
         gw.zero_()
         scratch = torch.empty(64, device=hidden.device, dtype=torch.float32)
         ops.weighted_sum_bwd(hidden, weights, normalize, dout, T, dout.stride(0), 0, scratch, gw, 1.0)
-        return gw, None, None, None, None, None
+        return gw, None, None, None, None, None, None
 
 
 # ---------------------------------------------------------------------------------------------------- parallel branch
@@ -119,14 +136,13 @@ class ParallelBranchFn(torch.autograd.Function):
         out, saved = head.cls_forward(workspace(audio_feat.device), p, audio_feat.detach(), kv_len)
         ctx.head, ctx.arena, ctx.saved, ctx.params = head, arena, saved, params
         ctx.need_dfeat = audio_feat.requires_grad
-        ctx.buf = arena.grad_buffer_index() if arena else 0
         return out
 
     @staticmethod
     def backward(ctx, dout):
         head, arena, params = ctx.head, ctx.arena, ctx.params
         p = dict(zip(PARAM_ORDER, params))
-        buf = ctx.buf
+        buf = arena.backward_buffer() if arena else 0
         g = {name: _grad_like(t, arena, buf) for name, t in p.items()}
         dfeat = head.cls_backward(workspace(dout.device), p, ctx.saved, dout.contiguous(), g, need_dfeat=ctx.need_dfeat)
         ctx.saved = None
@@ -151,7 +167,6 @@ class CascadedBranchFn(torch.autograd.Function):
             rt["sot"], rt["eot"], rt["training"], need_grad)
         ctx.head, ctx.arena, ctx.saved, ctx.params, ctx.rt = head, arena, saved, params, rt
         ctx.need_dfeat = audio_feat.requires_grad
-        ctx.buf = arena.grad_buffer_index() if arena else 0
         ctx.mark_non_differentiable(keywords, cos, idx, stats)
         return feat, keywords, cos, idx, stats
 
@@ -162,7 +177,8 @@ class CascadedBranchFn(torch.autograd.Function):
         if ctx.saved.get("text") is None:
             raise RuntimeError("KW_CascadedBranch: backward through an eval-mode forward (no activations were kept)")
         p = dict(zip(ORDER, params))
-        g = {name: _grad_like(t, arena, ctx.buf) for name, t in p.items()}
+        buf = arena.backward_buffer() if arena else 0
+        g = {name: _grad_like(t, arena, buf) for name, t in p.items()}
         dx = head.backward(workspace(dfeat.device), p, ctx.saved, dfeat.contiguous(), g, rt["vocab"], rt["text"], need_dfeat=ctx.need_dfeat)
         ctx.saved = None
         return (dx, None, None, None, None) + tuple(g[name] if p[name].requires_grad else None for name in ORDER)
@@ -278,14 +294,14 @@ class InfoNCEFn(torch.autograd.Function):
         if ids is not None:
             ids = ids.contiguous()
         ops.infonce(a, b, ids, log_mult, float(fixed_mult), float(margin), dcl, a2b, b2a, scratch, phase=1, loss=loss)
-        ctx.state = (a, b, ids, log_mult, float(fixed_mult), float(margin), dcl, a2b, b2a, scratch, arena,
-                     arena.grad_buffer_index() if arena else 0)
+        ctx.state = (a, b, ids, log_mult, float(fixed_mult), float(margin), dcl, a2b, b2a, scratch, arena)
         return loss
 
     @staticmethod
     def backward(ctx, dloss):
-        a, b, ids, log_mult, fixed_mult, margin, dcl, a2b, b2a, scratch, arena, buf = ctx.state
+        a, b, ids, log_mult, fixed_mult, margin, dcl, a2b, b2a, scratch, arena = ctx.state
         ctx.state = None
+        buf = arena.backward_buffer() if arena else 0
         if scratch is None:
             raise RuntimeError("MaskedContrastiveLoss: backward called twice (the logits scratch was consumed)")
         need_a, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1]

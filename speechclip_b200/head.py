@@ -208,6 +208,9 @@ class ParallelHead:
         src_t = ws.view(f"head_src_t_{ldt}", (d, ldt), BF, zero=True)
         ops.transpose(dkv.view(M, 2 * d), dkv_t[:, :M])
         ops.transpose(s["src"].view(M, d), src_t[:, :M])
+        if ldt > M:  # the buffers are shared by every M of this 256-bucket: columns [M, ldt) may hold a LONGER earlier batch
+            dkv_t[:, M:].zero_()
+            src_t[:, M:].zero_()
         if NS == 1:
             ops.gemm_raw(a=dkv_t, a_inner=M, a_rows=2 * d, a_row_stride=ldt, m_per_batch=2 * d, w=src_t, n=d, k=M, b_row_stride=ldt,
                          out=g_w, out_offset=d * d, ldc=d)

@@ -13,6 +13,25 @@ import torch
 from torch import nn
 
 
+class _Restore:
+    """Set while a model is being rebuilt from a Lightning checkpoint (``load_from_checkpoint``): the checkpoint's
+    ``state_dict`` carries every tower tensor, so the towers must not look for the separate fairseq / openai files that the
+    pickled config's ``pretrained: true`` asks for (a released SpeechCLIP ``.ckpt`` loads on a machine that never had them)."""
+    active = False
+
+
+class restoring_from_checkpoint:
+    def __enter__(self):
+        self._prev, _Restore.active = _Restore.active, True
+
+    def __exit__(self, *exc):
+        _Restore.active = self._prev
+
+
+def restoring() -> bool:
+    return _Restore.active
+
+
 class ParamTree(nn.Module):
     """A module tree built from dotted parameter names (numeric components become children named "0", "1", ...)."""
 

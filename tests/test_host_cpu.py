@@ -193,6 +193,41 @@ def test_gather_features_world_size_2_gloo():
     assert torch.equal(got[0], got[1])  # identical global feature matrix on both ranks
 
 
+def _allreduce_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from avssl.model import KWClip_GeneralTransformer
+    torch.manual_seed(0)
+    model = KWClip_GeneralTransformer(OrderedNamespace(parallel_config("tiny_large")))  # learnable temperature (model_large YAMLs)
+    params = [p for p in model.getTrainableParams() if p.requires_grad]
+    for p in params:
+        p.grad = torch.full_like(p, float(rank + 1))
+    model.on_after_backward()
+    t = model.criterion.temperature
+    others = [p for p in params if p is not t]
+    q.put((rank, float(t.grad), sorted({float(p.grad.flatten()[0]) for p in others}), all(bool((p.grad == p.grad.flatten()[0]).all()) for p in others)))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_counts_the_temperature_once_world_size_2_gloo():
+    """every rank differentiates the same GLOBAL loss, so each holds the FULL gradient of the criterion's
+    learnable temperature while the branch gradients are per-rank partial sums: after ``on_after_backward`` the branch gradients
+    are the sum over ranks and the temperature gradient is counted once (rank 0's), as in the reference's single-process DP."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_allreduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=180) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, t_grad, other_vals, uniform in got:
+        assert t_grad == 1.0, (rank, t_grad)          # rank 0 contributed 1, rank 1 contributed 0
+        assert other_vals == [3.0] and uniform, (rank, other_vals)   # 1 + 2
+
+
 def test_gelu_h16_fit_constants_in_the_cuda_header():
     """The sigmoid-polynomial erf-GELU of the 16-bit GEMM / conv0 epilogues (csrc/common.cuh: gelu_h16): the constants compiled
     into the kernels keep |error| <= 3e-5 on the GELU value over the whole real line, including beyond the clamp."""
