@@ -19,7 +19,7 @@ from torch import nn
 from speechclip_b200 import ops
 from speechclip_b200.cascaded import PARAM_ORDER as CASCADED_PARAM_ORDER
 from speechclip_b200.cascaded import CascadedHead
-from speechclip_b200.functional import CascadedBranchFn, GradArena, L2NormFn, ParallelBranchFn
+from speechclip_b200.functional import CascadedBranchFn, DropoutState, GradArena, L2NormFn, ParallelBranchFn
 from speechclip_b200.head import PARAM_ORDER, ParallelHead
 from speechclip_b200.optim import FusedAdam
 
@@ -360,6 +360,7 @@ class KW_CascadedBranch(nn.Module):
                                      learnable=bn.learnable if hasattr(bn, "learnable") else True,
                                      parallel=bn.parallel if hasattr(bn, "parallel") else False)
         self._scb_arena_fn = None
+        self._scb_dropout = DropoutState()
 
     def _create_cls(self) -> torch.nn.Parameter:
         return torch.nn.Parameter(torch.randn([1, self.keyword_num, self.config.model_settings.cascaded_branch.transformer_args.d_model]))
@@ -402,9 +403,10 @@ class KW_CascadedBranch(nn.Module):
         arena = self._scb_arena_fn() if self._scb_arena_fn is not None else None
         bn = self.bn_layer.bn_layer
         sot, eot = self.clip.special_tokens()
+        p_drop = float(self.self_att.dropout) if self.training else 0.0   # nn.MultiheadAttention(dropout=...) (TransformerModels.py:110-117)
         rt = dict(vocab=self.clip.vocabulary(dev), text=self.clip.text_plan(dev), bn_buffers=(bn.running_mean, bn.running_var),
                   temp=self.vector_quantizer.temperature(), sot=int(sot), eot=int(eot), training=self.training,
-                  need_grad=torch.is_grad_enabled())
+                  need_grad=torch.is_grad_enabled(), drop=(p_drop, self._scb_dropout.advance(dev)) if p_drop > 0 else None)
         feat, keywords, cos, idx, stats = CascadedBranchFn.apply(audio_feat, kv_len, head, arena, rt,
                                                                  *[p[k] for k in CASCADED_PARAM_ORDER])
         if self.training:
@@ -433,6 +435,7 @@ class KW_ParallelBranch(nn.Module):
         if self.need_projection:
             self.linear_proj = nn.Linear(self.audio_dim, self.out_dim)
         self._scb_arena_fn = None
+        self._scb_dropout = DropoutState()
 
     def _create_cls(self):
         return torch.nn.Parameter(torch.randn([1, 1, self.config.model_settings.parallel_branch.transformer_args.d_model]))
@@ -464,7 +467,9 @@ class KW_ParallelBranch(nn.Module):
         head, p = self._head()
         kv_len = self._kv_len(audio_len, audio_feat.size(1) + 1, audio_feat.device)
         arena = self._scb_arena_fn() if self._scb_arena_fn is not None else None
-        return ParallelBranchFn.apply(audio_feat, kv_len, head, arena, *[p[k] for k in PARAM_ORDER])
+        p_drop = float(self.self_att.dropout) if self.training else 0.0   # nn.TransformerEncoderLayer(dropout=...) (TransformerModels.py:55-75)
+        drop = (p_drop, self._scb_dropout.advance(audio_feat.device)) if p_drop > 0 else None
+        return ParallelBranchFn.apply(audio_feat, kv_len, head, arena, drop, *[p[k] for k in PARAM_ORDER])
 
 
 OVERLAP_TOWERS = os.environ.get("SCB_OVERLAP_TOWERS", "1") != "0"

@@ -43,7 +43,7 @@ class TransformerEncoder(nn.Module):
         shapes["norm.weight"], shapes["norm.bias"] = (d_model,), (d_model,)
         self.model = ParamTree.from_shapes(shapes)
         self.d_model, self.nhead, self.layer_norm_eps = d_model, nhead, layer_norm_eps
-        self.dropout = dropout  # eval-mode arithmetic: dropout is not applied on this path
+        self.dropout = dropout  # applied in train mode by the branch's kernel sequence (speechclip_b200/head.py: four sites of the layer)
         self.reset_parameters()
 
     @torch.no_grad()
@@ -113,7 +113,7 @@ class MultiheadAttentionAndNorm(nn.Module):
         self.multihead_attn_layer = tree.multihead_attn_layer
         self.attentionBlock_Norm = tree.attentionBlock_Norm
         self.d_model, self.nhead, self.layer_norm_eps = d_model, nhead, layer_norm_eps
-        self.dropout = dropout  # eval-mode arithmetic: attention dropout is not applied on this path
+        self.dropout = dropout  # attention dropout, applied in train mode by the keyword attention kernel (speechclip_b200/cascaded.py)
         self.reset_parameters()
 
     @torch.no_grad()

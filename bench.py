@@ -379,7 +379,7 @@ def run_own(args):
                                 "cascaded": "Cascaded SpeechCLIP-base (HuBERT-base + keyword VQ over 8112 subwords + CLIP ViT-B/32 text and image towers)"}[args.config]
                                + " training step, batch 256, 102400-sample utterances",
                    "global_batch": global_batch, "pairs_per_gpu": per_gpu, "frames": 319, "parallelism": f"dp{world}",
-                   "mode": "training step, eval-mode arithmetic (dropout p=0), frozen towers, trainable branch "
+                   "mode": "training step (model.train()): branch dropout p=0.1 active (Philox masks, regenerated in backward), frozen towers in eval arithmetic, trainable branch "
                            + ("2.77 M params (+ frozen CLIP text tower in the differentiated path)" if args.config == "cascaded" else "7.48 M params"),
                    "l2": "inputs (259 MB) and activations (GBs) larger than the 126 MB L2; no flush needed",
                    "cuda_graphs": use_graphs, "tower_streams": 2 if kwclip_mod.OVERLAP_TOWERS else 1},

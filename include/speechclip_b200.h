@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SCB_ABI_VERSION 2
+#define SCB_ABI_VERSION 3
 
 enum { SCB_OK = 0, SCB_EINVAL = -1, SCB_ECUDA = -2, SCB_EUNSUPPORTED = -3 };
 enum { SCB_F32 = 0, SCB_F16 = 1, SCB_BF16 = 2 };
@@ -106,13 +106,29 @@ int scb_attention_fwd(const void* q, const void* k, const void* v, void* o, int3
  * (kwClip.py:1103) and its query is the same learned vector for every utterance, so per (utterance, head) ONE
  * query attends over all keys.  q fp32 [heads*head_dim] (unscaled; scale applied inside); kv 16-bit [batch][Tk][kv_ld]
  * with K at column k_off + h*head_dim and V at v_off + h*head_dim.  probs fp32 [batch][heads][Tk] is saved for backward.
- * bwd writes dkv (16-bit, same layout as kv; rows >= kv_len zero) and ACCUMULATES dq (fp32 [heads*head_dim]). */
+ * bwd writes dkv (16-bit, same layout as kv; rows >= kv_len zero) and ACCUMULATES dq (fp32 [heads*head_dim]).
+ * drop_p > 0: attention dropout of nn.MultiheadAttention in train mode (TransformerModels.py:64-72, dropout 0.1): the context
+ * is sum_j p_j m_j v_j with m_j in {0, 1/(1-drop_p)} drawn from (rng_state, rng_site, element (b*heads+h)*Tk + j) — see
+ * scb_dropout_mask; probs keeps the UNdropped p and bwd regenerates m from the same rng_state. */
 int scb_cls_attention_fwd(const float* q, const void* kv, int32_t kv_fmt, int64_t kv_ld, int64_t kv_bs, int32_t k_off, int32_t v_off,
                           const int32_t* kv_len, int32_t batch, int32_t heads, int32_t head_dim, int32_t Tk, float scale, float* probs,
-                          float* ctx32, void* ctx16, int32_t ctx16_fmt, void* stream);
+                          float* ctx32, void* ctx16, int32_t ctx16_fmt, float drop_p, const int64_t* rng_state, int32_t rng_site,
+                          void* stream);
 int scb_cls_attention_bwd(const float* q, const void* kv, int32_t kv_fmt, int64_t kv_ld, int64_t kv_bs, int32_t k_off, int32_t v_off,
                           const int32_t* kv_len, int32_t batch, int32_t heads, int32_t head_dim, int32_t Tk, float scale,
-                          const float* probs, const float* dctx, void* dkv, int32_t dkv_fmt, float* dq_part, void* stream);
+                          const float* probs, const float* dctx, void* dkv, int32_t dkv_fmt, float* dq_part, float drop_p,
+                          const int64_t* rng_state, int32_t rng_site, void* stream);
+
+/* Dropout of the trainable branch (nn.TransformerEncoderLayer / nn.MultiheadAttention in train mode, p = 0.1:
+ * TransformerModels.py:55-75,110-117; spchclp_p.yaml:27).  Decisions are a pure function of (seed, step, site, element):
+ * Philox-4x32-10 with key = seed and counter = (element >> 2, site, step), 32-bit lane element & 3, dropped when the draw is
+ * below p * 2^32, survivors scaled by 1/(1-p).  rng_state is a device int64[2] = {seed, step}; scb_rng_advance does step += 1
+ * (once per training step, graph-capturable).  The backward pass regenerates the forward's masks from a copy of rng_state.
+ *   scb_dropout_mask: mask[i] = 0 or 1/(1-p) for element i of `site` (tests hand these masks to the CPU oracle);
+ *   scb_dropout_rows: y[i] = x[i] * mask[i] (in place allowed) — forward on activations, backward on their gradients. */
+int scb_rng_advance(int64_t* rng_state, void* stream);
+int scb_dropout_mask(const int64_t* rng_state, int32_t site, float p, float* mask, int64_t n, void* stream);
+int scb_dropout_rows(const float* x, float* y, int64_t n, float p, const int64_t* rng_state, int32_t site, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Waveform front end.
@@ -234,16 +250,19 @@ int scb_retrieval_rank(const float* score, int64_t ld, int32_t rows, int32_t col
  * (kwClip.py:866-872): nq <= 8 learned queries shared by every utterance attend over that utterance's frames.
  * q fp32 [nq][heads*head_dim] (already projected, unscaled); kv 16-bit [batch][Tk][kv_ld], K of head h at k_off + h*head_dim,
  * V at v_off + h*head_dim; kv_len[b] = valid rows (NULL = all) -- the key_padding_mask of kwClip.py:870.
- * probs fp32 [batch][heads][nq][Tk] (saved for the backward; zero beyond kv_len), ctx fp32 [batch][nq][heads*head_dim]. */
+ * probs fp32 [batch][heads][nq][Tk] (saved for the backward; zero beyond kv_len), ctx fp32 [batch][nq][heads*head_dim].
+ * drop_p > 0: attention dropout (train mode, TransformerModels.py:110-117) on element ((b*heads+h)*nq + k)*Tk + j of rng_site,
+ * as in scb_cls_attention_fwd. */
 int scb_mq_attention_fwd(const float* q, const void* kv, int32_t kv_fmt, int64_t kv_ld, int64_t kv_batch_stride, int32_t k_off, int32_t v_off,
                          const int32_t* kv_len, int32_t batch, int32_t heads, int32_t head_dim, int32_t nq, int32_t Tk, float scale,
-                         float* probs, float* ctx, void* stream);
+                         float* probs, float* ctx, float drop_p, const int64_t* rng_state, int32_t rng_site, void* stream);
 /* Backward: dkv (16-bit, layout of kv; rows >= kv_len zeroed; only the K and V column ranges are written), dq_part fp32
  * [batch][nq][heads*head_dim] = every utterance's contribution to dq (sum over the batch with scb_column_sum: no atomics,
  * bit-reproducible). */
 int scb_mq_attention_bwd(const float* q, const void* kv, int32_t kv_fmt, int64_t kv_ld, int64_t kv_batch_stride, int32_t k_off, int32_t v_off,
                          const int32_t* kv_len, int32_t batch, int32_t heads, int32_t head_dim, int32_t nq, int32_t Tk, float scale,
-                         const float* probs, const float* dctx, void* dkv, int32_t dkv_fmt, float* dq_part, void* stream);
+                         const float* probs, const float* dctx, void* dkv, int32_t dkv_fmt, float* dq_part, float drop_p,
+                         const int64_t* rng_state, int32_t rng_site, void* stream);
 
 /* Kw_BatchNorm, eachKw + parallel (avssl/module/speechclip_c_modules/kw_bn.py:96-125): x fp32 [batch][n_kw][d] is viewed as
  * BatchNorm1d over d*n_kw features with feature index f = dim * n_kw + kw (the permute/reshape of kw_bn.py:116-118).

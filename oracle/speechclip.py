@@ -52,7 +52,23 @@ class BranchEncoder(nn.Module):
         self.model = nn.TransformerEncoder(layer, n_layers, nn.LayerNorm(d_model, eps=1e-5), enable_nested_tensor=False)
         self.nhead, self.norm_first = nhead, norm_first
 
-    def _attn(self, lyr, x, key_pad):
+    # ``masks`` (train mode, TransformerModels.py:55-75 -> nn.TransformerEncoderLayer(dropout=p)): multiplicative dropout masks
+    # (0 or 1/(1-p)) for the four dropouts of the layer, given for query row 0 only — the row the branch consumes (kwClip.py:1103);
+    # keys "attn" [B, H, L], "dropout1" [B, D], "ffn" [B, F], "dropout2" [B, D]; masks with one more dimension cover every row
+    # ("attn" [B, H, L, L], ...).  torch draws them from its own generator inside library code, which cannot be replayed
+    # elsewhere; the oracle takes the masks as inputs so both sides evaluate the same realisation.  Pinned by
+    # tests/golden/ref_branch_train_dropout.npz (the reference's module in train mode with injected masks).
+    @staticmethod
+    def _row0(x, mask):
+        if mask is None:
+            return x
+        if mask.dim() == x.dim():
+            return x * mask
+        m = torch.ones_like(x)
+        m[:, 0] = mask
+        return x * m
+
+    def _attn(self, lyr, x, key_pad, masks=None):
         B, L, D = x.shape
         hd = D // self.nhead
         qkv = x @ lyr.self_attn.in_proj_weight.t() + lyr.self_attn.in_proj_bias
@@ -62,23 +78,32 @@ class BranchEncoder(nn.Module):
         v = v.view(B, L, self.nhead, hd).transpose(1, 2)
         s = q @ k.transpose(-1, -2)
         s = s.masked_fill(key_pad[:, None, None, :], float("-inf"))
-        o = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, L, D)
+        p = torch.softmax(s, -1)
+        if masks is not None:
+            if masks["attn"].dim() == 4:
+                p = p * masks["attn"]
+            else:
+                pm = torch.ones_like(p)
+                pm[:, :, 0, :] = masks["attn"]
+                p = p * pm
+        o = (p @ v).transpose(1, 2).reshape(B, L, D)
         return o @ lyr.self_attn.out_proj.weight.t() + lyr.self_attn.out_proj.bias
 
-    def _layer(self, lyr, x, key_pad):
-        ff = lambda y: lyr.linear2(F.gelu(lyr.linear1(y)))
+    def _layer(self, lyr, x, key_pad, masks=None):
+        m = masks or {}
+        ff = lambda y: self._row0(lyr.linear2(self._row0(F.gelu(lyr.linear1(y)), m.get("ffn"))), m.get("dropout2"))
         if self.norm_first:
-            x = x + self._attn(lyr, lyr.norm1(x), key_pad)
+            x = x + self._row0(self._attn(lyr, lyr.norm1(x), key_pad, masks), m.get("dropout1"))
             return x + ff(lyr.norm2(x))
-        x = lyr.norm1(x + self._attn(lyr, x, key_pad))
+        x = lyr.norm1(x + self._row0(self._attn(lyr, x, key_pad, masks), m.get("dropout1")))
         return lyr.norm2(x + ff(x))
 
-    def forward(self, src, key_padding_mask, hidden: Optional[list] = None):
+    def forward(self, src, key_padding_mask, hidden: Optional[list] = None, masks=None):
         x = src
         for lyr in self.model.layers:
             if hidden is not None:
                 hidden.append(x)
-            x = self._layer(lyr, x, key_padding_mask)
+            x = self._layer(lyr, x, key_padding_mask, masks)
         if hidden is not None:
             hidden.append(x)
         return self.model.norm(x)
@@ -96,9 +121,9 @@ class ParallelBranch(nn.Module):
         src = torch.cat([self.cls.expand(B, 1, -1), audio_feat], 1)          # kwClip.py:1093-1094
         return src, keypadding_mask(T + 1, audio_len + 1)                     # :1096-1099
 
-    def forward(self, audio_feat, audio_len):
+    def forward(self, audio_feat, audio_len, masks=None):
         src, kpm = self._src(audio_feat, audio_len)
-        out = self.self_att(src, kpm)
+        out = self.self_att(src, kpm, masks=masks)
         return self.linear_proj(out[:, 0])                                    # :1103-1106
 
     def extract_hidden_states(self, audio_feat, audio_len):
@@ -119,7 +144,9 @@ class AttentionAndNorm(nn.Module):
         self.attentionBlock_Norm = nn.LayerNorm(d_model, eps=layer_norm_eps)
         self.nhead = nhead
 
-    def forward(self, src, key_padding_mask):
+    def forward(self, src, key_padding_mask, attn_mask_rows=None):
+        """attn_mask_rows: train-mode attention-dropout mask (0 or 1/(1-p)) [B, H, K, L] for the first K query rows (the keyword
+        rows the cascaded branch consumes, kwClip.py:878-882); None = eval."""
         m = self.multihead_attn_layer
         B, L, D = src.shape
         hd = D // self.nhead
@@ -129,7 +156,12 @@ class AttentionAndNorm(nn.Module):
         k = k.view(B, L, self.nhead, hd).transpose(1, 2)
         v = v.view(B, L, self.nhead, hd).transpose(1, 2)
         s = (q @ k.transpose(-1, -2)).masked_fill(key_padding_mask[:, None, None, :], float("-inf"))
-        o = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, L, D)
+        p = torch.softmax(s, -1)
+        if attn_mask_rows is not None:
+            pm = torch.ones_like(p)
+            pm[:, :, :attn_mask_rows.shape[2], :] = attn_mask_rows
+            p = p * pm
+        o = (p @ v).transpose(1, 2).reshape(B, L, D)
         return self.attentionBlock_Norm(o @ m.out_proj.weight.t() + m.out_proj.bias + src)
 
 
@@ -200,12 +232,12 @@ class CascadedBranch(nn.Module):
         self.vq_temp = vq_temp
         self.sot_token, self.eot_token = sot_token, eot_token
 
-    def forward(self, audio_feat, audio_len, training=True, collect=None, force_idx=None):
+    def forward(self, audio_feat, audio_len, training=True, collect=None, force_idx=None, attn_mask_rows=None):
         B, T = audio_feat.shape[:2]
         K = self.keyword_num
         src = torch.cat([self.cls.expand(B, K, -1), audio_feat], 1)                     # kwClip.py:870-872
         kpm = keypadding_mask(T + K, audio_len + K)                                        # :874-876
-        kw = self.self_att(src, kpm)[:, :K]                                                # :878-882
+        kw = self.self_att(src, kpm, attn_mask_rows)[:, :K]                                # :878-882
         kw = self.linear_proj(kw)                                                          # :884
         kw = self.bn_layer(kw)                                                             # :886-887
         emb = self.clip_model[0].token_embedding.weight

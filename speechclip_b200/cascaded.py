@@ -167,6 +167,9 @@ class Vocabulary:
 
 
 # ====================================================================================================== the branch
+SITE_MQ_ATTN = 8   # dropout site of the keyword attention weights: element ((b * heads + h) * K + k) * (T + K) + j
+
+
 class CascadedHead:
     """Stateless executor of KW_CascadedBranch.forward; ``p`` maps PARAM_ORDER names to live fp32 CUDA tensors."""
 
@@ -184,10 +187,12 @@ class CascadedHead:
         ops.broadcast_row(p["cls"].view(-1), None, src, Tk * d, B, K * d)
         return src
 
-    def keywords_forward(self, ws: Workspace, p, audio_feat: torch.Tensor, kv_len: torch.Tensor, bn_buffers, training: bool):
+    def keywords_forward(self, ws: Workspace, p, audio_feat: torch.Tensor, kv_len: torch.Tensor, bn_buffers, training: bool, drop=None):
         """audio_feat fp32 [B, T, d]; kv_len int32 [B] = audio_len + K.  -> (kw_bn fp32 [B, K, W], saved).
-        kwClip.py:866-887: attention block on the keyword rows, linear_proj, Kw_BatchNorm."""
+        kwClip.py:866-887: attention block on the keyword rows, linear_proj, Kw_BatchNorm.
+        drop = (p, rng_state): train-mode attention dropout of nn.MultiheadAttention (TransformerModels.py:110-117)."""
         B, T, d = audio_feat.shape
+        drop = (float(drop[0]), drop[1].clone(), SITE_MQ_ATTN) if drop is not None and drop[0] > 0 else None
         K, W, hd, heads, dev = self.K, self.W, self.hd, self.heads, audio_feat.device
         Tk, R = T + K, B * K
         M = B * Tk
@@ -203,7 +208,7 @@ class CascadedHead:
         ops.rows_bias_act(q, b_in[:d], None, 0, ops.ACT_NONE, None, q)
         probs = _new((B, heads, K, Tk), dev)
         ctx = _new((B, K, d), dev)
-        ops.mq_attention_fwd(q, kv, 0, d, kv_len, heads, hd, hd ** -0.5, probs, ctx)
+        ops.mq_attention_fwd(q, kv, 0, d, kv_len, heads, hd, hd ** -0.5, probs, ctx, drop=drop)
         cls_rows = ws.view("casc_cls_rows", (R, d), torch.float32)
         ops.broadcast_row(p["cls"].view(-1), None, cls_rows, K * d, B, K * d)
         t1 = _new((R, d), dev)
@@ -218,7 +223,7 @@ class CascadedHead:
         ops.batchnorm_fwd(kwp, kw_bn, p["bn_layer.bn_layer.weight"], p["bn_layer.bn_layer.bias"], rm, rv, mean, rstd, self.bn_eps,
                           self.bn_momentum, training)
         saved = dict(B=B, T=T, src=src, kv=kv, q=q, probs=probs, ctx=ctx, t1=t1, x1=x1, st1=st1, kwp=kwp, mean=mean, rstd=rstd,
-                     kv_len=kv_len, kw_bn=kw_bn)
+                     kv_len=kv_len, kw_bn=kw_bn, drop=drop)
         return kw_bn, saved
 
     def quantize(self, ws: Workspace, vocab: Vocabulary, kw_bn: torch.Tensor, temp: float):
@@ -236,9 +241,9 @@ class CascadedHead:
         return cos, idx, stats
 
     def forward(self, ws: Workspace, p, audio_feat, kv_len, bn_buffers, vocab: Vocabulary, text: TextTowerPlan, temp: float,
-                sot: int, eot: int, training: bool, need_grad: bool):
+                sot: int, eot: int, training: bool, need_grad: bool, drop=None):
         """-> (text feature fp32 [B, embed], keywords fp32 [B, K, W], cos, idx, stats, saved)."""
-        kw_bn, s = self.keywords_forward(ws, p, audio_feat, kv_len, bn_buffers, training)
+        kw_bn, s = self.keywords_forward(ws, p, audio_feat, kv_len, bn_buffers, training, drop)
         cos, idx, stats = self.quantize(ws, vocab, kw_bn, temp)
         B, K, W = kw_bn.shape
         x0 = _new((B, K + 2, W), audio_feat.device)
@@ -299,7 +304,7 @@ class CascadedHead:
         dkv = ws.view("casc_dkv", (B, Tk, 2 * d), BF)
         g_w, g_b = g[A0 + "in_proj_weight"], g[A0 + "in_proj_bias"]
         dq_part = ws.view("casc_dq_part", (B, K * d), torch.float32)
-        ops.mq_attention_bwd(s["q"], kv, 0, d, s["kv_len"], heads, hd, hd ** -0.5, s["probs"], dctx, dkv, dq_part)
+        ops.mq_attention_bwd(s["q"], kv, 0, d, s["kv_len"], heads, hd, hd ** -0.5, s["probs"], dctx, dkv, dq_part, drop=s.get("drop"))
         dq = ws.view("casc_dq", (K, d), torch.float32)
         ops.column_sum(dq_part, dq.view(1, K * d))
         ops.sgemm(dq.t(), cls.t(), g_w[:d])                            # dWq[o, i] = sum_k dq[k, o] cls[k, i]

@@ -102,15 +102,17 @@ int scb_attention_fwd(const void* q, const void* k, const void* v, void* o, int3
 }
 int scb_cls_attention_fwd(const float* q, const void* kv, int32_t kv_fmt, int64_t kv_ld, int64_t kv_bs, int32_t k_off, int32_t v_off,
                           const int32_t* kv_len, int32_t batch, int32_t heads, int32_t head_dim, int32_t Tk, float scale, float* probs,
-                          float* ctx32, void* ctx16, int32_t ctx16_fmt, void* stream) {
+                          float* ctx32, void* ctx16, int32_t ctx16_fmt, float drop_p, const int64_t* rng_state, int32_t rng_site,
+                          void* stream) {
   return scb::cls_attention_fwd(q, kv, kv_fmt, kv_ld, kv_bs, k_off, v_off, kv_len, batch, heads, head_dim, Tk, scale, probs, ctx32, ctx16,
-                                ctx16_fmt, ST);
+                                ctx16_fmt, drop_p, (const long long*)rng_state, rng_site, ST);
 }
 int scb_cls_attention_bwd(const float* q, const void* kv, int32_t kv_fmt, int64_t kv_ld, int64_t kv_bs, int32_t k_off, int32_t v_off,
                           const int32_t* kv_len, int32_t batch, int32_t heads, int32_t head_dim, int32_t Tk, float scale,
-                          const float* probs, const float* dctx, void* dkv, int32_t dkv_fmt, float* dq, void* stream) {
+                          const float* probs, const float* dctx, void* dkv, int32_t dkv_fmt, float* dq, float drop_p,
+                          const int64_t* rng_state, int32_t rng_site, void* stream) {
   return scb::cls_attention_bwd(q, kv, kv_fmt, kv_ld, kv_bs, k_off, v_off, kv_len, batch, heads, head_dim, Tk, scale, probs, dctx, dkv,
-                                dkv_fmt, dq, ST);
+                                dkv_fmt, dq, drop_p, (const long long*)rng_state, rng_site, ST);
 }
 
 int scb_frame_lengths(const int64_t* wav_len, int32_t batch, int64_t tw_out, int32_t max_audio_len, int32_t n_frames, int32_t rate,
@@ -191,6 +193,13 @@ int scb_rows_bias_act(const float* x, int64_t x_ld, const float* bias, const flo
   return scb::rows_bias_act(x, x_ld, bias, res, res_ld, act, pre, y, y_ld, rows, d, ST);
 }
 int scb_gelu_bwd(const float* dy, const float* pre, float* dx, int64_t n, void* stream) { return scb::gelu_bwd(dy, pre, dx, n, ST); }
+int scb_rng_advance(int64_t* rng_state, void* stream) { return scb::rng_advance((long long*)rng_state, ST); }
+int scb_dropout_mask(const int64_t* rng_state, int32_t site, float p, float* mask, int64_t n, void* stream) {
+  return scb::dropout_mask((const long long*)rng_state, site, p, mask, n, ST);
+}
+int scb_dropout_rows(const float* x, float* y, int64_t n, float p, const int64_t* rng_state, int32_t site, void* stream) {
+  return scb::dropout_rows(x, y, n, p, (const long long*)rng_state, site, ST);
+}
 int scb_column_sum(const void* in, int32_t in_dtype, int64_t ld, int64_t rows, int32_t cols, float* out, float beta, void* stream) {
   return scb::column_sum(in, in_dtype, ld, rows, cols, out, beta, ST);
 }
@@ -216,15 +225,16 @@ int scb_retrieval_rank(const float* score, int64_t ld, int32_t rows, int32_t col
 
 int scb_mq_attention_fwd(const float* q, const void* kv, int32_t kv_fmt, int64_t kv_ld, int64_t kv_batch_stride, int32_t k_off, int32_t v_off,
                          const int32_t* kv_len, int32_t batch, int32_t heads, int32_t head_dim, int32_t nq, int32_t Tk, float scale,
-                         float* probs, float* ctx, void* stream) {
+                         float* probs, float* ctx, float drop_p, const int64_t* rng_state, int32_t rng_site, void* stream) {
   return scb::mq_attention_fwd(q, kv, kv_fmt, kv_ld, kv_batch_stride, k_off, v_off, kv_len, batch, heads, head_dim, nq, Tk, scale, probs, ctx,
-                               ST);
+                               drop_p, (const long long*)rng_state, rng_site, ST);
 }
 int scb_mq_attention_bwd(const float* q, const void* kv, int32_t kv_fmt, int64_t kv_ld, int64_t kv_batch_stride, int32_t k_off, int32_t v_off,
                          const int32_t* kv_len, int32_t batch, int32_t heads, int32_t head_dim, int32_t nq, int32_t Tk, float scale,
-                         const float* probs, const float* dctx, void* dkv, int32_t dkv_fmt, float* dq, void* stream) {
+                         const float* probs, const float* dctx, void* dkv, int32_t dkv_fmt, float* dq, float drop_p,
+                         const int64_t* rng_state, int32_t rng_site, void* stream) {
   return scb::mq_attention_bwd(q, kv, kv_fmt, kv_ld, kv_batch_stride, k_off, v_off, kv_len, batch, heads, head_dim, nq, Tk, scale, probs, dctx,
-                               dkv, dkv_fmt, dq, ST);
+                               dkv, dkv_fmt, dq, drop_p, (const long long*)rng_state, rng_site, ST);
 }
 int scb_batchnorm_fwd(const float* x, float* y, const float* gamma, const float* beta, float* running_mean, float* running_var,
                       float* save_mean, float* save_rstd, int32_t batch, int32_t n_kw, int32_t d, float eps, float momentum,

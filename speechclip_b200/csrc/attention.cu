@@ -347,7 +347,8 @@ __global__ void __launch_bounds__(128) cls_attention_fwd_kernel(const float* __r
                                                                 long long kv_ld, long long kv_bs, int k_off, int v_off,
                                                                 const int* __restrict__ kv_len, int Tk, int heads, float scale,
                                                                 float* __restrict__ probs, float* __restrict__ ctx32,
-                                                                uint16_t* __restrict__ ctx16, int ctx16_fmt, int batch) {
+                                                                uint16_t* __restrict__ ctx16, int ctx16_fmt, int batch, float drop_p,
+                                                                const long long* __restrict__ rng_state, int rng_site) {
   extern __shared__ float sm[];  // [Tk] scores/probs | [HD] q | [128 x 2] context partials | [8] reduction scratch
   float* sc = sm;
   float* sq = sc + Tk;
@@ -383,7 +384,12 @@ __global__ void __launch_bounds__(128) cls_attention_fwd_kernel(const float* __r
   sum = block_reduce(sum, red, false);  // (its barriers also publish sc[])
   const float inv = 1.f / sum;
   float* po = probs + ((long long)b * heads + h) * Tk;
-  for (int j = tid; j < Tk; j += 128) po[j] = j < len ? sc[j] * inv : 0.f;
+  for (int j = tid; j < Tk; j += 128) po[j] = j < len ? sc[j] * inv : 0.f;   // the UNdropped probabilities (softmax backward)
+  if (drop_p > 0.f) {  // attention dropout (nn.MultiheadAttention, train mode): the context uses p_j * m_j, m_j in {0, 1/(1-p)}
+    const DropoutRng rng(rng_state, rng_site, drop_p);
+    for (int j = tid; j < len; j += 128) sc[j] *= rng.scale(((unsigned long long)b * heads + h) * Tk + j);
+    __syncthreads();
+  }
   constexpr int P = HD / 2;                    // dim pairs
   constexpr int G = P >= 128 ? 1 : 128 / P;    // key groups
   const int pr = tid % P, grp = tid / P;
@@ -422,11 +428,13 @@ __global__ void __launch_bounds__(128) cls_attention_bwd_kernel(const float* __r
                                                                 long long kv_ld, long long kv_bs, int k_off, int v_off,
                                                                 const int* __restrict__ kv_len, int Tk, int heads, float scale,
                                                                 const float* __restrict__ probs, const float* __restrict__ dctx,
-                                                                uint16_t* __restrict__ dkv, int dkv_fmt, float* __restrict__ dq, int batch) {
-  extern __shared__ float sm[];  // [Tk] ds | [Tk] p | [HD] q | [HD] dctx | [256] partials | [8] scratch
+                                                                uint16_t* __restrict__ dkv, int dkv_fmt, float* __restrict__ dq, int batch,
+                                                                float drop_p, const long long* __restrict__ rng_state, int rng_site) {
+  extern __shared__ float sm[];  // [Tk] ds | [Tk] p | [Tk] p*m | [HD] q | [HD] dctx | [256] partials | [8] scratch
   float* sds = sm;
   float* sp = sds + Tk;
-  float* sq = sp + Tk;
+  float* spm = sp + Tk;   // p_j * m_j (dropout mask regenerated from the RNG state of the forward; = p_j without dropout)
+  float* sq = spm + Tk;
   float* sdc = sq + HD;
   float* part = sdc + HD;
   float* red = part + 256;
@@ -435,6 +443,7 @@ __global__ void __launch_bounds__(128) cls_attention_bwd_kernel(const float* __r
   const int len = kv_len ? min(kv_len[b], Tk) : Tk;
   const uint16_t* base = kv + (long long)b * kv_bs + h * HD;
   uint16_t* dbase = dkv + (long long)b * kv_bs + h * HD;
+  const DropoutRng rng(rng_state, rng_site, drop_p);
   const float* pr_g = probs + ((long long)b * heads + h) * Tk;
   for (int d = tid; d < HD; d += 128) {
     sq[d] = q[h * HD + d];
@@ -454,7 +463,10 @@ __global__ void __launch_bounds__(128) cls_attention_bwd_kernel(const float* __r
       dp += a.x * g[0] + a.y * g[1] + bb.x * g[2] + bb.y * g[3] + cc.x * g[4] + cc.y * g[5] + dd.x * g[6] + dd.y * g[7];
     }
     const float pj = pr_g[j];
+    const float mj = drop_p > 0.f ? rng.scale(((unsigned long long)b * heads + h) * Tk + j) : 1.f;
+    dp *= mj;            // d ctx / d p_j = m_j v_j
     sp[j] = pj;
+    spm[j] = pj * mj;
     sds[j] = dp;
     dot += pj * dp;
   }
@@ -467,7 +479,7 @@ __global__ void __launch_bounds__(128) cls_attention_bwd_kernel(const float* __r
     const int j = idx / CH, c = idx % CH;
     uint4 uk = make_uint4(0u, 0u, 0u, 0u), uv = uk;
     if (j < len) {
-      const float ds = sds[j], pj = sp[j];
+      const float ds = sds[j], pj = spm[j];
       const float* qq = sq + c * 8;
       const float* g = sdc + c * 8;
       uk.x = pack16(dkv_fmt, ds * qq[0], ds * qq[1]); uk.y = pack16(dkv_fmt, ds * qq[2], ds * qq[3]);
@@ -556,15 +568,16 @@ int attention_fwd(const void* q, const void* k, const void* v, void* o, int fmt,
 
 int cls_attention_fwd(const float* q, const void* kv, int kv_fmt, long long kv_ld, long long kv_bs, int k_off, int v_off,
                       const int* kv_len, int batch, int heads, int head_dim, int Tk, float scale, float* probs, float* ctx32, void* ctx16,
-                      int ctx16_fmt, cudaStream_t st) {
+                      int ctx16_fmt, float drop_p, const long long* rng_state, int rng_site, cudaStream_t st) {
   SCB_CHECK(q && kv && probs && (ctx32 || ctx16), SCB_EINVAL, "scb_cls_attention_fwd: null operand");
+  SCB_CHECK(drop_p == 0.f || (drop_p > 0.f && drop_p < 1.f && rng_state), SCB_EINVAL, "scb_cls_attention_fwd: dropout needs p in [0,1) and an rng_state");
   if (batch == 0) return SCB_OK;
   const size_t smem = (size_t)(Tk + head_dim + 256 + 8) * sizeof(float);
   SCB_CHECK(smem <= 48 * 1024, SCB_EUNSUPPORTED, "scb_cls_attention_fwd: Tk=%d too long", Tk);
   SCB_CHECK(kv_ld % 8 == 0 && kv_bs % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0 && head_dim % 8 == 0, SCB_EINVAL,
             "scb_cls_attention_fwd: kv strides / offsets / head_dim must be multiples of 8 elements");
   const unsigned grid = (unsigned)(batch * heads);
-  SCB_HD_SWITCH(head_dim, (cls_attention_fwd_kernel<HD_><<<grid, 128, smem, st>>>(q, (const uint16_t*)kv, kv_fmt, kv_ld, kv_bs, k_off, v_off, kv_len, Tk, heads, scale, probs, ctx32, (uint16_t*)ctx16, ctx16_fmt, batch)));
+  SCB_HD_SWITCH(head_dim, (cls_attention_fwd_kernel<HD_><<<grid, 128, smem, st>>>(q, (const uint16_t*)kv, kv_fmt, kv_ld, kv_bs, k_off, v_off, kv_len, Tk, heads, scale, probs, ctx32, (uint16_t*)ctx16, ctx16_fmt, batch, drop_p, rng_state, rng_site)));
   note_launch();
   SCB_LAUNCH_OK("cls_attention_fwd");
   return SCB_OK;
@@ -572,15 +585,16 @@ int cls_attention_fwd(const float* q, const void* kv, int kv_fmt, long long kv_l
 
 int cls_attention_bwd(const float* q, const void* kv, int kv_fmt, long long kv_ld, long long kv_bs, int k_off, int v_off,
                       const int* kv_len, int batch, int heads, int head_dim, int Tk, float scale, const float* probs, const float* dctx,
-                      void* dkv, int dkv_fmt, float* dq, cudaStream_t st) {
+                      void* dkv, int dkv_fmt, float* dq, float drop_p, const long long* rng_state, int rng_site, cudaStream_t st) {
   SCB_CHECK(q && kv && probs && dctx && dkv && dq, SCB_EINVAL, "scb_cls_attention_bwd: null operand");
+  SCB_CHECK(drop_p == 0.f || (drop_p > 0.f && drop_p < 1.f && rng_state), SCB_EINVAL, "scb_cls_attention_bwd: dropout needs p in [0,1) and an rng_state");
   if (batch == 0) return SCB_OK;
-  const size_t smem = (size_t)(2 * Tk + 2 * head_dim + 256 + 8) * sizeof(float);
+  const size_t smem = (size_t)(3 * Tk + 2 * head_dim + 256 + 8) * sizeof(float);
   SCB_CHECK(smem <= 48 * 1024, SCB_EUNSUPPORTED, "scb_cls_attention_bwd: Tk=%d too long", Tk);
   SCB_CHECK(kv_ld % 8 == 0 && kv_bs % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0 && head_dim % 8 == 0, SCB_EINVAL,
             "scb_cls_attention_bwd: kv strides / offsets / head_dim must be multiples of 8 elements");
   const unsigned grid = (unsigned)(batch * heads);
-  SCB_HD_SWITCH(head_dim, (cls_attention_bwd_kernel<HD_><<<grid, 128, smem, st>>>(q, (const uint16_t*)kv, kv_fmt, kv_ld, kv_bs, k_off, v_off, kv_len, Tk, heads, scale, probs, dctx, (uint16_t*)dkv, dkv_fmt, dq, batch)));
+  SCB_HD_SWITCH(head_dim, (cls_attention_bwd_kernel<HD_><<<grid, 128, smem, st>>>(q, (const uint16_t*)kv, kv_fmt, kv_ld, kv_bs, k_off, v_off, kv_len, Tk, heads, scale, probs, dctx, (uint16_t*)dkv, dkv_fmt, dq, batch, drop_p, rng_state, rng_site)));
   note_launch();
   SCB_LAUNCH_OK("cls_attention_bwd");
   return SCB_OK;

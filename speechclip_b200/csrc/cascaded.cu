@@ -100,7 +100,8 @@ __device__ __forceinline__ void mq_col_sums(const uint16_t* __restrict__ col, lo
 __global__ void __launch_bounds__(kMqThreads) mq_attention_fwd_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kv, int kv_fmt,
                                                                       long long kv_ld, long long kv_bs, int k_off, int v_off,
                                                                       const int* __restrict__ kv_len, int Tk, int heads, int hd, int nq,
-                                                                      float scale, float* __restrict__ probs, float* __restrict__ ctx) {
+                                                                      float scale, float* __restrict__ probs, float* __restrict__ ctx,
+                                                                      float drop_p, const long long* __restrict__ rng_state, int rng_site) {
   extern __shared__ __align__(16) float sm[];  // [nq][hd] q (scaled) | [nq][Tk] scores/probs | [8] scratch
   float* sq = sm;
   float* sc = sq + nq * hd;
@@ -127,9 +128,11 @@ __global__ void __launch_bounds__(kMqThreads) mq_attention_fwd_kernel(const floa
     sum = block_sum(sum, red);
     const float inv = 1.f / sum;
     float* po = probs + (((long long)b * heads + h) * nq + k) * Tk;
+    const DropoutRng rng(rng_state, rng_site, drop_p);
     for (int j = tid; j < Tk; j += kMqThreads) {
       const float pj = j < len ? sc[k * Tk + j] * inv : 0.f;
-      if (j < len) sc[k * Tk + j] = pj;
+      // attention dropout (nn.MultiheadAttention, train mode): probs keeps the UNdropped p, the context uses p_j * m_j
+      if (j < len) sc[k * Tk + j] = drop_p > 0.f ? pj * rng.scale((((unsigned long long)b * heads + h) * nq + k) * Tk + j) : pj;
       po[j] = pj;
     }
   }
@@ -150,13 +153,15 @@ __global__ void __launch_bounds__(kMqThreads) mq_attention_bwd_kernel(const floa
                                                                       const int* __restrict__ kv_len, int Tk, int heads, int hd, int nq,
                                                                       float scale, const float* __restrict__ probs,
                                                                       const float* __restrict__ dctx, uint16_t* __restrict__ dkv, int dkv_fmt,
-                                                                      float* __restrict__ dq_part) {
-  extern __shared__ __align__(16) float sm[];  // [nq][hd] q | [nq][hd] dctx | [nq][Tk] ds | [nq][Tk] p | [8]
+                                                                      float* __restrict__ dq_part, float drop_p,
+                                                                      const long long* __restrict__ rng_state, int rng_site) {
+  extern __shared__ __align__(16) float sm[];  // [nq][hd] q | [nq][hd] dctx | [nq][Tk] ds | [nq][Tk] p | [nq][Tk] p*m (dropout only) | [8]
   float* sq = sm;
   float* sdc = sq + nq * hd;
   float* sds = sdc + nq * hd;
   float* sp = sds + nq * Tk;
-  float* red = sp + nq * Tk;
+  float* spm = drop_p > 0.f ? sp + nq * Tk : sp;   // p_j * m_j: what multiplied V in the forward
+  float* red = spm + nq * Tk;
   const int tid = threadIdx.x;
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int D = heads * hd;
@@ -172,6 +177,16 @@ __global__ void __launch_bounds__(kMqThreads) mq_attention_bwd_kernel(const floa
   __syncthreads();
   mq_row_dots(base + v_off, kv_ld, kv_fmt, len, hd, nq, sdc, sds, Tk);   // dP[k][j] = <dctx_k, v_j>
   __syncthreads();
+  if (drop_p > 0.f) {   // regenerate the forward's mask: d ctx / d p_j = m_j v_j, and dV sees p_j m_j
+    const DropoutRng rng(rng_state, rng_site, drop_p);
+    for (int i = tid; i < nq * Tk; i += kMqThreads) {
+      const int k = i / Tk, j = i % Tk;
+      const float mj = j < len ? rng.scale((((unsigned long long)b * heads + h) * nq + k) * Tk + j) : 0.f;
+      sds[i] *= mj;
+      spm[i] = sp[i] * mj;
+    }
+    __syncthreads();
+  }
   for (int k = 0; k < nq; ++k) {
     float dot = 0.f;
     for (int j = tid; j < len; j += kMqThreads) dot += sp[k * Tk + j] * sds[k * Tk + j];
@@ -188,7 +203,7 @@ __global__ void __launch_bounds__(kMqThreads) mq_attention_bwd_kernel(const floa
     for (int i = 0; i < 8; ++i) gk[i] = gv[i] = 0.f;
     if (j < len) {
       for (int k = 0; k < nq; ++k) {
-        const float ds = sds[k * Tk + j], pj = sp[k * Tk + j];
+        const float ds = sds[k * Tk + j], pj = spm[k * Tk + j];
         const float4 q0 = *reinterpret_cast<const float4*>(sq + k * hd + c * 8), q1 = *reinterpret_cast<const float4*>(sq + k * hd + c * 8 + 4);
         const float4 g0 = *reinterpret_cast<const float4*>(sdc + k * hd + c * 8), g1 = *reinterpret_cast<const float4*>(sdc + k * hd + c * 8 + 4);
         gk[0] += ds * q0.x; gk[1] += ds * q0.y; gk[2] += ds * q0.z; gk[3] += ds * q0.w;
@@ -629,8 +644,10 @@ __global__ void split_tf32_kernel(const float* __restrict__ src, long long src_l
   } while (0)
 
 int mq_attention_fwd(const float* q, const void* kv, int kv_fmt, long long kv_ld, long long kv_bs, int k_off, int v_off, const int* kv_len,
-                     int batch, int heads, int head_dim, int nq, int Tk, float scale, float* probs, float* ctx, cudaStream_t st) {
+                     int batch, int heads, int head_dim, int nq, int Tk, float scale, float* probs, float* ctx, float drop_p,
+                     const long long* rng_state, int rng_site, cudaStream_t st) {
   SCB_CHECK(q && kv && probs && ctx, SCB_EINVAL, "scb_mq_attention_fwd: null operand");
+  SCB_CHECK(drop_p == 0.f || (drop_p > 0.f && drop_p < 1.f && rng_state), SCB_EINVAL, "scb_mq_attention_fwd: dropout needs p in [0,1) and an rng_state");
   SCB_CHECK(nq >= 1 && nq <= kMaxNQ, SCB_EUNSUPPORTED, "scb_mq_attention_fwd: nq=%d out of [1,%d]", nq, kMaxNQ);
   SCB_CHECK(head_dim % 8 == 0 && kv_ld % 8 == 0 && kv_bs % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0, SCB_EINVAL,
             "scb_mq_attention_fwd: head_dim / strides / offsets must be multiples of 8");
@@ -639,7 +656,7 @@ int mq_attention_fwd(const float* q, const void* kv, int kv_fmt, long long kv_ld
   SCB_CHECK(smem <= 200 * 1024, SCB_EUNSUPPORTED, "scb_mq_attention_fwd: nq*Tk + nq*head_dim too large");
   SCB_SMEM_ATTR(mq_attention_fwd_kernel, smem);
   mq_attention_fwd_kernel<<<batch * heads, kMqThreads, smem, st>>>(q, (const uint16_t*)kv, kv_fmt, kv_ld, kv_bs, k_off, v_off, kv_len, Tk, heads,
-                                                           head_dim, nq, scale, probs, ctx);
+                                                           head_dim, nq, scale, probs, ctx, drop_p, rng_state, rng_site);
   note_launch();
   SCB_LAUNCH_OK("mq_attention_fwd");
   return SCB_OK;
@@ -647,17 +664,18 @@ int mq_attention_fwd(const float* q, const void* kv, int kv_fmt, long long kv_ld
 
 int mq_attention_bwd(const float* q, const void* kv, int kv_fmt, long long kv_ld, long long kv_bs, int k_off, int v_off, const int* kv_len,
                      int batch, int heads, int head_dim, int nq, int Tk, float scale, const float* probs, const float* dctx, void* dkv,
-                     int dkv_fmt, float* dq, cudaStream_t st) {
+                     int dkv_fmt, float* dq, float drop_p, const long long* rng_state, int rng_site, cudaStream_t st) {
   SCB_CHECK(q && kv && probs && dctx && dkv && dq, SCB_EINVAL, "scb_mq_attention_bwd: null operand");
+  SCB_CHECK(drop_p == 0.f || (drop_p > 0.f && drop_p < 1.f && rng_state), SCB_EINVAL, "scb_mq_attention_bwd: dropout needs p in [0,1) and an rng_state");
   SCB_CHECK(nq >= 1 && nq <= kMaxNQ, SCB_EUNSUPPORTED, "scb_mq_attention_bwd: nq=%d out of [1,%d]", nq, kMaxNQ);
   SCB_CHECK(head_dim % 8 == 0 && kv_ld % 8 == 0 && kv_bs % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0, SCB_EINVAL,
             "scb_mq_attention_bwd: head_dim / strides / offsets must be multiples of 8");
   if (batch == 0) return SCB_OK;
-  const size_t smem = (size_t)(2 * nq * Tk + 2 * nq * head_dim + 8) * sizeof(float);
+  const size_t smem = (size_t)((drop_p > 0.f ? 3 : 2) * nq * Tk + 2 * nq * head_dim + 8) * sizeof(float);
   SCB_CHECK(smem <= 200 * 1024, SCB_EUNSUPPORTED, "scb_mq_attention_bwd: nq*Tk + nq*head_dim too large");
   SCB_SMEM_ATTR(mq_attention_bwd_kernel, smem);
   mq_attention_bwd_kernel<<<batch * heads, kMqThreads, smem, st>>>(q, (const uint16_t*)kv, kv_fmt, kv_ld, kv_bs, k_off, v_off, kv_len, Tk, heads,
-                                                           head_dim, nq, scale, probs, dctx, (uint16_t*)dkv, dkv_fmt, dq);
+                                                           head_dim, nq, scale, probs, dctx, (uint16_t*)dkv, dkv_fmt, dq, drop_p, rng_state, rng_site);
   note_launch();
   SCB_LAUNCH_OK("mq_attention_bwd");
   return SCB_OK;

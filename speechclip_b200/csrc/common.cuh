@@ -178,6 +178,43 @@ __device__ __forceinline__ uint64_t quick_gelu_x2(uint64_t x) {
 }
 __device__ __forceinline__ float quick_gelu(float x) { return x * rcp_approx(1.0f + ex2_approx(-1.702f * 1.4426950408889634f * x)); }
 
+// ---------------------------------------------------------------- counter-based RNG for dropout
+// Philox-4x32-10 (Salmon et al., SC'11).  A dropout decision is a pure function of (seed, step, site, element index), so the
+// backward pass regenerates the forward's mask instead of storing it, and a test can materialise the same mask for the oracle.
+//   rng_state (device int64[2]) = {seed, step};  counter = (index >> 2 [64 bit], site, step), key = seed, lane = index & 3.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+struct DropoutRng {
+  uint2 key;
+  uint32_t site, step, threshold;
+  float keep_scale;
+  // p in [0, 1): an element is dropped when its 32-bit draw is below p * 2^32; survivors are scaled by 1 / (1 - p)
+  __device__ __forceinline__ DropoutRng(const long long* state, int site_, float p) {
+    const unsigned long long seed = state ? (unsigned long long)state[0] : 0ull;   // NULL: caller runs with p = 0 and never draws
+    key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    step = state ? (uint32_t)state[1] : 0u;
+    site = (uint32_t)site_;
+    threshold = (uint32_t)fminf(p * 4294967296.f, 4294967040.f);
+    keep_scale = 1.f / (1.f - p);
+  }
+  __device__ __forceinline__ float scale(unsigned long long idx) const {
+    const unsigned long long blk = idx >> 2;
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), site, step), key);
+    const uint32_t lane = (uint32_t)idx & 3u;
+    const uint32_t u = lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
+    return u >= threshold ? keep_scale : 0.f;
+  }
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

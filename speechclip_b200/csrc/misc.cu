@@ -139,6 +139,21 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const float* __restrict__
   }
 }
 
+// ---- dropout of the trainable branch (TransformerModels.py:55-75,110-117: nn.TransformerEncoderLayer / nn.MultiheadAttention, p = 0.1)
+__global__ void rng_advance_kernel(long long* state) { state[1] += 1; }
+
+__global__ void __launch_bounds__(256) dropout_mask_kernel(const long long* __restrict__ state, int site, float p, float* __restrict__ mask,
+                                                           long long n) {
+  const DropoutRng rng(state, site, p);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) mask[i] = rng.scale(i);
+}
+
+__global__ void __launch_bounds__(256) dropout_rows_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float p,
+                                                           const long long* __restrict__ state, int site) {
+  const DropoutRng rng(state, site, p);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = x[i] * rng.scale(i);
+}
+
 // out[c] = beta*out[c] + sum_r in[r*ld + c].  Block = 32 columns x 8 row lanes; rows strided over blockIdx.y; atomics across y.
 template <typename T>
 __global__ void __launch_bounds__(256) column_sum_kernel(const T* __restrict__ in, long long ld, long long rows, int cols,
@@ -272,6 +287,38 @@ int gelu_bwd(const float* dy, const float* pre, float* dx, long long n, cudaStre
   gelu_bwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(dy, pre, dx, n);
   note_launch();
   SCB_LAUNCH_OK("gelu_bwd");
+  return SCB_OK;
+}
+
+int rng_advance(long long* state, cudaStream_t st) {
+  SCB_CHECK(state, SCB_EINVAL, "scb_rng_advance: null state");
+  rng_advance_kernel<<<1, 1, 0, st>>>(state);
+  note_launch();
+  SCB_LAUNCH_OK("rng_advance");
+  return SCB_OK;
+}
+
+int dropout_mask(const long long* state, int site, float p, float* mask, long long n, cudaStream_t st) {
+  SCB_CHECK(state && mask, SCB_EINVAL, "scb_dropout_mask: null operand");
+  SCB_CHECK(p >= 0.f && p < 1.f, SCB_EINVAL, "scb_dropout_mask: p = %f outside [0, 1)", p);
+  if (n == 0) return SCB_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
+  dropout_mask_kernel<<<(unsigned)blocks, 256, 0, st>>>(state, site, p, mask, n);
+  note_launch();
+  SCB_LAUNCH_OK("dropout_mask");
+  return SCB_OK;
+}
+
+int dropout_rows(const float* x, float* y, long long n, float p, const long long* state, int site, cudaStream_t st) {
+  SCB_CHECK(x && y && state, SCB_EINVAL, "scb_dropout_rows: null operand");
+  SCB_CHECK(p >= 0.f && p < 1.f, SCB_EINVAL, "scb_dropout_rows: p = %f outside [0, 1)", p);
+  if (n == 0) return SCB_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
+  dropout_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, n, p, state, site);
+  note_launch();
+  SCB_LAUNCH_OK("dropout_rows");
   return SCB_OK;
 }
 

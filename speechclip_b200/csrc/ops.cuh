@@ -22,10 +22,10 @@ int attention_fwd_tc(const void* q, const void* k, const void* v, void* o, int f
                      int head_dim, int Tq, int Tk, float scale, int causal, cudaStream_t st);
 int cls_attention_fwd(const float* q, const void* kv, int kv_fmt, long long kv_ld, long long kv_bs, int k_off, int v_off,
                       const int* kv_len, int batch, int heads, int head_dim, int Tk, float scale, float* probs, float* ctx32, void* ctx16,
-                      int ctx16_fmt, cudaStream_t st);
+                      int ctx16_fmt, float drop_p, const long long* rng_state, int rng_site, cudaStream_t st);
 int cls_attention_bwd(const float* q, const void* kv, int kv_fmt, long long kv_ld, long long kv_bs, int k_off, int v_off,
                       const int* kv_len, int batch, int heads, int head_dim, int Tk, float scale, const float* probs, const float* dctx,
-                      void* dkv, int dkv_fmt, float* dq, cudaStream_t st);
+                      void* dkv, int dkv_fmt, float* dq, float drop_p, const long long* rng_state, int rng_site, cudaStream_t st);
 // frontend.cu
 long long conv0_scratch_bytes(int batch);
 int conv0_groupnorm_gelu(const float* wav, long long wav_ld, int batch, int n_samples, const float* w, const float* conv_bias,
@@ -67,15 +67,19 @@ int wav_prepare(const float* wav, long long wav_ld, int batch, const int* crop_o
 int rows_bias_act(const float* x, long long x_ld, const float* bias, const float* res, long long res_ld, int act, float* pre, float* y,
                   long long y_ld, long long rows, int d, cudaStream_t st);
 int gelu_bwd(const float* dy, const float* pre, float* dx, long long n, cudaStream_t st);
+int rng_advance(long long* state, cudaStream_t st);
+int dropout_mask(const long long* state, int site, float p, float* mask, long long n, cudaStream_t st);
+int dropout_rows(const float* x, float* y, long long n, float p, const long long* state, int site, cudaStream_t st);
 int column_sum(const void* in, int in_dtype, long long ld, long long rows, int cols, float* out, float beta, cudaStream_t st);
 int retrieval_rank(const float* score, long long ld, int rows, int cols, const long long* cand_ids, const long long* answers, int* rank,
                    int* top1, cudaStream_t st);
 // cascaded.cu
 int mq_attention_fwd(const float* q, const void* kv, int kv_fmt, long long kv_ld, long long kv_bs, int k_off, int v_off, const int* kv_len,
-                     int batch, int heads, int head_dim, int nq, int Tk, float scale, float* probs, float* ctx, cudaStream_t st);
+                     int batch, int heads, int head_dim, int nq, int Tk, float scale, float* probs, float* ctx, float drop_p,
+                     const long long* rng_state, int rng_site, cudaStream_t st);
 int mq_attention_bwd(const float* q, const void* kv, int kv_fmt, long long kv_ld, long long kv_bs, int k_off, int v_off, const int* kv_len,
                      int batch, int heads, int head_dim, int nq, int Tk, float scale, const float* probs, const float* dctx, void* dkv,
-                     int dkv_fmt, float* dq, cudaStream_t st);
+                     int dkv_fmt, float* dq, float drop_p, const long long* rng_state, int rng_site, cudaStream_t st);
 int batchnorm_fwd(const float* x, float* y, const float* gamma, const float* beta, float* running_mean, float* running_var,
                   float* save_mean, float* save_rstd, int B, int NK, int D, float eps, float momentum, int training, cudaStream_t st);
 int batchnorm_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_rstd, float* dx,

@@ -27,6 +27,27 @@ def workspace(device) -> Workspace:
     return ws
 
 
+class DropoutState:
+    """Device-side RNG state of a module's train-mode dropout: int64 [seed, step] (scb_dropout_mask).  The seed follows
+    ``torch.initial_seed()`` (Lightning's ``seed_everything``) and the process rank; ``advance`` bumps ``step`` with a kernel,
+    so a captured CUDA graph draws fresh masks at every replay."""
+
+    def __init__(self):
+        self.state = None
+
+    def get(self, device) -> torch.Tensor:
+        if self.state is None or self.state.device != torch.device(device):
+            rank = torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
+            seed = (torch.initial_seed() * 0x9E3779B1 + rank * 0x85EBCA77 + 0x5bd1e995) % (2 ** 62)
+            self.state = torch.tensor([seed, 0], dtype=torch.int64).to(device)
+        return self.state
+
+    def advance(self, device) -> torch.Tensor:
+        st = self.get(device)
+        ops.rng_advance(st)
+        return st
+
+
 def _require_cuda(t: torch.Tensor, what: str):
     if not t.is_cuda:
         raise RuntimeError(f"{what}: CUDA tensor required — the sm_100a extension is the only implementation of this path "
@@ -129,11 +150,12 @@ class ParallelBranchFn(torch.autograd.Function):
     """kwClip.py:1076-1108 on the [CLS] row (see speechclip_b200/head.py)."""
 
     @staticmethod
-    def forward(ctx, audio_feat, kv_len, head: ParallelHead, arena, *params):
+    def forward(ctx, audio_feat, kv_len, head: ParallelHead, arena, drop, *params):
+        """drop: None (eval) or (p, rng_state int64[2]) — train-mode dropout of the encoder layer."""
         _require_cuda(audio_feat, "KW_ParallelBranch")
         p = dict(zip(PARAM_ORDER, params))
         audio_feat = audio_feat.contiguous()
-        out, saved = head.cls_forward(workspace(audio_feat.device), p, audio_feat.detach(), kv_len)
+        out, saved = head.cls_forward(workspace(audio_feat.device), p, audio_feat.detach(), kv_len, drop)
         ctx.head, ctx.arena, ctx.saved, ctx.params = head, arena, saved, params
         ctx.need_dfeat = audio_feat.requires_grad
         return out
@@ -146,13 +168,13 @@ class ParallelBranchFn(torch.autograd.Function):
         g = {name: _grad_like(t, arena, buf) for name, t in p.items()}
         dfeat = head.cls_backward(workspace(dout.device), p, ctx.saved, dout.contiguous(), g, need_dfeat=ctx.need_dfeat)
         ctx.saved = None
-        return (dfeat, None, None, None) + tuple(g[name] if p[name].requires_grad else None for name in PARAM_ORDER)
+        return (dfeat, None, None, None, None) + tuple(g[name] if p[name].requires_grad else None for name in PARAM_ORDER)
 
 
 # ---------------------------------------------------------------------------------------------------- cascaded branch
 class CascadedBranchFn(torch.autograd.Function):
     """kwClip.py:857-916 end to end (see speechclip_b200/cascaded.py).  ``rt`` carries the frozen pieces and switches:
-    dict(vocab, text, bn_buffers, temp, sot, eot, training, need_grad).  Returns (text feature, keywords, cos, idx, stats); only the
+    dict(vocab, text, bn_buffers, temp, sot, eot, training, need_grad[, drop = (p, rng_state)]).  Returns (text feature, keywords, cos, idx, stats); only the
     first output is differentiable."""
 
     @staticmethod
@@ -164,7 +186,7 @@ class CascadedBranchFn(torch.autograd.Function):
         need_grad = rt["need_grad"] and (audio_feat.requires_grad or any(t.requires_grad for t in params))
         feat, keywords, cos, idx, stats, saved = head.forward(
             workspace(audio_feat.device), p, audio_feat.detach(), kv_len, rt["bn_buffers"], rt["vocab"], rt["text"], rt["temp"],
-            rt["sot"], rt["eot"], rt["training"], need_grad)
+            rt["sot"], rt["eot"], rt["training"], need_grad, rt.get("drop"))
         ctx.head, ctx.arena, ctx.saved, ctx.params, ctx.rt = head, arena, saved, params, rt
         ctx.need_dfeat = audio_feat.requires_grad
         ctx.mark_non_differentiable(keywords, cos, idx, stats)

@@ -83,6 +83,11 @@ def dgrad(ws: Workspace, tag: str, dy: torch.Tensor, w: torch.Tensor, out: torch
     return ops.sgemm(dy, w.t(), out, beta=0.0 if residual is None else 1.0)
 
 
+# dropout sites of the branch layer (nn.TransformerEncoderLayer in train mode, TransformerModels.py:55-75): the element index of a
+# site is the flat index into the tensor named here, restricted to the [CLS] row the head evaluates
+SITE_ATTN, SITE_DROPOUT1, SITE_FFN, SITE_DROPOUT2 = 0, 1, 2, 3   # probs [B, heads, T+1] | out-proj [B, d] | GELU(linear1) [B, ffn] | linear2 [B, d]
+
+
 class ParallelHead:
     """Stateless executor; ``p`` maps the names in PARAM_ORDER to live fp32 CUDA tensors."""
 
@@ -100,9 +105,14 @@ class ParallelHead:
         ops.broadcast_row(p["cls"].view(-1), None, src, Tk * d, B, d)
         return src
 
-    def cls_forward(self, ws: Workspace, p: Dict[str, torch.Tensor], audio_feat: torch.Tensor, kv_len: torch.Tensor):
-        """audio_feat fp32 [B, T, d] contiguous; kv_len int32 [B] = audio_len + 1.  -> (out fp32 [B, out_dim], saved)."""
+    def cls_forward(self, ws: Workspace, p: Dict[str, torch.Tensor], audio_feat: torch.Tensor, kv_len: torch.Tensor, drop=None):
+        """audio_feat fp32 [B, T, d] contiguous; kv_len int32 [B] = audio_len + 1.  -> (out fp32 [B, out_dim], saved).
+        drop = (p, rng_state) in train mode: the layer's four dropouts (attention weights, after out-proj, after the
+        activation, after linear2) act on the [CLS] row; the masks are functions of rng_state (scb_dropout_mask), which the
+        backward pass reads again from ``saved``."""
         B, T, d = audio_feat.shape
+        dp, rng = (float(drop[0]), drop[1].clone()) if drop is not None and drop[0] > 0 else (0.0, None)
+        site = (lambda k: (dp, rng, k)) if rng is not None else (lambda k: None)
         Tk, hd, heads, dev = T + 1, self.hd, self.heads, audio_feat.device
         M = B * Tk
         w_in, b_in = p[L0 + "self_attn.in_proj_weight"], p[L0 + "self_attn.in_proj_bias"]
@@ -117,9 +127,11 @@ class ParallelHead:
         ops.rows_bias_act(q, b_in[:d], None, 0, ops.ACT_NONE, None, q)
         probs = _new((B, heads, Tk), dev)
         ctx = _new((B, d), dev)
-        ops.cls_attention_fwd(q, kv, 0, d, kv_len, heads, hd, hd ** -0.5, probs, ctx)
+        ops.cls_attention_fwd(q, kv, 0, d, kv_len, heads, hd, hd ** -0.5, probs, ctx, drop=site(SITE_ATTN))
         t1 = _new((B, d), dev)
         linear(ctx, p[L0 + "self_attn.out_proj.weight"], t1, bias=p[L0 + "self_attn.out_proj.bias"])
+        if rng is not None:
+            ops.dropout_rows(t1, t1, site(SITE_DROPOUT1))
         ops.rows_bias_act(t1, None, cls, 0, ops.ACT_NONE, None, t1)  # + [CLS] residual (one row, broadcast)
         x1, st1 = _new((B, d), dev), _new((B, 2), dev)
         ops.layernorm(t1, p[L0 + "norm1.weight"], p[L0 + "norm1.bias"], y32=x1, stats=st1, eps=self.eps)
@@ -128,7 +140,13 @@ class ParallelHead:
         linear(x1, p[L0 + "linear1.weight"], h_pre, bias=p[L0 + "linear1.bias"])
         ops.rows_bias_act(h_pre, None, None, 0, ops.ACT_GELU, None, h)
         t2 = _new((B, d), dev)
-        linear(h, p[L0 + "linear2.weight"], t2, bias=p[L0 + "linear2.bias"], residual=x1)
+        if rng is not None:
+            ops.dropout_rows(h, h, site(SITE_FFN))
+            linear(h, p[L0 + "linear2.weight"], t2, bias=p[L0 + "linear2.bias"])
+            ops.dropout_rows(t2, t2, site(SITE_DROPOUT2))
+            ops.rows_bias_act(t2, None, x1, x1.stride(0), ops.ACT_NONE, None, t2)
+        else:
+            linear(h, p[L0 + "linear2.weight"], t2, bias=p[L0 + "linear2.bias"], residual=x1)
         x2, st2 = _new((B, d), dev), _new((B, 2), dev)
         ops.layernorm(t2, p[L0 + "norm2.weight"], p[L0 + "norm2.bias"], y32=x2, stats=st2, eps=self.eps)
         x3, st3 = _new((B, d), dev), _new((B, 2), dev)
@@ -139,7 +157,7 @@ class ParallelHead:
         else:
             out = x3
         saved = dict(B=B, T=T, src=src, kv=kv, q=q, probs=probs, ctx=ctx, t1=t1, x1=x1, st1=st1, h_pre=h_pre, h=h, t2=t2, x2=x2,
-                     st2=st2, st3=st3, x3=x3, kv_len=kv_len)
+                     st2=st2, st3=st3, x3=x3, kv_len=kv_len, drop=(dp, rng))
         return out, saved
 
     # ------------------------------------------------------------------------------------------------- backward
@@ -154,6 +172,8 @@ class ParallelHead:
         w_in = p[L0 + "self_attn.in_proj_weight"]
         cls = p["cls"].view(1, d)
         dcls = g["cls"].view(1, d)
+        dp, rng = s.get("drop", (0.0, None))
+        site = (lambda k: (dp, rng, k)) if rng is not None else (lambda k: None)
         if self.need_projection:
             wp = p["linear_proj.weight"]
             wgrad(ws, "hp", dout, s["x3"], g["linear_proj.weight"])
@@ -171,30 +191,35 @@ class ParallelHead:
                           g["self_att.model.norm.bias"])
         dt2 = _new((B, d), dev)
         ops.layernorm_bwd(dx2, s["t2"], s["st2"], p[L0 + "norm2.weight"], dt2, g[L0 + "norm2.weight"], g[L0 + "norm2.bias"])
-        # MLP
-        wgrad(ws, "h2", dt2, s["h"], g[L0 + "linear2.weight"])
-        ops.column_sum(dt2, g[L0 + "linear2.bias"])
+        # MLP (train mode: the gradient of the linear2 path passes dropout2's mask, that of the activation dropout's; the
+        # residual path of dt2 does not)
+        dy2 = ops.dropout_rows(dt2, _new((B, d), dev), site(SITE_DROPOUT2)) if rng is not None else dt2
+        wgrad(ws, "h2", dy2, s["h"], g[L0 + "linear2.weight"])
+        ops.column_sum(dy2, g[L0 + "linear2.bias"])
         dh = _new(s["h"].shape, dev)
-        dgrad(ws, "h2", dt2, p[L0 + "linear2.weight"], dh)
+        dgrad(ws, "h2", dy2, p[L0 + "linear2.weight"], dh)
+        if rng is not None:
+            ops.dropout_rows(dh, dh, site(SITE_FFN))
         ops.gelu_bwd(dh, s["h_pre"], dh)
         wgrad(ws, "h1", dh, s["x1"], g[L0 + "linear1.weight"])
         ops.column_sum(dh, g[L0 + "linear1.bias"])
         dgrad(ws, "h1", dh, p[L0 + "linear1.weight"], dt2, residual=dt2)  # dx1 = dt2 (residual path) + dh W1
         dt1 = _new((B, d), dev)
         ops.layernorm_bwd(dt2, s["t1"], s["st1"], p[L0 + "norm1.weight"], dt1, g[L0 + "norm1.weight"], g[L0 + "norm1.bias"])
-        # attention out-proj (+ residual = [CLS])
-        wgrad(ws, "ho", dt1, s["ctx"], g[L0 + "self_attn.out_proj.weight"])
-        ops.column_sum(dt1, g[L0 + "self_attn.out_proj.bias"])
+        # attention out-proj (+ residual = [CLS]; dropout1 sits on the out-proj path only)
+        dy1 = ops.dropout_rows(dt1, _new((B, d), dev), site(SITE_DROPOUT1)) if rng is not None else dt1
+        wgrad(ws, "ho", dy1, s["ctx"], g[L0 + "self_attn.out_proj.weight"])
+        ops.column_sum(dy1, g[L0 + "self_attn.out_proj.bias"])
         ops.column_sum(dt1, dcls)
         dctx = _new((B, d), dev)
-        dgrad(ws, "ho", dt1, p[L0 + "self_attn.out_proj.weight"], dctx)
+        dgrad(ws, "ho", dy1, p[L0 + "self_attn.out_proj.weight"], dctx)
         # single-query attention
         kv = s["kv"]
         dkv = ws.view("head_dkv", (B, Tk, 2 * d), BF)
         g_w, g_b = g[L0 + "self_attn.in_proj_weight"], g[L0 + "self_attn.in_proj_bias"]
         dq = g_b[:d]
         dq.zero_()
-        ops.cls_attention_bwd(s["q"], kv, 0, d, s["kv_len"], heads, hd, hd ** -0.5, s["probs"], dctx, dkv, dq)
+        ops.cls_attention_bwd(s["q"], kv, 0, d, s["kv_len"], heads, hd, hd ** -0.5, s["probs"], dctx, dkv, dq, drop=site(SITE_ATTN))
         ops.sgemm(dq.view(d, 1), cls.view(d, 1), g_w[:d])            # dWq = dq (x) cls
         ops.sgemm(dq.view(1, d), w_in[:d].t(), dcls, beta=1.0)        # dcls += Wq^T dq
         ops.column_sum(dkv.view(M, 2 * d), g_b[d:])

@@ -139,17 +139,41 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     return out
 
 
-def cls_attention_fwd(q, kv, k_off, v_off, kv_len, heads, hd, scale, probs, ctx32):
+def cls_attention_fwd(q, kv, k_off, v_off, kv_len, heads, hd, scale, probs, ctx32, drop=None):
+    """drop = (p, rng_state int64[2] on the device, site) for train-mode attention dropout, or None."""
     B, Tk = kv.shape[0], kv.shape[1]
+    p, state, site = drop if drop is not None else (0.0, None, 0)
     _call("scb_cls_attention_fwd", _p(q), _p(kv), _DT[kv.dtype], kv.stride(1), kv.stride(0), k_off, v_off, _p(kv_len), B, heads, hd,
-          Tk, scale, _p(probs), _p(ctx32), None, 0)
+          Tk, scale, _p(probs), _p(ctx32), None, 0, p, _p(state), site)
 
 
-def cls_attention_bwd(q, kv, k_off, v_off, kv_len, heads, hd, scale, probs, dctx, dkv, dq):
+def cls_attention_bwd(q, kv, k_off, v_off, kv_len, heads, hd, scale, probs, dctx, dkv, dq, drop=None):
     B, Tk = kv.shape[0], kv.shape[1]
     assert dkv.shape == kv.shape and dkv.stride() == kv.stride()
+    p, state, site = drop if drop is not None else (0.0, None, 0)
     _call("scb_cls_attention_bwd", _p(q), _p(kv), _DT[kv.dtype], kv.stride(1), kv.stride(0), k_off, v_off, _p(kv_len), B, heads, hd,
-          Tk, scale, _p(probs), _p(dctx), _p(dkv), _DT[dkv.dtype], _p(dq))
+          Tk, scale, _p(probs), _p(dctx), _p(dkv), _DT[dkv.dtype], _p(dq), p, _p(state), site)
+
+
+# ------------------------------------------------------------------------------------------------ dropout (trainable branch)
+def rng_advance(state):
+    assert state.dtype == torch.int64 and state.numel() == 2
+    _call("scb_rng_advance", _p(state))
+
+
+def dropout_mask(state, site, p, n):
+    """The multiplicative mask (0 or 1/(1-p), fp32 [n]) of dropout site ``site`` at the RNG state ``state``."""
+    mask = torch.empty(n, device=state.device, dtype=torch.float32)
+    _call("scb_dropout_mask", _p(state), site, p, _p(mask), n)
+    return mask
+
+
+def dropout_rows(x, y, drop):
+    """y = x * mask(drop) elementwise over a contiguous fp32 tensor (in place allowed); drop = (p, rng_state, site)."""
+    p, state, site = drop
+    assert x.is_contiguous() and y.is_contiguous() and x.dtype == y.dtype == torch.float32
+    _call("scb_dropout_rows", _p(x), _p(y), x.numel(), p, _p(state), site)
+    return y
 
 
 # ------------------------------------------------------------------------------------------------ front end
@@ -299,19 +323,22 @@ def retrieval_rank(score, cand_ids, answers, rank, top1):
 
 
 # ------------------------------------------------------------------------------------------------ cascaded branch
-def mq_attention_fwd(q, kv, k_off, v_off, kv_len, heads, hd, scale, probs, ctx32):
-    """q fp32 [NQ, heads*hd]; kv 16-bit [B, Tk, ld]; probs fp32 [B, heads, NQ, Tk]; ctx32 fp32 [B, NQ, heads*hd]."""
+def mq_attention_fwd(q, kv, k_off, v_off, kv_len, heads, hd, scale, probs, ctx32, drop=None):
+    """q fp32 [NQ, heads*hd]; kv 16-bit [B, Tk, ld]; probs fp32 [B, heads, NQ, Tk]; ctx32 fp32 [B, NQ, heads*hd];
+    drop = (p, rng_state, site) for train-mode attention dropout, or None."""
     B, Tk = kv.shape[0], kv.shape[1]
+    p, state, site = drop if drop is not None else (0.0, None, 0)
     _call("scb_mq_attention_fwd", _p(q), _p(kv), _DT[kv.dtype], kv.stride(1), kv.stride(0), k_off, v_off, _p(kv_len), B, heads, hd,
-          q.shape[0], Tk, scale, _p(probs), _p(ctx32))
+          q.shape[0], Tk, scale, _p(probs), _p(ctx32), p, _p(state), site)
 
 
-def mq_attention_bwd(q, kv, k_off, v_off, kv_len, heads, hd, scale, probs, dctx, dkv, dq_part):
+def mq_attention_bwd(q, kv, k_off, v_off, kv_len, heads, hd, scale, probs, dctx, dkv, dq_part, drop=None):
     """dq_part fp32 [B, NQ * heads*hd]: per-utterance contributions to dq (sum over dim 0 with column_sum)."""
     B, Tk = kv.shape[0], kv.shape[1]
     assert dkv.shape == kv.shape and dkv.stride() == kv.stride() and dq_part.numel() == B * q.numel()
+    p, state, site = drop if drop is not None else (0.0, None, 0)
     _call("scb_mq_attention_bwd", _p(q), _p(kv), _DT[kv.dtype], kv.stride(1), kv.stride(0), k_off, v_off, _p(kv_len), B, heads, hd,
-          q.shape[0], Tk, scale, _p(probs), _p(dctx), _p(dkv), _DT[dkv.dtype], _p(dq_part))
+          q.shape[0], Tk, scale, _p(probs), _p(dctx), _p(dkv), _DT[dkv.dtype], _p(dq_part), p, _p(state), site)
 
 
 def batchnorm_fwd(x, y, gamma, beta, running_mean, running_var, save_mean, save_rstd, eps, momentum, training):

@@ -158,6 +158,63 @@ def part1_reference():
          code_perplexity=r["code_perplexity"], prob_perplexity=r["prob_perplexity"], ent_per_t=r["ent_per_t"],
          diversity_loss=r["diversity_loss"], subword_prob_eval=r_eval["subword_prob"])
 
+    # ---- TRAIN mode of the two branch encoders (dropout 0.1: spchclp_p.yaml:27, TransformerModels.py:55-75,110-117).  torch draws
+    #      its dropout masks from its own generator inside library code, which no other implementation can replay; so the masks are
+    #      drawn HERE (from g) and injected into the reference's own modules by temporarily replacing the two library entry points
+    #      that consume randomness (F.dropout; F.scaled_dot_product_attention, evaluated as softmax(qk^T/sqrt(d) + mask) * m @ v —
+    #      checked bit-exact against torch's CPU kernel, which applies the mask the same way).  Fixtures hold inputs, masks, outputs.
+    import torch.nn.functional as F
+    drawn = []
+
+    def draw(shape, p):
+        m = (torch.rand(shape, generator=g) >= p).float() / (1.0 - p)
+        drawn.append(m)
+        return m
+
+    def patched_dropout(x, p=0.5, training=True, inplace=False):
+        return x * draw(x.shape, p) if training and p > 0 else x
+
+    def patched_sdpa(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=False, scale=None, **kw):
+        sc = q @ k.transpose(-1, -2) * (q.shape[-1] ** -0.5 if scale is None else scale)
+        if attn_mask is not None:
+            sc = sc.masked_fill(attn_mask, float("-inf")) if attn_mask.dtype == torch.bool else sc + attn_mask
+        pr = torch.softmax(sc, -1)
+        if dropout_p > 0:
+            pr = pr * draw(pr.shape, dropout_p)
+        return pr @ v
+
+    orig = (F.dropout, F.scaled_dot_product_attention)
+    F.dropout, F.scaled_dot_product_attention = patched_dropout, patched_sdpa
+    try:
+        torch.manual_seed(17)
+        enc = tm.TransformerEncoder(n_layers=1, d_model=64, nhead=8, dim_feedforward=128, dropout=0.1, activation="gelu",
+                                    layer_norm_eps=1e-5, batch_first=True, norm_first=False)
+        for p in enc.parameters():
+            p.data.add_(0.05 * torch.randn(p.shape, generator=g))
+        enc.train()
+        src = torch.randn(4, 11, 64, generator=g)
+        kpm = du.get_keypadding_mask(11, torch.tensor([11, 4, 8, 10]))
+        drawn.clear()
+        out = enc(src, kpm)
+        assert [tuple(m.shape) for m in drawn] == [(4, 8, 11, 11), (4, 11, 64), (4, 11, 128), (4, 11, 64)], [m.shape for m in drawn]
+        save("ref_branch_train_dropout.npz", src=src, kpm=kpm, out=out, m_attn=drawn[0], m_dropout1=drawn[1], m_ffn=drawn[2],
+             m_dropout2=drawn[3], **{"sd." + k: v for k, v in enc.state_dict().items()})
+
+        torch.manual_seed(19)
+        mha = tm.MultiheadAttentionAndNorm(d_model=64, nhead=1, dropout=0.1)
+        for p in mha.parameters():
+            p.data.add_(0.05 * torch.randn(p.shape, generator=g))
+        mha.train()
+        src = torch.randn(3, 12, 64, generator=g)
+        kpm = du.get_keypadding_mask(12, torch.tensor([12, 6, 9]))
+        drawn.clear()
+        out = mha(src, kpm)
+        assert [tuple(m.shape) for m in drawn] == [(3, 12, 12)], [m.shape for m in drawn]   # [B * heads, L, L]
+        save("ref_mha_norm_train_dropout.npz", src=src, kpm=kpm, out=out, m_attn=drawn[0].view(3, 1, 12, 12),
+             **{"sd." + k: v for k, v in mha.state_dict().items()})
+    finally:
+        F.dropout, F.scaled_dot_product_attention = orig
+
     # ---- random_crop_max_length semantics (audio_transforms.py:5-23): shapes only (np.random offset)
     at = load_ref("data/audio_transforms.py", "ref_at")
     assert at.random_crop_max_length(torch.arange(10), 4, 10).shape == (4,)

@@ -336,7 +336,9 @@ def _check_branch_grads(mine: dict, ref: dict, tol: float, prefix: str = "") -> 
     return n
 
 
-def _branch_pair(size, K=8, seed=0, vocab_npy=None):
+def _branch_pair(size, K=8, seed=0, vocab_npy=None, dropout=0.0):
+    """dropout = 0: these tests run the model in train mode for the BatchNorm batch statistics / straight-through path and
+    compare with the oracle's deterministic arithmetic; the train-mode attention dropout has its own test (test_dropout_gpu.py)."""
     from avssl.base import OrderedNamespace
     from avssl.model import KWClip_GeneralTransformer
     from oracle import clip as oc
@@ -345,6 +347,7 @@ def _branch_pair(size, K=8, seed=0, vocab_npy=None):
     from speechclip_b200.configs import cascaded_config
     cfg = cascaded_config(size, vocab_npy)
     cfg["model_settings"]["cascaded_branch"]["keyword"]["number"] = K
+    cfg["model_settings"]["cascaded_branch"]["transformer_args"]["dropout"] = dropout
     torch.manual_seed(seed)
     model = KWClip_GeneralTransformer(OrderedNamespace(cfg))
     with torch.no_grad():

@@ -109,3 +109,33 @@ def test_cascaded_pieces_match_reference(golden):
     for k in ("code_perplexity", "prob_perplexity", "ent_per_t", "diversity_loss"):
         assert torch.allclose(r[k], T(z[k]), atol=1e-5), k
     assert torch.equal(osc.simple_vector_quantizer(T(z["cos"]), 0.1, False)["subword_prob"], T(z["subword_prob_eval"]))
+
+
+def test_train_mode_dropout_matches_reference_modules(golden):
+    """The reference's TransformerEncoder / MultiheadAttentionAndNorm in TRAIN mode (dropout 0.1) with the dropout masks injected
+    (make_golden.py): the oracle evaluated with the same masks reproduces every row; with only the row-0 / keyword-row masks (what
+    the CUDA path consumes) it reproduces those rows."""
+    z = golden("ref_branch_train_dropout.npz")
+    enc = osc.BranchEncoder(n_layers=1, d_model=64, nhead=8, dim_feedforward=128).eval()
+    enc.load_state_dict({k[3:]: T(z[k]) for k in z.files if k.startswith("sd.")})
+    full = dict(attn=T(z["m_attn"]), dropout1=T(z["m_dropout1"]), ffn=T(z["m_ffn"]), dropout2=T(z["m_dropout2"]))
+    assert 0.05 < (full["attn"] == 0).float().mean() < 0.15 and abs(full["ffn"].max().item() - 1 / 0.9) < 1e-6
+    with torch.no_grad():
+        out = enc(T(z["src"]), T(z["kpm"]), masks=full)
+        row0 = enc(T(z["src"]), T(z["kpm"]), masks=dict(attn=full["attn"][:, :, 0], dropout1=full["dropout1"][:, 0],
+                                                        ffn=full["ffn"][:, 0], dropout2=full["dropout2"][:, 0]))
+        plain = enc(T(z["src"]), T(z["kpm"]))
+    valid = ~T(z["kpm"])
+    assert torch.allclose(out[valid], T(z["out"])[valid], atol=2e-5)
+    assert torch.allclose(row0[:, 0], T(z["out"])[:, 0], atol=2e-5)
+    assert (plain[:, 0] - T(z["out"])[:, 0]).abs().max() > 0.05   # the masks matter
+
+    z = golden("ref_mha_norm_train_dropout.npz")
+    m = osc.AttentionAndNorm(64, 1).eval()
+    m.load_state_dict({k[3:]: T(z[k]) for k in z.files if k.startswith("sd.")})
+    with torch.no_grad():
+        out = m(T(z["src"]), T(z["kpm"]), T(z["m_attn"]))
+        rows = m(T(z["src"]), T(z["kpm"]), T(z["m_attn"])[:, :, :3])
+    valid = ~T(z["kpm"])
+    assert torch.allclose(out[valid], T(z["out"])[valid], atol=2e-5)
+    assert torch.allclose(rows[:, :3], T(z["out"])[:, :3], atol=2e-5)
