@@ -2,22 +2,38 @@
 // frozen towers (HuBERT 319 frames, CLIP ViT 50 / 257 tokens, CLIP text 77 tokens).
 //
 // One persistent CTA per SM walks (utterance, head) items.  Per item the producer thread TMA-loads K [NK x 64], V [NK x 64]
-// and all Q tiles [128 x 64] straight out of the fused QKV activation (three 3-D tensor maps), 128B-swizzled.  Per 128-query
-// tile:
-//   MMA thread      S = Q K^T           tcgen05.mma 128 x NK x 64 (two instructions of N = NK/2 when NK > 256) -> TMEM cols [0, NK)
-//   16 softmax warps row max / exp2 / row sum straight from TMEM (tcgen05.ld; the whole key axis of a row is resident, so there is
-//                   no online rescaling), key-padding / causal masks, P (fp16/bf16) -> shared memory in the K-major swizzled
-//                   layout the next MMA reads as its A operand
-//   MMA thread      O = P V             tcgen05.mma 128 x 64 x NK, V read as the MN-major B operand directly from its row-major
-//                   tile (no transposed copy of V anywhere) -> TMEM cols [320, 384)
-//   16 softmax warps O / rowsum -> 16-bit -> global
-// The S MMAs of tile i+1 are issued right behind the PV MMAs of tile i, so they run while the softmax warps drain O.
+// and all Q tiles [128 x 64] straight out of the fused QKV activation (three 3-D tensor maps), 128B-swizzled.
+//
+// A 128-query tile is processed as TWO key halves of H = NK / 2 columns, each with its own S accumulator in TMEM
+// (columns [0, H) and [H, 2H)); O lives in columns [320, 384):
+//   MMA thread       S_h = Q K_h^T        tcgen05.mma 128 x H x 64                          -> s_full[h]
+//   16 softmax warps two passes over their H/4-column slice of S_h straight from TMEM (tcgen05.ld): row max (exchanged between the
+//                    4 warps of a lane quarter), then exp2, 16-bit P into the K-major 128B-swizzled shared-memory operand and
+//                    row sums                                                                  -> s_free[h], p_full[h]
+//   MMA thread       O (+)= P_h V_h        tcgen05.mma 128 x 64 x H, V as the MN-major B operand (no transposed copy of V)
+// so that while the softmax warps work on one half the tensor pipe computes S of the other half / of the next query tile and the
+// P V of the previous half: the softmax warps never wait for an MMA in steady state, and the kernel runs at the rate of its
+// exponentials (MUFU) instead of the sum of all phases (round 1: one 320-column S, every phase serial, 17 % tensor pipe).
+// The two halves share one running row maximum: half 1 keeps the maximum of half 0 unless its own maximum is more than 2^8 above
+// it (P <= 256 is harmless in 16 bits; softmax is shift-invariant), in which case — rare — the warps rescale O and the partial
+// row sum in place (tcgen05.ld / st) before P V of half 1 is issued.
+// O of a tile is drained (divided by the row sum, packed, stored) inside the NEXT tile, also across items.  Query quarters
+// (32 rows) that lie entirely beyond Tq skip all softmax work (T = 319: 2 of the 12 quarters of an item).
 #include <cstdlib>
 
 #include "common.cuh"
 #include "ops.cuh"
 
 namespace scb {
+#ifdef SCB_ATTN_TRACE
+__device__ long long g_attn_trace[64 * 16];
+#define ATTN_TRACE(cond, tile, slot) do { if ((cond) && blockIdx.x == 0 && (tile) < 64 && (tile) >= 0) g_attn_trace[(tile) * 16 + (slot)] = clock64(); } while (0)
+extern "C" int scb_debug_attn_trace(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_attn_trace, sizeof(g_attn_trace));
+}
+#else
+#define ATTN_TRACE(cond, tile, slot) do { } while (0)
+#endif
 namespace {
 
 constexpr int HD = 64;
@@ -25,13 +41,17 @@ constexpr int BQ = 128;
 constexpr int MAX_NK = 320;
 constexpr int MAX_QT = 3;                       // query tiles resident per item (Tq <= 384)
 constexpr int O_COL = 320;                      // TMEM column of the O accumulator
-constexpr int kSoftmaxWarps = 16;                // 4 per TMEM lane quarter, each owning NK/4 key columns
-constexpr int kThreads = (2 + kSoftmaxWarps) * 32;  // warp 0: TMA producer (+ TMEM alloc), warp 1: MMA issuer, then the softmax warps
+constexpr int kSoftmaxWarps = 16;                // 4 per TMEM lane quarter, each owning H/4 key columns of a half
+constexpr int kCtrlWarps = 2;                    // warp 0: TMA producer (+ TMEM alloc), warp 1: MMA issuer; then the softmax warps
+constexpr int kThreads = (kCtrlWarps + kSoftmaxWarps) * 32;
 constexpr int K_BYTES = MAX_NK * 128;           // 40 KB
 constexpr int V_BYTES = MAX_NK * 128;           // 40 KB (5 key blocks of 64 rows x 128 B)
 constexpr int Q_BYTES = MAX_QT * BQ * 128;      // 48 KB
-constexpr int P_BYTES = (MAX_NK / 64) * BQ * 128;  // 80 KB (5 k-blocks of [128 x 64])
-constexpr int SMEM_BYTES = K_BYTES + V_BYTES + Q_BYTES + P_BYTES + 2 * 4 * BQ * 4 + 256 + 1024;  // 256: mbarriers + TMEM slot
+constexpr int P_BYTES = (MAX_NK / 64) * BQ * 128;  // 80 KB (5 k-blocks of [128 x 64]; half h owns the keys [h H, h H + H))
+constexpr int RED_FLOATS = 3 * 4 * BQ;          // row max of half 0 / half 1, row sums: [4 column parts][128 rows] each
+constexpr int COLD_BYTES = kSoftmaxWarps * 32 * 16;   // per softmax thread: the pending tile's (item, tile, 1 / row sum)
+constexpr int SMEM_BYTES = K_BYTES + V_BYTES + Q_BYTES + P_BYTES + RED_FLOATS * 4 + COLD_BYTES + 256 + 1024;  // 256: mbarriers + TMEM slot
+constexpr float kRescaleLog2 = 8.f;             // half 1 keeps half 0's row maximum unless its own is > 2^8 above it
 
 struct AttnTcParams {
   uint16_t* o;
@@ -42,34 +62,62 @@ struct AttnTcParams {
   int causal, bf16;
 };
 
+// Bounded wait WITHOUT a printf: a call in the hot loops makes the compiler keep loop state in stack slots, and with the shared-memory
+// carve-out at its maximum the L1 behind the stack is ~28 KB — the reloads then cost L2 latency on the MMA issue path.
+__device__ __forceinline__ bool try_wait_hint(uint64_t* bar, uint32_t parity) {
+  // suspend-time hint (ns): the hardware parks the thread until the phase completes (or the hint expires) instead of returning
+  // early — a parked waiter takes no issue slots from the softmax warps that share its scheduler
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
+  if (try_wait_hint(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!try_wait_hint(bar, parity))
+    if (clock64() - t0 > 8000000000LL) __trap();
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 // kind::f16 instruction descriptor with an MN-major B operand (bit 16)
 __device__ __forceinline__ uint32_t idesc_pv(int fmt) { return umma_idesc_f16(BQ, HD, fmt) | (1u << 16); }
 
-template <bool BF16>
+// NCH = NK / 64 (1..5): compile-time so that every S slice has a static register footprint
+template <bool BF16, int NCH>
 __global__ void __launch_bounds__(kThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                     const AttnTcParams p) {
+  constexpr int NK = NCH * 64;
+  constexpr int H = NK / 2;       // keys per half: 32 .. 160 (multiple of 32)
+  constexpr int CW = H / 4;       // key columns of a half owned by one softmax warp: 8 .. 40
+  constexpr int NCK = CW / 8;     // ... in chunks of 8 (one 16-byte unit of a P row)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sK = smem;
   uint8_t* sV = sK + K_BYTES;
   uint8_t* sQ = sV + V_BYTES;
   uint8_t* sP = sQ + Q_BYTES;
-  float* red_max = reinterpret_cast<float*>(sP + P_BYTES);  // [4 column parts][128 rows]
-  float* red_sum = red_max + 4 * BQ;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(red_sum + 4 * BQ);
-  uint64_t* kq_full = bars + 0;    // K and every Q tile of the item have landed
-  uint64_t* item_empty = bars + 1; // every PV MMA of the item has retired: V may be overwritten
-  uint64_t* s_full = bars + 2;
-  uint64_t* p_full = bars + 3;
-  uint64_t* o_full = bars + 4;
-  uint64_t* o_empty = bars + 5;
-  uint64_t* v_full = bars + 6;     // V of the item has landed
-  uint64_t* kq_empty = bars + 7;   // every S MMA of the item has retired: K and Q may be overwritten
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* red_max = reinterpret_cast<float*>(sP + P_BYTES);  // [half][4 column parts][128 rows]
+  float* red_sum = red_max + 2 * 4 * BQ;                    // [4 column parts][128 rows]
+  int4* cold = reinterpret_cast<int4*>(red_sum + 4 * BQ);   // [softmax thread]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cold + kSoftmaxWarps * 32);
+  uint64_t* kq_full = bars + 0;     // K and every Q tile of the item have landed
+  uint64_t* kq_empty = bars + 1;    // every S MMA of the item has retired: K and Q may be overwritten
+  uint64_t* v_full = bars + 2;      // V of the item has landed
+  uint64_t* item_empty = bars + 3;  // every PV MMA of the item has retired: V may be overwritten
+  uint64_t* s_full = bars + 4;      // [2] S_h of the tile is in TMEM
+  uint64_t* s_free = bars + 6;      // [2] every softmax warp holds its slice of S_h in registers
+  uint64_t* p_full = bars + 8;      // [2] P_h of the tile is in shared memory
+  uint64_t* pv_done = bars + 10;    // [2] P_h V_h (and every earlier MMA) has retired; pv_done[1] = O of the tile is complete
+  uint64_t* o_empty = bars + 12;    // O of the tile has been read out of TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -79,12 +127,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
   if (warp == 1 && lane == 0) {
     mbar_init(kq_full, 1);
-    mbar_init(item_empty, 1);
-    mbar_init(v_full, 1);
     mbar_init(kq_empty, 1);
-    mbar_init(s_full, 1);
-    mbar_init(p_full, kSoftmaxWarps);
-    mbar_init(o_full, 1);
+    mbar_init(v_full, 1);
+    mbar_init(item_empty, 1);
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(s_full + h, 1);
+      mbar_init(s_free + h, kSoftmaxWarps);
+      mbar_init(p_full + h, kSoftmaxWarps);
+      mbar_init(pv_done + h, 1);
+    }
     mbar_init(o_empty, kSoftmaxWarps);
     mbar_fence_init();
   }
@@ -96,202 +147,287 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   griddep_wait();               // programmatic dependent launch: global memory is only touched below
   griddep_launch_dependents();
   const int n_items = p.batch * p.heads;
-  const int NK = p.NK;
-  const int nkb = NK / 64;  // key blocks of the PV contraction
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ producer
-    // K and Q of the NEXT item are loaded as soon as the last S = Q K^T of the current item has retired (kq_empty), i.e. while
-    // its last query tile is still in the softmax / P V / drain phases; V follows once the last P V has retired (item_empty).
-    // Without this split every item started with a ~2 us load bubble (14 % of the kernel at 319 frames).
+    // K and Q of the NEXT item are loaded as soon as the last S of the current item has retired (kq_empty), i.e. while its last
+    // query tile is still in the softmax / P V phases; V follows once the last P V has retired (item_empty).
     uint32_t ph = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / p.heads, h = item % p.heads;
-      mbar_wait(kq_empty, ph ^ 1u);
+      wait_bar(kq_empty, ph ^ 1u);
       mbar_expect_tx(kq_full, (uint32_t)(NK * 128 + p.n_qt * BQ * 128));
-      if (NK <= 256) {
-        tma_load_3d(sK, &tmK, kq_full, h * HD, 0, b);
-      } else {
-        tma_load_3d(sK, &tmK, kq_full, h * HD, 0, b);
-        tma_load_3d(sK + (NK / 2) * 128, &tmK, kq_full, h * HD, NK / 2, b);
-      }
+      tma_load_3d(sK, &tmK, kq_full, h * HD, 0, b);
+      tma_load_3d(sK + H * 128, &tmK, kq_full, h * HD, H, b);
       for (int qt = 0; qt < p.n_qt; ++qt) tma_load_3d(sQ + qt * BQ * 128, &tmQ, kq_full, h * HD, qt * BQ, b);
-      mbar_wait(item_empty, ph ^ 1u);
+      wait_bar(item_empty, ph ^ 1u);
       mbar_expect_tx(v_full, (uint32_t)(NK * 128));
-      for (int kb = 0; kb < nkb; ++kb) tma_load_3d(sV + kb * 64 * 128, &tmV, v_full, h * HD, kb * 64, b);
+      for (int kb = 0; kb < NCH; ++kb) tma_load_3d(sV + kb * 64 * 128, &tmV, v_full, h * HD, kb * 64, b);
       ph ^= 1u;
     }
   } else if (warp == 1 && lane == 0) {
     // ------------------------------------------------------------------ MMA issuer
     const int fmt = BF16 ? 1 : 0;
-    const int n1 = NK <= 256 ? NK : NK / 2;
-    const uint32_t idesc_s = umma_idesc_f16(BQ, n1, fmt);
+    const uint32_t idesc_s = umma_idesc_f16(BQ, H, fmt);
     const uint32_t idesc_o = idesc_pv(fmt);
-    uint32_t ph_item = 0, ph_p = 0, ph_oe = 0;
-    auto issue_s = [&](int qt) {
+    // S_h of query tile qt: 4 k-steps of 16 over the head dimension
+    auto issue_s = [&](int qt, int h) __attribute__((always_inline)) {
       const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(sQ + qt * BQ * 128));
+      const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(sK + h * H * 128));
 #pragma unroll
-      for (int k = 0; k < HD / 16; ++k) {
-        tc_mma_f16(tmem_base, a_desc + (uint64_t)(2 * k), umma_desc_kmajor_sw128(smem_u32(sK)) + (uint64_t)(2 * k), idesc_s, (uint32_t)(k != 0));
-        if (NK > 256)
-          tc_mma_f16(tmem_base + (uint32_t)n1, a_desc + (uint64_t)(2 * k),
-                     umma_desc_kmajor_sw128(smem_u32(sK + n1 * 128)) + (uint64_t)(2 * k), idesc_s, (uint32_t)(k != 0));
-      }
-      tc_commit(s_full);
+      for (int k = 0; k < HD / 16; ++k)
+        tc_mma_f16(tmem_base + (uint32_t)(h * H), a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc_s, (uint32_t)(k != 0));
+      tc_commit(s_full + h);
     };
-    // S(0) of an item is issued as soon as its K / Q have landed AND the S columns are free, i.e. right behind the P V MMAs of
-    // the previous item's last tile (same slot S(qt+1) takes inside an item).
-    bool first = true;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      if (first) {
-        mbar_wait(kq_full, ph_item);
-        tc_fence_after();
-        issue_s(0);
-        if (p.n_qt == 1) tc_commit(kq_empty);
-        first = false;
+    // O (+)= P_h V_h: H / 16 k-steps of 16 keys; key kk lives in block kk / 64 of P (K-major, 32 B per step inside the 128-byte
+    // row) and of V (MN-major: 16 rows per step)
+    auto issue_pv = [&](int h) __attribute__((always_inline)) {
+#pragma unroll 1
+      for (int j = 0; j < H / 16; ++j) {
+        const int kk = h * H + j * 16;
+        const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(sP + (kk >> 6) * (BQ * 128))) + (uint64_t)(((kk & 63) * 2) >> 4);
+        const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(sV + (kk >> 6) * (64 * 128))) + (uint64_t)(((kk & 63) >> 4) * ((16 * 128) >> 4));
+        tc_mma_f16(tmem_base + O_COL, a_desc, b_desc, idesc_o, (uint32_t)((h | j) != 0));
       }
+      tc_commit(pv_done + h);
+    };
+    uint32_t ph_item = 0, pt = 0;  // parity of the item / of the query tile (every per-tile barrier completes once per tile)
+    int trace_tile = 0;
+    (void)trace_tile;
+    wait_bar(kq_full, ph_item);
+    tc_fence_after();
+    issue_s(0, 0);
+    issue_s(0, 1);
+    if (p.n_qt == 1) tc_commit(kq_empty);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const bool has_next = item + (int)gridDim.x < n_items;
       for (int qt = 0; qt < p.n_qt; ++qt) {
-        mbar_wait(p_full, ph_p);       // P(qt) is in shared memory and S(qt) has been read
-        ph_p ^= 1u;
+        const bool same_item = qt + 1 < p.n_qt;
+        const bool next = same_item || has_next;
+        const int nqt = same_item ? qt + 1 : 0;
+        // ---- half 0: P V, then S of the next tile's half 0 into the accumulator the softmax warps released long ago
+        wait_bar(p_full + 0, pt);
+        if (qt == 0) wait_bar(v_full, ph_item);
+        wait_bar(o_empty, pt ^ 1u);   // O of the previous tile has been read out of TMEM
         tc_fence_after();
-        // S of the next tile goes first: the softmax warps start on it while the PV MMAs below are still running
-        if (qt + 1 < p.n_qt) {
-          issue_s(qt + 1);
-          if (qt + 2 == p.n_qt) tc_commit(kq_empty);  // the item's last S: K / Q are free once it retires
-        }
-        if (qt == 0) {
-          mbar_wait(v_full, ph_item);
+        issue_pv(0);
+        ATTN_TRACE(true, trace_tile, 10);
+        if (next) {
+          wait_bar(s_free + 0, pt);
+          if (!same_item) wait_bar(kq_full, ph_item ^ 1u);
           tc_fence_after();
+          issue_s(nqt, 0);
         }
-        mbar_wait(o_empty, ph_oe ^ 1u);  // O of the previous tile has been read out of TMEM
-        ph_oe ^= 1u;
+        ATTN_TRACE(true, trace_tile, 11);
+        // ---- half 1
+        wait_bar(p_full + 1, pt);
         tc_fence_after();
-        for (int kb = 0; kb < nkb; ++kb) {
-          const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(sP + kb * BQ * 128));
-          const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(sV + kb * 64 * 128));
-#pragma unroll
-          for (int k = 0; k < 4; ++k)  // 16 keys per instruction: A advances 32 B inside its row, B (MN-major) by 16 rows
-            tc_mma_f16(tmem_base + O_COL, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(k * ((16 * 128) >> 4)), idesc_o,
-                       (uint32_t)((kb | k) != 0));
+        issue_pv(1);
+        ATTN_TRACE(true, trace_tile, 12);
+        if (!same_item) tc_commit(item_empty);
+        if (next) {
+          wait_bar(s_free + 1, pt);
+          tc_fence_after();
+          issue_s(nqt, 1);
+          if (same_item ? (qt + 2 == p.n_qt) : (p.n_qt == 1)) tc_commit(kq_empty);  // the item's last S: K / Q are free once it retires
         }
-        tc_commit(o_full);
-        if (qt + 1 == p.n_qt) {
-          tc_commit(item_empty);
-          if (has_next) {  // next item's first S behind this item's last P V
-            mbar_wait(kq_full, ph_item ^ 1u);
-            tc_fence_after();
-            issue_s(0);
-            if (p.n_qt == 1) tc_commit(kq_empty);
-          }
-        }
+        ATTN_TRACE(true, trace_tile, 13);
+        ++trace_tile;
+        pt ^= 1u;
       }
       ph_item ^= 1u;
     }
-  } else if (warp >= 2) {
+  } else if (warp >= kCtrlWarps) {
     // ------------------------------------------------------------------ softmax + output
-    const int q = warp & 3, part = (warp - 2) >> 2;  // TMEM lane quarter; which quarter of the key columns
-    const int r = q * 32 + lane;                       // row of the query tile owned by this lane
-    const int part_cols = NK / 4;                      // multiple of 16
-    const int nchunk = part_cols / 16;
+    const int q = warp & 3, part = (warp - kCtrlWarps) >> 2;  // TMEM lane quarter; which quarter of a half's key columns
+    const int r = q * 32 + lane;                                // row of the query tile owned by this lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t ph_s = 0, ph_o = 0;
-    // O / rowsum of one query tile -> global (its P V MMAs run while the softmax of the NEXT tile is in flight)
-    auto drain_o = [&](int b, int h, int row_g, float inv) {
-      mbar_wait(o_full, ph_o);
-      ph_o ^= 1u;
+    const float c2 = p.scale_log2;
+    uint8_t* const p_row = sP + r * 128;   // this lane's row inside a P block
+    const int rx = r & 7;                   // its 128B-swizzle phase
+    uint32_t pt = 0;
+    int trace_tile = 0;
+    (void)trace_tile;
+    const bool tr = (warp == kCtrlWarps + 2 || warp == kCtrlWarps + 3) && lane == 0;   // (q = 0, part = 0) and (q = 1, part = 0)
+    const int trace_off = warp == kCtrlWarps + 3 ? 32 : 0;
+    (void)trace_off;
+    (void)tr;
+    // the tile whose O is still to be drained: always the previous tile of this CTA, possibly of the previous item.  Its (item,
+    // tile, 1 / row sum) live in SHARED memory, not in registers: the softmax loop is at the register limit, and what the
+    // compiler spills goes to the stack, whose L1 is almost entirely carved out for shared memory here (an L2 round trip in
+    // front of a barrier wait); a 16-byte LDS per tile is cheap and predictable.
+    int4* my_cold = cold + (threadIdx.x - kCtrlWarps * 32);
+    bool have_pend = false;
+    // O / rowsum of the previous query tile -> global (its last P V was issued when the previous tile's P_1 was complete)
+    auto drain_o = [&]() __attribute__((always_inline)) {
+      wait_bar(pv_done + 1, pt ^ 1u);
       tc_fence_after();
+      ATTN_TRACE(tr, trace_tile + trace_off, 4);
+      const int4 pc = *my_cold;
+      const int pend_item = pc.x, pend_qt = pc.y;
+      const float pend_inv = __int_as_float(pc.z);
+      const bool pend_live = pend_qt * BQ + q * 32 < p.Tq;
       uint32_t ov[16];
-      tmem_ld_32x16(lane_addr + (uint32_t)(O_COL + part * 16), ov);
-      tmem_ld_wait();
+      if (pend_live) {
+        tmem_ld_32x16(lane_addr + (uint32_t)(O_COL + part * 16), ov);
+        tmem_ld_wait();
+      }
+      ATTN_TRACE(tr, trace_tile + trace_off, 14);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
-      if (row_g < p.Tq) {
-        uint16_t* dst = p.o + (long long)b * p.o_bs + (long long)row_g * p.o_ld + h * HD + part * 16;
+      const int pend_row = pend_qt * BQ + r;
+      if (pend_live && pend_row < p.Tq) {
+        const int pb = pend_item / p.heads, phd = pend_item % p.heads;
+        uint16_t* dst = p.o + (long long)pb * p.o_bs + (long long)pend_row * p.o_ld + phd * HD + part * 16;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           uint4 u;
           uint32_t* uu = reinterpret_cast<uint32_t*>(&u);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            uu[i] = H16<BF16 ? SCB_BF16 : SCB_F16>::pack(__uint_as_float(ov[t * 8 + 2 * i]) * inv, __uint_as_float(ov[t * 8 + 2 * i + 1]) * inv);
+            uu[i] = H16<BF16 ? SCB_BF16 : SCB_F16>::pack(__uint_as_float(ov[t * 8 + 2 * i]) * pend_inv, __uint_as_float(ov[t * 8 + 2 * i + 1]) * pend_inv);
           *reinterpret_cast<uint4*>(dst + t * 8) = u;
         }
       }
     };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int b = item / p.heads, h = item % p.heads;
-      const int kvl = p.kv_len ? min(p.kv_len[b], p.Tk) : p.Tk;
-      float inv_prev = 0.f;
+      const int kvl = p.kv_len ? min(p.kv_len[item / p.heads], p.Tk) : p.Tk;
       for (int qt = 0; qt < p.n_qt; ++qt) {
         const int row_g = qt * BQ + r;      // query index
+        const bool live = qt * BQ + q * 32 < p.Tq;  // warp-uniform (and uniform over the 4 warps of this lane quarter)
         const int key_hi = p.causal ? min(kvl, row_g + 1) : kvl;  // keys [0, key_hi) are visible to this row
-        mbar_wait(s_full, ph_s);
-        ph_s ^= 1u;
-        tc_fence_after();
-        // ---- pass 1: row max over this warp's quarter of the keys (masking only on chunks that straddle key_hi).
-        //      (Keeping the 80 S values of a lane in registers instead of re-reading TMEM in pass 2 was measured SLOWER:
-        //      408 vs 310 us per B=256 layer call — the kernel is bound by barrier / MMA / MUFU latency chains, not by TMEM
-        //      read bandwidth: ncu shows tensor pipe 14 %, XU 28 %, LDTM 3 % busy.)
-        float mx = -INFINITY;
-        for (int c = 0; c < nchunk; ++c) {
-          uint32_t v[16];
-          const int key0 = part * part_cols + c * 16;
-          tmem_ld_32x16(lane_addr + (uint32_t)key0, v);
-          tmem_ld_wait();
-          if (__all_sync(0xffffffffu, key0 + 16 <= key_hi)) {
+        float m_run = -INFINITY, l_run = 0.f;   // running row maximum (raw score units) / this warp's partial row sum
+        ATTN_TRACE(tr, trace_tile + trace_off, 7);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        for (int hf = 0; hf < 2; ++hf) {
+          wait_bar(s_full + hf, pt);
+          tc_fence_after();
+          ATTN_TRACE(tr, trace_tile + trace_off, hf * 5 + 0);
+          const int col0 = hf * H + part * CW;   // first key column of this warp's slice (= TMEM column of S)
+          if (live) {
+            // ---- pass 1: row max of this half straight from TMEM (nothing is kept: holding the slice in registers from here to
+            //      the exp pass pushes the loop over the register limit, and the spills / rematerialisation cost more than the
+            //      second TMEM read), masking only on chunks that straddle key_hi; exchanged between the 4 warps of the quarter
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c0 = 0; c0 < NCK; c0 += 2) {
+              uint32_t v[2][8];
+              tmem_ld_32x8(lane_addr + (uint32_t)(col0 + c0 * 8), v[0]);
+              if (c0 + 1 < NCK) tmem_ld_32x8(lane_addr + (uint32_t)(col0 + c0 * 8 + 8), v[1]);
+              tmem_ld_wait();
+#pragma unroll
+              for (int cc = 0; cc < 2; ++cc) {
+                if (c0 + cc < NCK) {
+                  const int key0 = col0 + (c0 + cc) * 8;
+                  if (__all_sync(0xffffffffu, key0 + 8 <= key_hi)) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) mx = fmaxf(mx, __uint_as_float(v[cc][i]));
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                      if (key0 + i < key_hi) mx = fmaxf(mx, __uint_as_float(v[cc][i]));
+                  }
+                }
+              }
+            }
+            float* rm = red_max + hf * 4 * BQ;
+            rm[part * BQ + r] = mx;
+            named_bar_sync(1 + q, 128);
+            mx = fmaxf(fmaxf(rm[r], rm[BQ + r]), fmaxf(rm[2 * BQ + r], rm[3 * BQ + r]));
+            ATTN_TRACE(tr, trace_tile + trace_off, hf * 5 + 1);
+            if (hf == 0) {
+              m_run = mx;
+              // ---- the previous tile's O (the P V MMAs that produced it also read the P rows the stores below overwrite)
+              if (have_pend) drain_o();
+              ATTN_TRACE(tr, trace_tile + trace_off, 2);
+            } else {
+              // ---- half 1 keeps the running maximum unless its own is more than 2^8 above it; otherwise (rare) O and the partial
+              //      row sum are rescaled in place.  The 4 warps of a quarter see the same rows, so they all take the same branch.
+              const bool need = mx * c2 > m_run * c2 + kRescaleLog2;
+              if (__any_sync(0xffffffffu, need)) {
+                wait_bar(pv_done + 0, pt);      // P_0 V_0 of THIS tile has retired: O holds it
+                tc_fence_after();
+                const float alpha = need ? ex2_approx((m_run - mx) * c2) : 1.f;   // m_run = -inf (no visible key in half 0): 0
+                uint32_t ov[16];
+                tmem_ld_32x16(lane_addr + (uint32_t)(O_COL + part * 16), ov);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+                tmem_st_32x16(lane_addr + (uint32_t)(O_COL + part * 16), ov);
+                tmem_st_wait();
+                tc_fence_before();
+                l_run *= alpha;
+                if (need) m_run = mx;
+              }
+            }
+            // ---- pass 2: p = 2^((s - m) * scale), row sum, P -> shared memory (K-major, 128B-swizzled A operand of P V).  A row
+            //      of P is 5 blocks of 8 16-byte units; this warp's chunk c is unit u0 + c of the row.
+            const float m_off = (m_run == -INFINITY) ? 0.f : -m_run * c2;
+            const int u0 = col0 >> 3;
+#pragma unroll
+            for (int c0 = 0; c0 < NCK; c0 += 2) {
+              uint32_t v[2][8];
+              tmem_ld_32x8(lane_addr + (uint32_t)(col0 + c0 * 8), v[0]);
+              if (c0 + 1 < NCK) tmem_ld_32x8(lane_addr + (uint32_t)(col0 + c0 * 8 + 8), v[1]);
+              tmem_ld_wait();
+#pragma unroll
+              for (int cc = 0; cc < 2; ++cc) {
+                if (c0 + cc < NCK) {
+                  const int key0 = col0 + (c0 + cc) * 8;
+                  float pv[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(v[cc][i]), c2, m_off));
+                  if (!__all_sync(0xffffffffu, key0 + 8 <= key_hi)) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                      if (key0 + i >= key_hi) pv[i] = 0.f;
+                  }
+                  uint32_t pk[4];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    l_run += pv[2 * i] + pv[2 * i + 1];
+                    pk[i] = H16<BF16 ? SCB_BF16 : SCB_F16>::pack(pv[2 * i], pv[2 * i + 1]);
+                  }
+                  const int u = u0 + c0 + cc;
+                  *reinterpret_cast<uint4*>(p_row + ((u >> 3) << 14) + (((u & 7) ^ rx) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+              }
+            }
+            tc_fence_before();
+            fence_proxy_async();  // generic-proxy writes of P become visible to the tensor core's async-proxy reads
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(s_free + hf);   // S_hf has been read for the last time: the MMA thread may overwrite the accumulator
+              mbar_arrive(p_full + hf);
+            }
+            ATTN_TRACE(tr, trace_tile + trace_off, hf * 5 + 3);
           } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (key0 + i < key_hi) mx = fmaxf(mx, __uint_as_float(v[i]));
+            // rows beyond Tq: nothing to compute (the MMA rows they would feed are never read); keep the barrier protocol going
+            if (hf == 0 && have_pend) drain_o();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(s_free + hf);
+              mbar_arrive(p_full + hf);
+            }
           }
         }
-        red_max[part * BQ + r] = mx;
-        named_bar_sync(1 + q, 128);
-        mx = fmaxf(fmaxf(red_max[r], red_max[BQ + r]), fmaxf(red_max[2 * BQ + r], red_max[3 * BQ + r]));
-        const float m_off = (mx == -INFINITY) ? 0.f : -mx * p.scale_log2;
-        // ---- the previous tile's O: its PV MMAs read P, which pass 2 below overwrites
-        if (qt > 0) drain_o(b, h, row_g - BQ, inv_prev);
-        // ---- pass 2: p = 2^(s*scale - m*scale), row sum, P -> shared memory (K-major, 128B-swizzled A operand)
-        float sum = 0.f;
-        for (int c = 0; c < nchunk; ++c) {
-          uint32_t v[16];
-          const int key0 = part * part_cols + c * 16;
-          tmem_ld_32x16(lane_addr + (uint32_t)key0, v);
-          tmem_ld_wait();
-          float pv[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, m_off));
-          if (!__all_sync(0xffffffffu, key0 + 16 <= key_hi)) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (key0 + i >= key_hi) pv[i] = 0.f;
-          }
-          uint32_t pk[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            sum += pv[2 * i] + pv[2 * i + 1];
-            pk[i] = H16<BF16 ? SCB_BF16 : SCB_F16>::pack(pv[2 * i], pv[2 * i + 1]);
-          }
-          uint8_t* prow = sP + (key0 >> 6) * (BQ * 128) + r * 128;
-          const int c8 = (key0 & 63) >> 3;  // first 16-byte unit of this chunk inside the 128-byte row (0, 2, 4 or 6)
-          *reinterpret_cast<uint4*>(prow + ((c8 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(prow + (((c8 + 1) ^ (r & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        float inv = 0.f;
+        if (live) {
+          red_sum[part * BQ + r] = l_run;
+          named_bar_sync(1 + q, 128);
+          const float sum = (red_sum[r] + red_sum[BQ + r]) + (red_sum[2 * BQ + r] + red_sum[3 * BQ + r]);
+          inv = sum > 0.f ? 1.f / sum : 0.f;
         }
-        red_sum[part * BQ + r] = sum;
-        tc_fence_before();
-        fence_proxy_async();  // generic-proxy writes of P become visible to the tensor core's async-proxy reads
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
-        named_bar_sync(1 + q, 128);
-        sum = (red_sum[r] + red_sum[BQ + r]) + (red_sum[2 * BQ + r] + red_sum[3 * BQ + r]);
-        inv_prev = sum > 0.f ? 1.f / sum : 0.f;
+        ATTN_TRACE(tr, trace_tile + trace_off, 9);
+        ++trace_tile;
+        *my_cold = make_int4(item, qt, __float_as_int(inv), 0);
+        have_pend = true;
+        pt ^= 1u;
       }
-      drain_o(b, h, (p.n_qt - 1) * BQ + r, inv_prev);
     }
+    if (have_pend) drain_o();
   }
 
   tc_fence_before();
@@ -335,22 +471,31 @@ int attention_fwd_tc(const void* q, const void* k, const void* v, void* o, int f
   const uint64_t sq[2] = {(uint64_t)q_ld * 2, (uint64_t)q_bs * 2}, sk[2] = {(uint64_t)k_ld * 2, (uint64_t)k_bs * 2},
                  sv[2] = {(uint64_t)v_ld * 2, (uint64_t)v_bs * 2};
   const uint32_t bq[3] = {64, BQ, 1};
-  const uint32_t bk[3] = {64, (uint32_t)(p.NK <= 256 ? p.NK : p.NK / 2), 1};
+  const uint32_t bk[3] = {64, (uint32_t)(p.NK / 2), 1};   // K is loaded as the two key halves
   const uint32_t bv[3] = {64, 64, 1};
   int e = make_tmap(&tmQ, q, 2, 3, dq, sq, bq, 1);
   if (!e) e = make_tmap(&tmK, k, 2, 3, dk, sk, bk, 1);
   if (!e) e = make_tmap(&tmV, v, 2, 3, dk, sv, bv, 1);
   if (e) return e;
-  static bool configured = false;
-  if (!configured) {
-    SCB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    SCB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    configured = true;
-  }
   const int items = batch * heads;
   const int grid = items < num_sms() ? items : num_sms();
-  if (p.bf16) SCB_CUDA(launch_pdl(attention_tc_kernel<true>, dim3((unsigned)grid), kThreads, SMEM_BYTES, st, tmQ, tmK, tmV, p));
-  else SCB_CUDA(launch_pdl(attention_tc_kernel<false>, dim3((unsigned)grid), kThreads, SMEM_BYTES, st, tmQ, tmK, tmV, p));
+  static bool configured[2][6] = {};   // per kernel instantiation: the opt-in to > 48 KB of dynamic shared memory
+  const int nch = p.NK / 64;
+  auto launch = [&](auto kernel) -> int {
+    if (!configured[p.bf16][nch]) {
+      SCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      configured[p.bf16][nch] = true;
+    }
+    SCB_CUDA(launch_pdl(kernel, dim3((unsigned)grid), kThreads, SMEM_BYTES, st, tmQ, tmK, tmV, p));
+    return SCB_OK;
+  };
+  if (p.bf16)
+    e = nch == 1 ? launch(attention_tc_kernel<true, 1>) : nch == 2 ? launch(attention_tc_kernel<true, 2>) : nch == 3 ? launch(attention_tc_kernel<true, 3>)
+        : nch == 4 ? launch(attention_tc_kernel<true, 4>) : launch(attention_tc_kernel<true, 5>);
+  else
+    e = nch == 1 ? launch(attention_tc_kernel<false, 1>) : nch == 2 ? launch(attention_tc_kernel<false, 2>) : nch == 3 ? launch(attention_tc_kernel<false, 3>)
+        : nch == 4 ? launch(attention_tc_kernel<false, 4>) : launch(attention_tc_kernel<false, 5>);
+  if (e) return e;
   note_launch();
   SCB_LAUNCH_OK("attention_tc");
   return SCB_OK;

@@ -36,7 +36,10 @@ class DropoutState:
         self.state = None
 
     def get(self, device) -> torch.Tensor:
-        if self.state is None or self.state.device != torch.device(device):
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        if self.state is None or self.state.device != device:
             rank = torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
             seed = (torch.initial_seed() * 0x9E3779B1 + rank * 0x85EBCA77 + 0x5bd1e995) % (2 ** 62)
             self.state = torch.tensor([seed, 0], dtype=torch.int64).to(device)

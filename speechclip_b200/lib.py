@@ -45,7 +45,7 @@ def ensure_built(force: bool = False, verbose: bool = False) -> str:
         obj = src[:-3] + ".o"
         objs.append(obj)
         cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-               "-Xcompiler", "-fPIC", "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
+               "-Xcompiler", "-fPIC", "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else []) + os.environ.get("SCB_NVCC_EXTRA", "").split()
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
         out, _ = p.communicate()
