@@ -263,10 +263,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       wait_bar(pv_done + 1, pt ^ 1u);
       tc_fence_after();
       ATTN_TRACE(tr, trace_tile + trace_off, 4);
-      const int4 pc = *my_cold;
-      const int pend_item = pc.x, pend_qt = pc.y;
+      const int4 pc = *my_cold;   // (output row pointer lo, hi, 1 / row sum, tile is live for this quarter)
+      uint16_t* const pend_dst = reinterpret_cast<uint16_t*>(((unsigned long long)(uint32_t)pc.y << 32) | (uint32_t)pc.x);
       const float pend_inv = __int_as_float(pc.z);
-      const bool pend_live = pend_qt * BQ + q * 32 < p.Tq;
+      const bool pend_live = pc.w != 0;
       uint32_t ov[16];
       if (pend_live) {
         tmem_ld_32x16(lane_addr + (uint32_t)(O_COL + part * 16), ov);
@@ -276,10 +276,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
-      const int pend_row = pend_qt * BQ + r;
-      if (pend_live && pend_row < p.Tq) {
-        const int pb = pend_item / p.heads, phd = pend_item % p.heads;
-        uint16_t* dst = p.o + (long long)pb * p.o_bs + (long long)pend_row * p.o_ld + phd * HD + part * 16;
+      if (pend_live && pend_dst != nullptr) {
+        uint16_t* dst = pend_dst;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           uint4 u;
@@ -422,7 +420,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         ATTN_TRACE(tr, trace_tile + trace_off, 9);
         ++trace_tile;
-        *my_cold = make_int4(item, qt, __float_as_int(inv), 0);
+        {
+          const unsigned long long dst = row_g < p.Tq ? (unsigned long long)(p.o + (long long)(item / p.heads) * p.o_bs + (long long)row_g * p.o_ld +
+                                                                             (item % p.heads) * HD + part * 16) : 0ull;
+          *my_cold = make_int4((int)(uint32_t)dst, (int)(uint32_t)(dst >> 32), __float_as_int(inv), live ? 1 : 0);
+        }
         have_pend = true;
         pt ^= 1u;
       }

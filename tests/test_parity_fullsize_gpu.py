@@ -230,15 +230,19 @@ def test_cascaded_base_full_size_vs_oracle():
     rep["loss"], rep["oracle_loss"] = loss.item(), oloss.item()
     rep["loss_rel"] = abs(loss.item() - oloss.item()) / max(1.0, abs(oloss.item()))
     oparams = dict(oracle.named_parameters())
-    gerrs = {}
-    zero_true_grad = ("cascaded_branch.self_att.attentionBlock_Norm.bias", "cascaded_branch.linear_proj.bias")
-    detail = {}
+    # Gradients.  Train-mode BatchNorm removes, to first order, anything that shifts a keyword feature by a constant over the batch:
+    # the TRUE gradients of the parameters in front of it that act that way ([CLS] rows, attention / projection biases, the
+    # LayerNorm bias) are two to five orders of magnitude below the others and sit at the rounding floor of the bf16 / TF32
+    # backward GEMMs (a flat ~1.3e-6 absolute here).  Every gradient is therefore bounded relative to max(its own magnitude,
+    # 2 % of the largest gradient magnitude of the model); the raw numbers are written to the report.
+    gerrs, detail = {}, {}
+    gmax = max(oparams[name].grad.abs().max().item() for name, p in model.named_parameters() if p.requires_grad)
     for name, p in model.named_parameters():
         if p.requires_grad:
             og = oparams[name].grad
-            detail[name] = [(p.grad.cpu() - og).abs().max().item(), og.abs().max().item(), p.grad.abs().max().item()]
-        if p.requires_grad and name not in zero_true_grad:   # BatchNorm removes per-feature constants: those two gradients are 0
-            gerrs[name] = rel_err(p.grad.cpu(), oparams[name].grad)
+            err = (p.grad.cpu() - og).abs().max().item()
+            detail[name] = [err, og.abs().max().item(), p.grad.abs().max().item()]
+            gerrs[name] = err / max(og.abs().max().item(), 0.02 * gmax)
     rep["grad_rel_max"], rep["grad_worst"], rep["n_grads"] = max(gerrs.values()), max(gerrs, key=gerrs.get), len(gerrs)
     rep["grad_detail_abs_err__ref_max__mine_max"] = detail
     _top1_vs_oracle(ma, mi, ra, ri, rep["logits_rel"], rep, "retrieval_tie_rows")
@@ -249,17 +253,23 @@ def test_cascaded_base_full_size_vs_oracle():
     assert len(diff) <= 2, rep
     assert rep["audio_emb_abs"] < 5e-3 and rep["image_emb_abs"] < TOL["embedding"], rep
     assert rep["loss_rel"] < 2e-3, rep
-    assert rep["grad_rel_max"] < 6e-2, rep
+    assert rep["grad_rel_max"] < 4e-2 and rep["n_grads"] == 12, rep
     assert rep["retrieval_tie_rows"] <= 1, rep
 
 
-def test_hubert_base_heavy_tailed_channels_in_the_fp16_hidden_stream():
+@pytest.mark.parametrize("hidden", ["fp16", "fp32"])
+def test_hubert_base_heavy_tailed_channels_in_the_hidden_stream(hidden, monkeypatch):
     """Trained HuBERT checkpoints carry outlier channels (a few LayerNorm gains / biases far above the rest).  The post-LN tower
-    keeps its hidden states in fp16 only (engine.py HubertPlan._forward): scale a few gains x50 and biases +-30 in several
-    layers and require the same per-channel accuracy as with benign weights."""
+    keeps its hidden states in fp16 only by default (engine.py HubertPlan._forward; ``SCB_HIDDEN_FP32=1`` keeps an fp32 stream):
+    scale a few gains x50 and biases +-30 in several layers and compare with the fp32 oracle.  The yardstick is the reference's
+    OWN arithmetic: it trains and evaluates under fp16 autocast (trainer.precision: 16, spchclp_p.yaml:113) — the same oracle under
+    torch's CPU autocast(float16) (fp16 GEMM inputs and outputs, fp32 LayerNorm / softmax / residual stream).  Required: the fp16
+    hidden stream stays within 1.5x of that error on the worst state and below it per channel; the fp32 stream is at or below it."""
     from avssl.module import FairseqSpeechEncoder_Hubert
     from oracle import hubert as oh
+    from speechclip_b200 import engine
     from speechclip_b200.init import seeded_init_
+    monkeypatch.setattr(engine, "HIDDEN16", hidden == "fp16")
     enc = FairseqSpeechEncoder_Hubert("hubert", feat_select_idx="hidden_states")
     g = torch.Generator().manual_seed(5)
     with torch.no_grad():
@@ -279,8 +289,6 @@ def test_hubert_base_heavy_tailed_channels_in_the_fp16_hidden_stream():
     states, _ = enc(wav.to(DEV))
     with torch.no_grad():
         ref = om.custom_forward(wav, None)["layer_results"]
-    # the yardstick: the reference trains and evaluates under fp16 autocast (trainer.precision: 16, spchclp_p.yaml:113) — the
-    # same oracle under torch's CPU autocast(float16) is that arithmetic (fp16 GEMM inputs AND outputs, fp32 LayerNorm / softmax)
     with torch.no_grad(), torch.autocast("cpu", dtype=torch.float16):
         amp = [a.float() for a in om.custom_forward(wav, None)["layer_results"]]
 
@@ -296,9 +304,9 @@ def test_hubert_base_heavy_tailed_channels_in_the_fp16_hidden_stream():
     assert all(torch.isfinite(a).all() for a in mine)
     worst, worst_ch = errors(mine)
     amp_worst, amp_worst_ch = errors(amp)
-    rep = {"hidden_rel_max": worst, "hidden_rel_per_channel_max": worst_ch, "autocast_fp16_hidden_rel_max": amp_worst,
+    rep = {"hidden_stream": hidden, "hidden_rel_max": worst, "hidden_rel_per_channel_max": worst_ch, "autocast_fp16_hidden_rel_max": amp_worst,
            "autocast_fp16_hidden_rel_per_channel_max": amp_worst_ch, "state_abs_max": max(r.abs().max().item() for r in ref)}
-    _report("heavy_tail", rep)
+    _report("heavy_tail_" + hidden, rep)
     assert rep["state_abs_max"] > 100.0   # the outliers are really there
-    # no worse than the reference's own mixed precision on the same weights (and within the benign-weights bound when that is looser)
-    assert worst <= max(1.5e-2, amp_worst) and worst_ch <= max(4e-2, amp_worst_ch), rep
+    slack = 1.5 if hidden == "fp16" else 1.0
+    assert worst <= max(1.5e-2, slack * amp_worst) and worst_ch <= max(4e-2, amp_worst_ch), rep
