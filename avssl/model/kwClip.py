@@ -47,40 +47,74 @@ def l2_normalize(x: torch.Tensor) -> torch.Tensor:
     return L2NormFn.apply(x)
 
 
-def _all_gather_rows(x: torch.Tensor) -> torch.Tensor:
-    x = x.contiguous()
-    out = torch.empty((dist.get_world_size() * x.shape[0],) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
-    dist.all_gather_into_tensor(out, x)
+def _timed_collective(name: str, fn):
+    """Run a torch.distributed call; under bench.py's per-call profiling bracket it with CUDA events like every C-ABI call."""
+    prof = ops.PROFILE
+    if prof is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = fn()
+    e1.record()
+    prof.append((name, 0.0, e0, e1, ""))
     return out
 
 
-class _GatherRows(torch.autograd.Function):
-    """all_gather along dim 0 over the default process group (NCCL over NVLink on the GPU box); backward hands every rank
-    the gradient rows of its own slice — each rank evaluates the same global loss, so no reduction is needed here, and the
-    per-rank parameter gradients are summed afterwards (``KWClipBase.allreduce_gradients``)."""
+def _all_gather_rows(x: torch.Tensor) -> torch.Tensor:
+    x = x.contiguous()
+    out = torch.empty((dist.get_world_size() * x.shape[0],) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
+    _timed_collective("nccl_all_gather", lambda: dist.all_gather_into_tensor(out, x))
+    return out
+
+
+class _GatherPacked(torch.autograd.Function):
+    """ONE all-gather for the whole feature dict: ids (int64, carried as two fp32 words) and every [B, D_i] fp32 feature matrix
+    are packed into one [B, 2 + sum D_i] buffer (NCCL over NVLink on the GPU box; the messages are a few hundred KB, so the call
+    count, not the byte count, is what costs).  Backward hands every rank the gradient rows of its own slice — each rank
+    evaluates the same global loss, so no reduction is needed here; the per-rank parameter gradients are summed afterwards
+    (``KWClipBase.allreduce_gradients``)."""
 
     @staticmethod
-    def forward(ctx, x):
-        ctx.rows = x.shape[0]
-        return _all_gather_rows(x)
+    def forward(ctx, ids, *feats):
+        B = feats[0].shape[0]
+        widths = [f.shape[1] for f in feats]
+        buf = torch.empty(B, 2 + sum(widths), device=feats[0].device, dtype=torch.float32)
+        buf[:, :2] = ids.to(torch.int64).contiguous().view(torch.float32).view(B, 2)
+        off = 2
+        for f, w in zip(feats, widths):
+            buf[:, off:off + w] = f
+            off += w
+        out = _all_gather_rows(buf)
+        ctx.rows, ctx.widths = B, widths
+        gids = out[:, :2].contiguous().view(torch.int64).view(-1)
+        res, off = [gids], 2
+        for w in widths:
+            res.append(out[:, off:off + w])
+            off += w
+        ctx.mark_non_differentiable(gids)
+        return tuple(res)
 
     @staticmethod
-    def backward(ctx, g):
-        rank = dist.get_rank()
-        return g[rank * ctx.rows:(rank + 1) * ctx.rows]
+    def backward(ctx, _gid, *grads):
+        r0 = dist.get_rank() * ctx.rows
+        return (None,) + tuple(None if g is None else g[r0:r0 + ctx.rows] for g in grads)
 
 
 def gather_features(feats: dict) -> dict:
-    """Per-rank ``{id, image_feat, parallel_audio_feat}`` -> the same dict over the global batch (rank-major order).
-    Replaces Lightning's DataParallel gather in front of ``training_step_end`` (kwClip.py:147-167)."""
+    """Per-rank ``{id, image_feat, parallel_audio_feat | cascaded_audio_feat}`` -> the same dict over the global batch (rank-major
+    order).  Replaces Lightning's DataParallel gather in front of ``training_step_end`` (kwClip.py:147-167)."""
     if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
         return feats
-    out = {}
-    for k, v in feats.items():
-        if isinstance(v, torch.Tensor) and v.dim() >= 1:
-            out[k] = _GatherRows.apply(v) if v.requires_grad else _all_gather_rows(v)
-        else:
-            out[k] = v
+    keys = [k for k, v in feats.items() if k != "id" and isinstance(v, torch.Tensor) and v.dim() == 2 and v.dtype == torch.float32]
+    if "id" in feats and isinstance(feats["id"], torch.Tensor) and feats["id"].dim() == 1 and keys:
+        packed = _GatherPacked.apply(feats["id"], *[feats[k] for k in keys])
+        out = {"id": packed[0], **{k: v for k, v in zip(keys, packed[1:])}}
+    else:
+        out, keys = {}, []
+    for k, v in feats.items():   # anything else (other dtypes / ranks): one call each, or passed through
+        if k in out:
+            continue
+        out[k] = _all_gather_rows(v) if isinstance(v, torch.Tensor) and v.dim() >= 1 else v
     return out
 
 
@@ -199,11 +233,11 @@ class KWClipBase(BaseLightningModel):
             for k in (0, 1):
                 base = arena.flat_g[k].data_ptr()
                 if all(p.grad is not None and p.grad.data_ptr() == base + 4 * off for p, off in zip(arena.params, arena.offsets)):
-                    dist.all_reduce(arena.flat_g[k])
+                    _timed_collective("nccl_all_reduce", lambda: dist.all_reduce(arena.flat_g[k]))
                     return
         for p in (arena.params if arena is not None else self.getTrainableParams()):  # gradients that autograd did not adopt in place
             if p.grad is not None:
-                dist.all_reduce(p.grad)
+                _timed_collective("nccl_all_reduce", lambda: dist.all_reduce(p.grad))
 
     # ------------------------------------------------------------------------------------------------- validation hooks
     def validation_step(self, batch: dict, batch_idx: int = 0) -> dict:
@@ -346,7 +380,8 @@ class KW_CascadedBranch(nn.Module):
             logger.info("kw_projection not specified, using single linear layer as default")
             self.linear_proj = nn.Linear(cb.transformer_args.d_model, self.text_dim)
         else:
-            self.linear_proj = MLPLayers(units=self.kw_projection_config.dimensions, dropout=self.kw_projection_config.dropout)
+            raise NotImplementedError("KW_CascadedBranch on B200: keyword.kw_projection (an MLP instead of the single Linear, kwClip.py:757-768) "
+                                      "is not wired into the fused keyword path; no shipped config sets it")
         self.vq_type = cb.vq.type
         if not hasattr(vector_quantizers, cb.vq.type):
             raise NotImplementedError("Vq ({}) not implemented".format(cb.vq.type))
@@ -500,12 +535,15 @@ class KWClip_GeneralTransformer(KWClipBase):
         if self.config.model_settings.parallel_objective_weight > 0:
             logger.info("Create Parallel Branch")
             self.parallel_branch = KW_ParallelBranch(config=self.config, audio_dim=self.audio_embd_dim, out_dim=self.subword_embd_dim)
-        self.img_enc_proj_net = None
-        self.p_branch_proj_net = None
-        self.c_branch_proj_net = None
-        for key in ("image_encoder_projection", "parallel_branch_projection", "cascaded_branch_projection"):
-            if self.config.model_settings.get(key, None) is not None:
-                MLPLayers()  # raises: projections are not on the shipped path
+        # optional projection networks (kwClip.py:1147-1187; absent from every shipped YAML)
+        ms = self.config.model_settings
+        self.img_enc_proj_net = self.p_branch_proj_net = self.c_branch_proj_net = None
+        for attr, key in (("img_enc_proj_net", "image_encoder_projection"), ("p_branch_proj_net", "parallel_branch_projection"),
+                          ("c_branch_proj_net", "cascaded_branch_projection")):
+            spec = ms.get(key, None)
+            if spec is not None:
+                logger.info(f"{key} dims:{spec.dimensions} droupout:{spec.dropout}")
+                setattr(self, attr, MLPLayers(units=spec.dimensions, dropout=spec.dropout))
         self._wire_arena()
 
     def _wire_arena(self):
@@ -522,6 +560,12 @@ class KWClip_GeneralTransformer(KWClipBase):
             _params += list(self.cascaded_branch.parameters())
         if self.parallel_branch is not None:
             _params += list(self.parallel_branch.parameters())
+        if self.img_enc_proj_net is not None:
+            logger.info("Add img_enc_proj_net parameters")
+            _params += list(self.img_enc_proj_net.parameters())
+        if self.p_branch_proj_net is not None:
+            logger.info("Add parallel_branch_projection parameters")
+            _params += list(self.p_branch_proj_net.parameters())
         return _params
 
     def feature_extractor_s3prl(self, wav) -> Tuple[torch.Tensor, Tuple]:
@@ -565,7 +609,10 @@ class KWClip_GeneralTransformer(KWClipBase):
             cascaded_audio_feat, vq_results, keywords = self.cascaded_branch(audio_feat=audio_feat, audio_len=audio_len)
             cascaded_audio_feat = l2_normalize(cascaded_audio_feat)
         if self.parallel_branch is not None:
-            parallel_audio_feat = l2_normalize(self.parallel_branch(audio_feat=audio_feat, audio_len=audio_len))
+            parallel_audio_feat = self.parallel_branch(audio_feat=audio_feat, audio_len=audio_len)
+            if self.p_branch_proj_net is not None:
+                parallel_audio_feat = self.p_branch_proj_net(parallel_audio_feat)
+            parallel_audio_feat = l2_normalize(parallel_audio_feat)
         return {"cascaded_audio_feat": cascaded_audio_feat, "parallel_audio_feat": parallel_audio_feat, "vq_results": vq_results,
                 "keywords": keywords}
 
@@ -583,10 +630,12 @@ class KWClip_GeneralTransformer(KWClipBase):
             image_raw.record_stream(cur)
             audio_feat, audio_len = self.forward_audio(wav, wav_len)
             cur.wait_stream(side)
-            image_feat = l2_normalize(image_raw)
         else:
             audio_feat, audio_len = self.forward_audio(wav, wav_len)
-            image_feat = l2_normalize(self.forward_image(image))
+            image_raw = self.forward_image(image)
+        if self.img_enc_proj_net is not None:
+            image_raw = self.img_enc_proj_net(image_raw)
+        image_feat = l2_normalize(image_raw)
         losses_ = {"id": id, "image_feat": image_feat}
         log_metrics = {}
         cascaded_audio_feat = parallel_audio_feat = vq_results = keywords = None
@@ -595,7 +644,10 @@ class KWClip_GeneralTransformer(KWClipBase):
             cascaded_audio_feat = l2_normalize(cascaded_audio_feat)
             losses_["cascaded_audio_feat"] = cascaded_audio_feat
         if self.parallel_branch is not None:
-            parallel_audio_feat = l2_normalize(self.parallel_branch(audio_feat=audio_feat, audio_len=audio_len))
+            parallel_audio_feat = self.parallel_branch(audio_feat=audio_feat, audio_len=audio_len)
+            if self.p_branch_proj_net is not None:
+                parallel_audio_feat = self.p_branch_proj_net(parallel_audio_feat)
+            parallel_audio_feat = l2_normalize(parallel_audio_feat)
             losses_["parallel_audio_feat"] = parallel_audio_feat
         if self.config.model_settings.cascaded_objective_weight > 0:
             log_metrics["softmax_temp"] = vq_results["temp"]

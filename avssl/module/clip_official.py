@@ -114,7 +114,27 @@ class ClipModel(nn.Module):
         return self
 
     def prep_image(self, paths: list) -> torch.Tensor:
-        raise NotImplementedError("image file preprocessing (PIL + torchvision transforms) is out of scope: pass [B,3,H,W] tensors")
+        """Image files -> preprocessed tensor [B, 3, n_px, n_px] on the model's device (clip_official.py:151-164 with openai's
+        ``_transform``: bicubic resize of the short side to n_px, centre crop, RGB, ToTensor, Normalize).  Decode / resize / crop run
+        on the host with PIL exactly as in openai CLIP (the same library calls, so the same pixels); ToTensor + Normalize run on the
+        device from the uint8 pixels (``scb_image_normalize``)."""
+        from PIL import Image
+        n_px = self.arch.image_size
+        dev = self.model.token_embedding.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("ClipModel.prep_image: move the module to a CUDA device first (no CPU path)")
+        pixels = []
+        for p in paths:
+            img = Image.open(p) if not isinstance(p, Image.Image) else p
+            w, h = img.size
+            scale = n_px / min(w, h)   # torchvision Resize(n_px): short side -> n_px, long side int(n_px * long / short)
+            nw, nh = (n_px, int(n_px * h / w)) if w <= h else (int(n_px * w / h), n_px)
+            img = img.resize((nw, nh), Image.BICUBIC)
+            left, top = int(round((nw - n_px) / 2.0)), int(round((nh - n_px) / 2.0))   # torchvision CenterCrop
+            img = img.crop((left, top, left + n_px, top + n_px)).convert("RGB")
+            pixels.append(torch.from_numpy(np.asarray(img, dtype=np.uint8).copy()))
+        from avssl.data.collate_function import CLIP_MEAN, CLIP_STD
+        return ops.image_normalize(torch.stack(pixels).to(dev), CLIP_MEAN, CLIP_STD)
 
     def prep_text(self, sents: list) -> torch.Tensor:
         raise NotImplementedError("the openai BPE tokenizer is not available offline: pass token tensors")

@@ -244,6 +244,31 @@ int scb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, doubl
 int scb_retrieval_rank(const float* score, int64_t ld, int32_t rows, int32_t cols, const int64_t* cand_ids, const int64_t* answers,
                        int32_t* rank, int32_t* top1, void* stream);
 
+/* ---- input side and pooling (SURVEY.md 8 rows f3 / b) -------------------------------------------------------------------- */
+
+/* openai CLIP's image transform after the resize / crop (ToTensor + Normalize; the transform the reference's datasets and
+ * ClipModel.prep_image apply per image on the host, clip_official.py:151-164): uint8 [batch][H][W][3] -> fp32 [batch][3][H][W],
+ * (x / 255 - mean[c]) / std[c].  The host ships 1 byte per sample instead of 4. */
+int scb_image_normalize(const uint8_t* img_hwc, int32_t batch, int32_t H, int32_t W, const float* mean3, const float* std3, float* out_chw,
+                        void* stream);
+/* collate_general's pad_sequence (avssl/data/collate_function.py:30-31) on the device: row b is packed[offsets[b] .. + lens[b]),
+ * out is [batch][tmax] zero padded (every element written). */
+int scb_pad_rows(const float* packed, const int64_t* offsets, const int64_t* lens, int32_t batch, int64_t tmax, float* out, void* stream);
+/* MeanPoolingLayer (avssl/module/pooling.py:40-60): out[b][d] = mean over the first lens[b] frames of x [batch][T][D] (lens NULL:
+ * all T).  bwd: dx[b][t][d] = dout[b][d] / lens[b] for t < lens[b], else 0. */
+int scb_masked_mean_fwd(const float* x, const int64_t* lens, int32_t batch, int32_t T, int32_t D, float* out, void* stream);
+int scb_masked_mean_bwd(const float* dout, const int64_t* lens, int32_t batch, int32_t T, int32_t D, float* dx, void* stream);
+/* AttentivePoolingLayer.forward (pooling.py:335-390) after the two alignment GEMMs: align [batch][TA][TB] = A^T U B (before the
+ * tanh), mask additive [batch][TA][TB] or NULL, A [batch][dA][TA], B [batch][dB][TB]:
+ *   s = tanh(align) + mask; scoreA = softmax_TA(max_TB s); scoreB = softmax_TB(max_TA s); outA = A scoreA; outB = B scoreB. */
+int scb_attentive_pool_fwd(const float* align, const float* mask, const float* A, const float* B, int32_t batch, int32_t TA, int32_t TB,
+                           int32_t dA, int32_t dB, float* outA, float* outB, void* stream);
+/* AttentivePoolingLayer.cal_batch_embedding (pooling.py:262-333): y = softmax over TA of tanh(x [batch][TA][N]) + mask [batch][TA]. */
+int scb_tanh_softmax_dim1(const float* x, const float* mask, int32_t batch, int32_t TA, int32_t N, float* y, void* stream);
+/* MLPLayers (avssl/module/projections.py:6-29): ReLU forward / backward on fp32 rows. */
+int scb_relu_fwd(const float* x, float* y, int64_t n, void* stream);
+int scb_relu_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream);
+
 /* ---- cascaded branch (avssl/model/kwClip.py:857-916 KW_CascadedBranch.extract_hidden_states / forward) ------------------- */
 
 /* MultiheadAttentionAndNorm (avssl/module/kw_modules/TransformerModels.py:11-60) with the keyword [CLS] vectors as queries

@@ -193,6 +193,28 @@ int scb_rows_bias_act(const float* x, int64_t x_ld, const float* bias, const flo
   return scb::rows_bias_act(x, x_ld, bias, res, res_ld, act, pre, y, y_ld, rows, d, ST);
 }
 int scb_gelu_bwd(const float* dy, const float* pre, float* dx, int64_t n, void* stream) { return scb::gelu_bwd(dy, pre, dx, n, ST); }
+int scb_image_normalize(const uint8_t* img_hwc, int32_t batch, int32_t H, int32_t W, const float* mean3, const float* std3, float* out_chw,
+                        void* stream) {
+  return scb::image_normalize(img_hwc, batch, H, W, mean3, std3, out_chw, ST);
+}
+int scb_pad_rows(const float* packed, const int64_t* offsets, const int64_t* lens, int32_t batch, int64_t tmax, float* out, void* stream) {
+  return scb::pad_rows(packed, (const long long*)offsets, (const long long*)lens, batch, tmax, out, ST);
+}
+int scb_masked_mean_fwd(const float* x, const int64_t* lens, int32_t batch, int32_t T, int32_t D, float* out, void* stream) {
+  return scb::masked_mean_fwd(x, (const long long*)lens, batch, T, D, out, ST);
+}
+int scb_masked_mean_bwd(const float* dout, const int64_t* lens, int32_t batch, int32_t T, int32_t D, float* dx, void* stream) {
+  return scb::masked_mean_bwd(dout, (const long long*)lens, batch, T, D, dx, ST);
+}
+int scb_attentive_pool_fwd(const float* align, const float* mask, const float* A, const float* B, int32_t batch, int32_t TA, int32_t TB,
+                           int32_t dA, int32_t dB, float* outA, float* outB, void* stream) {
+  return scb::attentive_pool_fwd(align, mask, A, B, batch, TA, TB, dA, dB, outA, outB, ST);
+}
+int scb_tanh_softmax_dim1(const float* x, const float* mask, int32_t batch, int32_t TA, int32_t N, float* y, void* stream) {
+  return scb::tanh_softmax_dim1(x, mask, batch, TA, N, y, ST);
+}
+int scb_relu_fwd(const float* x, float* y, int64_t n, void* stream) { return scb::relu_fwd(x, y, n, ST); }
+int scb_relu_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream) { return scb::relu_bwd(dy, y, dx, n, ST); }
 int scb_rng_advance(int64_t* rng_state, void* stream) { return scb::rng_advance((long long*)rng_state, ST); }
 int scb_dropout_mask(const int64_t* rng_state, int32_t site, float p, float* mask, int64_t n, void* stream) {
   return scb::dropout_mask((const long long*)rng_state, site, p, mask, n, ST);

@@ -101,4 +101,14 @@ int softmax_rows(const float* s, long long ld, long long rows, int rows_per_batc
 int split_tf32(const float* src, long long src_ld, float* dst, long long rows, int cols, int role, cudaStream_t st);
 int act16_fwd(const void* pre, int fmt, int act, void* out, long long n, cudaStream_t st);
 int act_bwd(const float* dy, const void* pre, int fmt, int act, float* dx, long long n, cudaStream_t st);
+// pooling.cu
+int image_normalize(const uint8_t* img, int batch, int H, int W, const float* mean3, const float* std3, float* out, cudaStream_t st);
+int pad_rows(const float* packed, const long long* offsets, const long long* lens, int batch, long long tmax, float* out, cudaStream_t st);
+int masked_mean_fwd(const float* x, const long long* lens, int batch, int T, int D, float* out, cudaStream_t st);
+int masked_mean_bwd(const float* dout, const long long* lens, int batch, int T, int D, float* dx, cudaStream_t st);
+int attentive_pool_fwd(const float* align, const float* mask, const float* A, const float* Bm, int batch, int TA, int TB, int dA, int dB,
+                       float* outA, float* outB, cudaStream_t st);
+int tanh_softmax_dim1(const float* x, const float* mask, int batch, int TA, int N, float* y, cudaStream_t st);
+int relu_fwd(const float* x, float* y, long long n, cudaStream_t st);
+int relu_bwd(const float* dy, const float* y, float* dx, long long n, cudaStream_t st);
 }  // namespace scb

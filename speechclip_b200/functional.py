@@ -340,3 +340,92 @@ class InfoNCEFn(torch.autograd.Function):
         ops.infonce(a, b, ids, log_mult, fixed_mult, margin, dcl, a2b, b2a, scratch, phase=2, upstream_dev=dloss.contiguous().float(),
                     dA=dA, dB=dB, dlog_mult=dT)
         return dA, dB, None, dT, None, None, None, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------------- small differentiable row ops
+# (MeanPoolingLayer / MLPLayers of the reference's module surface: avssl/module/pooling.py:8-60, projections.py:6-29.  fp32 rows on
+#  the TF32 tensor-core GEMM, the same helpers the trainable head uses.)
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b on fp32 rows [..., K] (nn.Linear)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        from .head import linear
+        _require_cuda(x, "Linear")
+        x2 = x.contiguous().float().view(-1, x.shape[-1])
+        y = torch.empty(x2.shape[0], weight.shape[0], device=x.device, dtype=torch.float32)
+        linear(x2, weight, y, bias=bias)
+        ctx.save_for_backward(x2, weight)
+        ctx.shape, ctx.has_bias = x.shape, bias is not None
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        from .head import dgrad, wgrad
+        x2, weight = ctx.saved_tensors
+        ws = workspace(dy.device)
+        dy2 = dy.contiguous().float().view(-1, weight.shape[0])
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x2)
+            dgrad(ws, "lin", dy2, weight, dx)
+            dx = dx.view(ctx.shape)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(weight)
+            wgrad(ws, "lin", dy2, x2, dw)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.empty(weight.shape[0], device=dy.device, dtype=torch.float32)
+            ops.column_sum(dy2, db)
+        return dx, dw, db
+
+
+class MaskedMeanFn(torch.autograd.Function):
+    """mean over the first len[b] frames of x [B, T, D] (pooling.py:52-56)."""
+
+    @staticmethod
+    def forward(ctx, x, lens):
+        _require_cuda(x, "MeanPoolingLayer")
+        x = x.contiguous().float()
+        B, T, D = x.shape
+        if lens is not None:
+            lens = lens.to(device=x.device, dtype=torch.int64).contiguous()
+        out = torch.empty(B, D, device=x.device, dtype=torch.float32)
+        ops.masked_mean_fwd(x, lens, out)
+        ctx.lens, ctx.shape = lens, (B, T, D)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dx = torch.empty(ctx.shape, device=dout.device, dtype=torch.float32)
+        ops.masked_mean_bwd(dout.contiguous().float(), ctx.lens, dx)
+        return dx, None
+
+
+class ReluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _require_cuda(x, "ReLU")
+        x = x.contiguous().float()
+        y = ops.relu_fwd(x, torch.empty_like(x))
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        return ops.relu_bwd(dy.contiguous().float(), y, torch.empty_like(y))
+
+
+class DropoutFn(torch.autograd.Function):
+    """Elementwise dropout with the counter-based masks of scb_dropout_mask; ``drop`` = (p, rng_state, site)."""
+
+    @staticmethod
+    def forward(ctx, x, drop):
+        x = x.contiguous().float()
+        ctx.drop = (drop[0], drop[1].clone(), drop[2])
+        return ops.dropout_rows(x, torch.empty_like(x), ctx.drop)
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous().float()
+        return ops.dropout_rows(dy, torch.empty_like(dy), ctx.drop), None

@@ -102,6 +102,14 @@ def _declare(lib):
         "scb_cls_attention_fwd": [vp, vp, i32, i64, i64, i32, i32, vp, i32, i32, i32, i32, f32, vp, vp, vp, i32, f32, vp, i32, vp],
         "scb_cls_attention_bwd": [vp, vp, i32, i64, i64, i32, i32, vp, i32, i32, i32, i32, f32, vp, vp, vp, i32, vp, f32, vp, i32, vp],
         "scb_rng_advance": [vp, vp],
+        "scb_image_normalize": [vp, i32, i32, i32, vp, vp, vp, vp],
+        "scb_pad_rows": [vp, vp, vp, i32, i64, vp, vp],
+        "scb_masked_mean_fwd": [vp, vp, i32, i32, i32, vp, vp],
+        "scb_masked_mean_bwd": [vp, vp, i32, i32, i32, vp, vp],
+        "scb_attentive_pool_fwd": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp],
+        "scb_tanh_softmax_dim1": [vp, vp, i32, i32, i32, vp, vp],
+        "scb_relu_fwd": [vp, vp, i64, vp],
+        "scb_relu_bwd": [vp, vp, vp, i64, vp],
         "scb_dropout_mask": [vp, i32, f32, vp, i64, vp],
         "scb_dropout_rows": [vp, vp, i64, f32, vp, i32, vp],
         "scb_frame_lengths": [vp, i32, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp],
@@ -156,7 +164,8 @@ EXPORTS = ["scb_abi_version", "scb_last_error", "scb_launch_count", "scb_conv0_s
            "scb_l2norm_bwd", "scb_weighted_sum_fwd", "scb_weighted_sum_bwd", "scb_rows_bias_act", "scb_gelu_bwd", "scb_column_sum",
            "scb_infonce", "scb_adam_step", "scb_retrieval_rank", "scb_mq_attention_fwd", "scb_mq_attention_bwd", "scb_batchnorm_fwd",
            "scb_batchnorm_bwd", "scb_vq_forward", "scb_vq_backward", "scb_cosine_bwd_rows", "scb_vq_diagnostics", "scb_keyword_embed",
-           "scb_rng_advance", "scb_dropout_mask", "scb_dropout_rows",
+           "scb_rng_advance", "scb_dropout_mask", "scb_dropout_rows", "scb_image_normalize", "scb_pad_rows", "scb_masked_mean_fwd",
+           "scb_masked_mean_bwd", "scb_attentive_pool_fwd", "scb_tanh_softmax_dim1", "scb_relu_fwd", "scb_relu_bwd",
            "scb_attention_small_bwd", "scb_token_embed", "scb_gather_rows", "scb_softmax_rows", "scb_split_tf32", "scb_act16_fwd", "scb_act_bwd"]
 
 

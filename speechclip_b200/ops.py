@@ -411,3 +411,59 @@ def gather_rows(src, row, out):
 def softmax_rows(s, rows_per_batch, lens, cols, out, out_cols):
     """s fp32 [rows, ld]; lens int32 [rows / rows_per_batch] or None; out 16-bit [rows, out_ld]."""
     _call("scb_softmax_rows", _p(s), s.stride(0), s.shape[0], rows_per_batch, _p(lens), cols, _p(out), _DT[out.dtype], out.stride(0), out_cols)
+
+
+# ------------------------------------------------------------------------------------------------ input side / pooling
+def image_normalize(img_u8, mean, std, out=None):
+    """uint8 [B, H, W, 3] (device) -> fp32 [B, 3, H, W], (x / 255 - mean) / std  (CLIP's ToTensor + Normalize)."""
+    B, H, W, C = img_u8.shape
+    assert C == 3 and img_u8.dtype == torch.uint8 and img_u8.is_contiguous()
+    if out is None:
+        out = torch.empty(B, 3, H, W, device=img_u8.device, dtype=torch.float32)
+    m = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    s_ = (ctypes.c_float * 3)(*[float(v) for v in std])
+    _call("scb_image_normalize", _p(img_u8), B, H, W, m, s_, _p(out))
+    return out
+
+
+def pad_rows(packed, offsets, lens, tmax, out=None):
+    """Ragged fp32 rows packed back to back (device) -> zero-padded [B, tmax]."""
+    B = lens.numel()
+    assert packed.dtype == torch.float32 and offsets.dtype == lens.dtype == torch.int64
+    if out is None:
+        out = torch.empty(B, tmax, device=packed.device, dtype=torch.float32)
+    _call("scb_pad_rows", _p(packed), _p(offsets), _p(lens), B, tmax, _p(out))
+    return out
+
+
+def masked_mean_fwd(x, lens, out):
+    B, T, D = x.shape
+    _call("scb_masked_mean_fwd", _p(x), _p(lens), B, T, D, _p(out))
+    return out
+
+
+def masked_mean_bwd(dout, lens, dx):
+    B, T, D = dx.shape
+    _call("scb_masked_mean_bwd", _p(dout), _p(lens), B, T, D, _p(dx))
+    return dx
+
+
+def attentive_pool_fwd(align, mask, A, Bm, outA, outB):
+    B, TA, TB = align.shape
+    _call("scb_attentive_pool_fwd", _p(align), _p(mask), _p(A), _p(Bm), B, TA, TB, A.shape[1], Bm.shape[1], _p(outA), _p(outB))
+
+
+def tanh_softmax_dim1(x, mask, y):
+    B, TA, N = x.shape
+    _call("scb_tanh_softmax_dim1", _p(x), _p(mask), B, TA, N, _p(y))
+    return y
+
+
+def relu_fwd(x, y):
+    _call("scb_relu_fwd", _p(x), _p(y), x.numel())
+    return y
+
+
+def relu_bwd(dy, y, dx):
+    _call("scb_relu_bwd", _p(dy), _p(y), _p(dx), y.numel())
+    return dx

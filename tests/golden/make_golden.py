@@ -215,6 +215,50 @@ def part1_reference():
     finally:
         F.dropout, F.scaled_dot_product_attention = orig
 
+    # ---- pooling layers (pooling.py:8-390) and MLPLayers (projections.py:6-29): the reference's own modules on seeded inputs
+    pl = load_ref("module/pooling.py", "ref_pool")
+    torch.manual_seed(23)
+    mp = pl.MeanPoolingLayer(in_dim=24, out_dim=16)
+    x = torch.randn(5, 9, 24, generator=g).requires_grad_()
+    xl = torch.tensor([9, 3, 7, 1, 5])
+    y = mp(x, xl)
+    wy = torch.randn(5, 16, generator=g)
+    (y * wy).sum().backward()
+    y_nolen = mp(x.detach())
+    ap = pl.AttentivePoolingLayer(dim_A=12, dim_B=10)
+    with torch.no_grad():
+        ap.U.copy_(0.3 * torch.randn(12, 10, generator=g))
+        a_in, b_in = torch.randn(4, 12, 7, generator=g), torch.randn(4, 10, 5, generator=g)
+        msk = ap.generate_input_msk(input_A_lens=torch.tensor([7, 4, 6, 2]), input_B_lens=torch.tensor([5, 5, 3, 1]), max_Alen=7, max_Blen=5)
+        oa, ob = ap(a_in, b_in, msk)
+        oa_nm, ob_nm = ap(a_in, b_in)
+        msk_a = ap.generate_input_msk(input_A_lens=torch.tensor([7, 4, 6, 2]), max_Alen=7, max_Blen=1)
+        b2 = torch.randn(3, 10, 5, generator=g)
+        boa, bob = ap.batch_forward(a_in, b2, msk_a)
+        bvec = torch.randn(10, 6, generator=g)
+        emb = ap.cal_batch_embedding(a_in, bvec, msk_a)
+    save("ref_pooling.npz", mp_x=x, mp_len=xl, mp_y=y, mp_w=wy, mp_dx=x.grad, mp_y_nolen=y_nolen,
+         **{"mp_sd." + k: v for k, v in mp.state_dict().items()}, **{"mp_grad." + k: v.grad for k, v in mp.named_parameters()},
+         ap_U=ap.U, ap_a=a_in, ap_b=b_in, ap_msk=msk, ap_oa=oa, ap_ob=ob, ap_oa_nomask=oa_nm, ap_ob_nomask=ob_nm, ap_msk_a=msk_a,
+         ap_b2=b2, ap_boa=boa, ap_bob=bob, ap_bvec=bvec, ap_emb=emb)
+    pj = load_ref("module/projections.py", "ref_proj")
+    torch.manual_seed(29)
+    mlp = pj.MLPLayers(units=[16, 32, 8], dropout=0.1).eval()
+    xm = torch.randn(6, 16, generator=g).requires_grad_()
+    ym = mlp(xm)
+    wm = torch.randn(6, 8, generator=g)
+    (ym * wm).sum().backward()
+    save("ref_mlp.npz", x=xm, y=ym, w=wm, dx=xm.grad, **{"sd." + k: v for k, v in mlp.state_dict().items()},
+         **{"grad." + k: v.grad for k, v in mlp.named_parameters()})
+
+    # ---- collate_general (collate_function.py:7-36)
+    cf = load_ref("data/collate_function.py", "ref_cf")
+    rows = [{"wav": torch.randn(n, generator=g), "image": torch.randn(3, 4, 4, generator=g), "id": i * 3, "text": torch.arange(5).view(1, 5) + i}
+            for i, n in enumerate((11, 7, 15))]
+    col = cf.collate_general(rows)
+    save("ref_collate.npz", **{f"row{i}_{k}": v for i, r in enumerate(rows) for k, v in r.items() if isinstance(v, torch.Tensor)},
+         **{"out_" + k: v for k, v in col.items()}, out_keys=np.array(list(col.keys())))
+
     # ---- random_crop_max_length semantics (audio_transforms.py:5-23): shapes only (np.random offset)
     at = load_ref("data/audio_transforms.py", "ref_at")
     assert at.random_crop_max_length(torch.arange(10), 4, 10).shape == (4,)

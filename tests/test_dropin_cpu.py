@@ -3,7 +3,7 @@
 * the reference's own YAML configs + vocabulary tables build the model (needs /root/reference; skipped on the GPU box);
 * with this repo in front of the reference on ``sys.path`` the reference's task runner (``run_task.py:6`` ->
   ``avssl/task/base_task.py``) imports, resolving ``avssl.model`` / ``avssl.module`` / ``avssl.base`` here and its control
-  plane (``avssl.task``, ``avssl.data``, ``avssl.util.{args,log}``) in the reference;
+  plane (``avssl.task``, the datasets of ``avssl.data``, ``avssl.util.{args,log}``) in the reference;
 * a reference-layout Lightning checkpoint (pickled ``OrderedNamespace`` hparams with ``pretrained: true``, duplicate
   ``cascaded_branch.clip.*`` keys, ``criterion.*`` buffers, torch-Adam ``optimizer_states``) loads through
   ``load_from_checkpoint`` and ``FusedAdam.load_state_dict``.
@@ -104,9 +104,12 @@ def test_reference_task_runner_imports_with_this_repo_in_front(tmp_path):
         import avssl.model, avssl.module, avssl.base, avssl.util, avssl.data, avssl.optim
         runner = task.TrainKWClip_GeneralTransformer()           # run_task.py:16
         here, ref = {ROOT!r}, {REF!r}
-        assert task.__file__.startswith(ref) and avssl.data.__file__.startswith(ref)
-        for m in (avssl.model, avssl.module, avssl.base, avssl.optim, avssl.util):
+        assert task.__file__.startswith(ref)
+        for m in (avssl.model, avssl.module, avssl.base, avssl.optim, avssl.util, avssl.data):
             assert m.__file__.startswith(here), m.__file__
+        from avssl.data import FlickrDataset, CoCoDataset, collate_general as cg   # datasets: the reference's own files
+        assert sys.modules[FlickrDataset.__module__].__file__.startswith(ref) and cg.__module__ == "avssl.data.collate_function"
+        assert sys.modules[cg.__module__].__file__.startswith(here)
         from avssl.task import train_KWClip
         assert train_KWClip.KWClip_GeneralTransformer is avssl.model.KWClip_GeneralTransformer
         assert train_KWClip.KWClip_GeneralTransformer.__module__ == "avssl.model.kwClip"
@@ -211,3 +214,26 @@ def test_reference_layout_lightning_checkpoint_loads(tmp_path, kind):
         assert int(out["state"][i]["step"]) == 2
         assert torch.equal(out["state"][i]["exp_avg"], st["exp_avg"]) and torch.equal(out["state"][i]["exp_avg_sq"], st["exp_avg_sq"])
     assert out["param_groups"][0]["lr"] == ckpt["optimizer_states"][0]["param_groups"][0]["lr"]
+
+
+def test_collate_general_matches_reference_fixture(golden):
+    """avssl.data.collate_general (host code) on the rows the reference's own collate_general was run on
+    (tests/golden/make_golden.py): same keys in the same order, wav_len appended, zero padding, stacking, LongTensor ids."""
+    import numpy as np
+    from avssl.data import collate_general, collate_packed
+    z = golden("ref_collate.npz")
+    rows = []
+    for i in range(3):
+        rows.append({"wav": torch.from_numpy(z[f"row{i}_wav"]), "image": torch.from_numpy(z[f"row{i}_image"]), "id": i * 3,
+                     "text": torch.from_numpy(z[f"row{i}_text"])})
+    out = collate_general(rows)
+    assert list(out.keys()) == [str(k) for k in z["out_keys"]]
+    for k, v in out.items():
+        ref = torch.from_numpy(z["out_" + k])
+        assert v.dtype == ref.dtype and torch.equal(v, ref), k
+    # the packed variant carries the same information in fewer bytes
+    pk = collate_packed(rows)
+    assert pk["wav"].numel() == 11 + 7 + 15 and pk["wav_len"].tolist() == [11, 7, 15] and pk["wav_offset"].tolist() == [0, 11, 18]
+    for i in range(3):
+        assert torch.equal(pk["wav"][pk["wav_offset"][i]:pk["wav_offset"][i] + pk["wav_len"][i]], rows[i]["wav"])
+    assert torch.equal(pk["image"], out["image"]) and torch.equal(pk["id"], out["id"])
