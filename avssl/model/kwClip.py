@@ -158,9 +158,9 @@ class KWClipBase(BaseLightningModel):
 
     # ------------------------------------------------------------------------------------------------- towers
     def forward_audio(self, wav: Union[torch.Tensor, list], wav_len: Union[torch.Tensor, list] = [],
-                      return_hidden_states: bool = False):
+                      return_hidden_states: bool = False, frozen: dict = None):
         if self.audio_encoder_type in ["s3prl_plus", "FairseqHubert"]:
-            return self.audio_encoder(wav, wav_len, return_hidden_states=return_hidden_states)
+            return self.audio_encoder(wav, wav_len, return_hidden_states=return_hidden_states, frozen=frozen)
         raise NotImplementedError("Unknown type:{}".format(self.audio_encoder_type))
 
     def forward_image(self, images: Union[list, torch.Tensor]) -> torch.Tensor:
@@ -511,8 +511,8 @@ OVERLAP_TOWERS = os.environ.get("SCB_OVERLAP_TOWERS", "1") != "0"
 _SIDE_STREAMS: dict = {}
 
 
-def _side_stream(device) -> "torch.cuda.Stream":
-    key = str(device)
+def _side_stream(device, which: str = "image") -> "torch.cuda.Stream":
+    key = (str(device), which)
     if key not in _SIDE_STREAMS:
         _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
     return _SIDE_STREAMS[key]
@@ -616,12 +616,45 @@ class KWClip_GeneralTransformer(KWClipBase):
         return {"cascaded_audio_feat": cascaded_audio_feat, "parallel_audio_feat": parallel_audio_feat, "vq_results": vq_results,
                 "keywords": keywords}
 
+    def precompute_towers(self, batch: dict, slot: int = 0) -> dict:
+        """Launch the two FROZEN towers for ``batch`` on the tower streams and return at once: ``{"audio": handle, "image_raw":
+        tensor, "events": (audio_done, image_done)}``.  Passing the result as ``batch["_scb_towers"]`` makes ``forward`` skip the
+        towers and wait for the events instead.  Every shipped configuration freezes both towers, so their outputs for batch
+        i + 1 do not depend on the optimizer step of batch i: ``speechclip_b200.runtime.TowerPipeline`` uses this to run them under
+        the (latency-bound) head / loss / backward / all-reduce / Adam tail of the previous batch."""
+        image = batch["image"]
+        dev = image.device
+        cur = torch.cuda.current_stream(dev)
+        sa, si = _side_stream(dev, "audio"), _side_stream(dev, "image")
+        sa.wait_stream(cur)   # the inputs are ready (and earlier users of this slot's buffers are done) once `cur` gets here
+        si.wait_stream(cur)
+        self.clip.update_device(self.device)
+        with torch.cuda.stream(si):
+            image_raw = self.forward_image(image)
+            ev_i = torch.cuda.Event()
+            ev_i.record(si)
+        with torch.cuda.stream(sa):
+            frozen = self.audio_encoder.encode_frozen(batch["wav"], batch["wav_len"], slot=slot)
+            ev_a = torch.cuda.Event()
+            ev_a.record(sa)
+        return {"audio": frozen, "image_raw": image_raw, "events": (ev_a, ev_i)}
+
     def forward(self, batch) -> tuple:
         wav, wav_len, image, id = batch["wav"], batch["wav_len"], batch["image"], batch["id"]
         self.clip.update_device(self.device)
+        pre = batch.get("_scb_towers") if isinstance(batch, dict) else None
         # The two frozen towers are independent until the loss: the image tower runs on a side stream, so its small, latency-bound
         # kernels (50 tokens per image) fill SMs the speech tower's kernels leave idle at their tails (SCB_OVERLAP_TOWERS=0: serial).
-        if OVERLAP_TOWERS and isinstance(image, torch.Tensor) and image.is_cuda:
+        if pre is not None:   # towers launched ahead of time (precompute_towers): wait for them, hand their outputs to this stream
+            cur = torch.cuda.current_stream(image.device)
+            for ev in pre["events"]:
+                cur.wait_event(ev)
+            image_raw = pre["image_raw"]
+            image_raw.record_stream(cur)
+            for t in (pre["audio"]["hidden"], pre["audio"]["feat_len"]):
+                t.record_stream(cur)
+            audio_feat, audio_len = self.forward_audio(None, frozen=pre["audio"])
+        elif OVERLAP_TOWERS and isinstance(image, torch.Tensor) and image.is_cuda:
             cur = torch.cuda.current_stream(image.device)
             side = _side_stream(image.device)
             side.wait_stream(cur)

@@ -174,8 +174,11 @@ class FairseqSpeechEncoder_Hubert(nn.Module):
         lens = torch.tensor([len(w) for w in wavs], dtype=torch.int64).to(dev)
         return pad_sequence(wavs, batch_first=True).contiguous(), lens
 
-    def forward(self, wav: Union[torch.Tensor, list], wav_len: Union[torch.Tensor, list] = [],
-                feat_select_idx: Union[str, list] = None, return_hidden_states: bool = False) -> tuple:
+    def encode_frozen(self, wav: Union[torch.Tensor, list], wav_len: Union[torch.Tensor, list] = [], slot: int = 0) -> dict:
+        """The frozen part of ``forward`` — crop / pad / normalise, frame lengths, the HuBERT tower — on the CURRENT stream;
+        returns a handle for ``forward(..., frozen=handle)``.  ``slot`` selects one of the independent sets of staging
+        and tower buffers (``functional.workspace``; under CUDA-graph replay each set gets its own graph and output slab): a caller that runs the tower of batch i + 1 before the
+        backward pass of batch i (``speechclip_b200.runtime.TowerPipeline``) alternates slots."""
         wav, lens = self._batch(wav, wav_len)
         B, Tmax = wav.shape
         dev = wav.device
@@ -184,7 +187,7 @@ class FairseqSpeechEncoder_Hubert(nn.Module):
         T = conv_out_len(tw)
         if T < 1:
             raise ValueError(f"utterances of {tw} samples are shorter than HuBERT's receptive field (400 samples)")
-        ws = workspace(dev)
+        ws = workspace(dev, slot)
         ints = ws.view("len_ints", (4, B), torch.int32)  # persistent: valid_frames' address is part of the tower's graph signature
         crop_off, crop_len, valid_frames, feat_len32 = ints[0], ints[1], ints[2], ints[3]
         feat_len = torch.empty(B, device=dev, dtype=torch.int64)
@@ -196,6 +199,13 @@ class FairseqSpeechEncoder_Hubert(nn.Module):
         ops.wav_prepare(wav, crop_off, crop_len, tw, self.arch.normalize_wav, stats, wav_p)
         with torch.no_grad():
             hidden, T = self.plan(dev).forward(ws, wav_p, valid_frames if lens is not None else None)
+        return {"hidden": hidden, "T": T, "B": B, "feat_len": feat_len}
+
+    def forward(self, wav: Union[torch.Tensor, list] = None, wav_len: Union[torch.Tensor, list] = [],
+                feat_select_idx: Union[str, list] = None, return_hidden_states: bool = False, frozen: dict = None) -> tuple:
+        if frozen is None:
+            frozen = self.encode_frozen(wav, wav_len)
+        hidden, T, B, feat_len = frozen["hidden"], frozen["T"], frozen["B"], frozen["feat_len"]
         d = self.out_dim
         slab = hidden.view(hidden.shape[0], B, T, d)
         slab._scb_graph_output = hidden if hasattr(hidden, "_scb_generation") else None
@@ -226,7 +236,6 @@ class FairseqSpeechEncoder_Hubert(nn.Module):
         if return_hidden_states:
             ret.append(states())
         return tuple(ret)
-
 
 class S3prlSpeechEncoderPlus(nn.Module):
     """Reference: avssl/module/speech_encoder_plus.py:110-336 (speech encoders loaded through the s3prl hub).  Every shipped

@@ -210,7 +210,8 @@ def run_own(args):
         dist.init_process_group("nccl", device_id=dev)
     lib.load()
 
-    per_gpu = GLOBAL_BATCH // world if args.scaling == "strong" else GLOBAL_BATCH
+    gb = args.global_batch or GLOBAL_BATCH   # --global-batch 4096: BASELINE.json configs[4] (8 GPUs x 512 pairs, all-gathered negatives)
+    per_gpu = gb // world if args.scaling == "strong" else gb
     if args.batch:
         per_gpu = args.batch
     global_batch = per_gpu * world
@@ -231,7 +232,7 @@ def run_own(args):
     opts, scheds = model.configure_optimizers()
     opt, sched = opts[0], scheds[0]["scheduler"]
 
-    from speechclip_b200.runtime import DevicePrefetcher, bind_to_gpu_numa_node
+    from speechclip_b200.runtime import DevicePrefetcher, TowerPipeline, bind_to_gpu_numa_node
     numa_node = bind_to_gpu_numa_node(local)  # pinned staging buffers local to the GPU's PCIe root (None: topology not visible)
     host = synth_batch(per_gpu, 7122 + rank, True)
     host["id"] += rank * per_gpu
@@ -269,8 +270,17 @@ def run_own(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(max(args.warmup, 3)):
-        step(resident)
+    # Cross-step overlap (speechclip_b200.runtime.TowerPipeline): the frozen towers of batch i + 1 are enqueued on the tower
+    # streams before the head / loss / backward / all-reduce / Adam tail of batch i, whose ~150 small dependent kernels then no
+    # longer leave the GPU idle.  K timed steps are K complete steps: the first batch's towers run un-overlapped inside the
+    # timed region, and nothing of step K + 1 is started.
+    pipe = TowerPipeline(model) if args.pipeline == "on" else None
+
+    def run_steps(batches):
+        for batch in (pipe.iterate(batches) if pipe is not None else batches):
+            step(batch)
+
+    run_steps(resident for _ in range(max(args.warmup, 3)))
     barrier()
 
     # ---- device-resident timing.  The two towers run on two streams (and, at small per-GPU batch, as CUDA-graph replays), so a
@@ -284,8 +294,8 @@ def run_own(args):
         time.sleep(0.3)
     n0 = lib.launch_count() + engine.graph_replayed_kernels()
     ops.PROFILE = None
-    ms_total = timed(lambda: step(resident), args.steps)
-    host_ms = timed.host_ms
+    ms_total = timed(lambda: run_steps(resident for _ in range(args.steps)), 1)
+    host_ms = timed.host_ms / args.steps
     launches = lib.launch_count() + engine.graph_replayed_kernels() - n0
     prof_steps = 1 if use_graphs else min(args.steps, 5)
     overlap, kwclip_mod.OVERLAP_TOWERS = kwclip_mod.OVERLAP_TOWERS, False
@@ -301,7 +311,7 @@ def run_own(args):
     # ---- end to end through the public API with host buffers: every step's inputs are copied from pinned host memory
     # (double-buffered on a copy stream by speechclip_b200.runtime.DevicePrefetcher) and its loss is read back to the host
     host_times = []
-    prefetcher = DevicePrefetcher(None, dev)  # one object for the warm-up and the timed pass: its two device slots are allocated once
+    prefetcher = DevicePrefetcher(None, dev, lookahead=1 if pipe is not None else 0)  # one object for the warm-up and the timed pass: its two device slots are allocated once
     # host->device bandwidth of this process's pinned buffers (diagnostic: the copy must hide behind one step)
     probe = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -320,7 +330,8 @@ def run_own(args):
         # Every step's loss is copied to pinned host memory and read by the host — one step late (after step i+1 has been
         # enqueued), the way a training loop logs without draining the GPU between steps.
         last, pending = None, None
-        for i, batch in enumerate(prefetcher.iterate(host for _ in range(n))):
+        staged = prefetcher.iterate(host for _ in range(n))
+        for i, batch in enumerate(pipe.iterate(staged) if pipe is not None else staged):
             t_h = time.perf_counter()
             if dbg is not None:
                 e_a = torch.cuda.Event(enable_timing=True)
@@ -417,12 +428,12 @@ def run_own(args):
         "config": {"workload": {"base": "Parallel SpeechCLIP-base (HuBERT-base + CLIP ViT-B/32)",
                                 "large": "Parallel SpeechCLIP-large (HuBERT-large + CLIP ViT-L/14)",
                                 "cascaded": "Cascaded SpeechCLIP-base (HuBERT-base + keyword VQ over 8112 subwords + CLIP ViT-B/32 text and image towers)"}[args.config]
-                               + " training step, batch 256, 102400-sample utterances",
+                               + f" training step, batch {global_batch}, 102400-sample utterances",
                    "global_batch": global_batch, "pairs_per_gpu": per_gpu, "frames": 319, "parallelism": f"dp{world}",
                    "mode": "training step (model.train()): branch dropout p=0.1 active (Philox masks, regenerated in backward), frozen towers in eval arithmetic, trainable branch "
                            + ("2.77 M params (+ frozen CLIP text tower in the differentiated path)" if args.config == "cascaded" else "7.48 M params"),
                    "l2": "inputs (259 MB) and activations (GBs) larger than the 126 MB L2; no flush needed",
-                   "cuda_graphs": use_graphs, "tower_streams": 2 if kwclip_mod.OVERLAP_TOWERS else 1},
+                   "cuda_graphs": use_graphs, "tower_pipeline": pipe is not None, "tower_streams": 2 if kwclip_mod.OVERLAP_TOWERS else 1},
         "e2e": {"value": global_batch / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "h2d_gb_per_s_measured": h2d_gbs, "numa_node_bound": numa_node, "passes_ms_per_step": [t[0] for t in passes],
                 "reported": "median pass", "fastest_pass_ms_per_step": min(t[0] for t in passes), "diagnostics": e2e_diag,
@@ -472,9 +483,12 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--batch", type=int, default=0, help="pairs per GPU (default: 256 / N strong, 256 weak)")
+    ap.add_argument("--global-batch", type=int, default=0, help="global batch under strong scaling (default 256; 4096 = BASELINE.json configs[4])")
     ap.add_argument("--config", default="base", choices=["base", "large", "cascaded"],
                     help="base = BASELINE.json configs[1] (headline); large = HuBERT-large + ViT-L/14 (configs[3])")
     ap.add_argument("--graphs", default="auto", choices=["auto", "on", "off"], help="replay the frozen towers as CUDA graphs")
+    ap.add_argument("--pipeline", default="on", choices=["on", "off"],
+                    help="run the frozen towers of batch i+1 under the head/backward/Adam tail of batch i (runtime.TowerPipeline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-profile", default="", help="write the per-GEMM-shape timing table (CSV) here")
     args = ap.parse_args()

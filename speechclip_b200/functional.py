@@ -17,13 +17,16 @@ from .head import PARAM_ORDER, ParallelHead
 _WS: Dict[int, Workspace] = {}
 
 
-def workspace(device) -> Workspace:
+def workspace(device, slot: int = 0) -> Workspace:
+    """The device's scratch-buffer set.  ``slot`` > 0 names further, independent sets (runtime.TowerPipeline keeps the frozen
+    towers of consecutive batches in alternating slots, so the tower of batch i + 1 never writes what batch i still reads)."""
     idx = torch.device(device).index
     if idx is None:
         idx = torch.cuda.current_device()
-    ws = _WS.get(idx)
+    key = idx if slot == 0 else (idx, slot)
+    ws = _WS.get(key)
     if ws is None:
-        ws = _WS[idx] = Workspace(torch.device("cuda", idx))
+        ws = _WS[key] = Workspace(torch.device("cuda", idx))
     return ws
 
 
