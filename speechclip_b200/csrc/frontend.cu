@@ -91,8 +91,9 @@ __global__ void conv0_finalize_kernel(const double* __restrict__ acc, const floa
 // constant columns — so the accumulator IS scale*conv + shift and the epilogue is only GELU + pack + store.  That leaves
 // ~16 instructions per output element instead of ~32 on the fp32 SIMT path (the kernel evaluates 2.7 G activations per step).
 // Block = 8 warps = 2 frame halves x 4 channel groups of 128; a warp keeps its 16 B-fragments (128 channels) in registers
-// and walks frame tiles of 16.  The fragment column -> channel map is chosen so that every lane ends up with 32 CONTIGUOUS
-// channels of a frame (64 bytes): column j of n-block n is channel (j/2)*32 + n*2 + (j%2).
+// and walks frame tiles of 16.  The fragment column -> channel map is chosen so that a store instruction writes whole 32-byte
+// sectors: column j of n-block n is channel (j/4)*64 + (n/4)*16 + ((j/2)%2)*8 + (n%4)*2 + (j%2), so after four n-blocks a lane
+// holds 8 contiguous channels (16 bytes) and its neighbour (lane ^ 1) the next 8.
 constexpr int kFramesPerBlock = 128;
 template <int FMT>
 __device__ __forceinline__ uint32_t gelu_pack(float a, float b) {  // two activations on the packed-fp32 path, then one 16-bit pair
@@ -100,16 +101,17 @@ __device__ __forceinline__ uint32_t gelu_pack(float a, float b) {  // two activa
   upk2(gelu_h16_x2(pk2(a, b)), lo, hi);
   return H16<FMT>::pack(lo, hi);
 }
+template <int FPB>  // frames per block: the B fragments (weights x GroupNorm scale, 2 dependent global reads) are built once per block
 __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restrict__ wav, long long wav_ld, const float* __restrict__ w,
                                                           const float2* __restrict__ scale_shift, void* __restrict__ out, int out_fmt,
                                                           int n_frames, long long out_batch_stride, int channels) {
-  __shared__ float xs[kFramesPerBlock * kStride + kTaps + 6];
+  __shared__ float xs[FPB * kStride + kTaps + 6];
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * kFramesPerBlock;
-  const int nt = min(kFramesPerBlock, n_frames - t0);
+  const int t0 = blockIdx.x * FPB;
+  const int nt = min(FPB, n_frames - t0);
   const int nsamp = (nt - 1) * kStride + kTaps;
   const float* x = wav + (long long)b * wav_ld + (long long)t0 * kStride;
-  for (int i = threadIdx.x; i < kFramesPerBlock * kStride + kTaps + 6; i += blockDim.x) xs[i] = i < nsamp ? __ldg(x + i) : 0.f;
+  for (int i = threadIdx.x; i < FPB * kStride + kTaps + 6; i += blockDim.x) xs[i] = i < nsamp ? __ldg(x + i) : 0.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const int cgrp = warp & 3, fhalf = warp >> 2;
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restric
   uint32_t bfrag[16][2];
 #pragma unroll
   for (int nb = 0; nb < 16; ++nb) {
-    const int ch = cgrp * 128 + (g >> 1) * 32 + nb * 2 + (g & 1);
+    const int ch = cgrp * 128 + (g >> 2) * 64 + (nb >> 2) * 16 + ((g >> 1) & 1) * 8 + (nb & 3) * 2 + (g & 1);
     const float2 ss = scale_shift[(long long)b * channels + ch];
     const float* wc = w + ch * kTaps;
     bfrag[nb][0] = H16<SCB_F16>::pack(wc[t4 * 2] * ss.x, wc[t4 * 2 + 1] * ss.x);
@@ -132,7 +134,8 @@ __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restric
     }
   }
   __syncthreads();
-  uint16_t* obase = reinterpret_cast<uint16_t*>(out) + (long long)b * out_batch_stride + (long long)t0 * channels + cgrp * 128 + t4 * 32;
+  uint16_t* obase = reinterpret_cast<uint16_t*>(out) + (long long)b * out_batch_stride + (long long)t0 * channels + cgrp * 128 +
+                    (t4 >> 1) * 64 + (t4 & 1) * 8;
   for (int ft = fhalf; ft * 16 < nt; ft += 2) {
     const int f0 = ft * 16;
     // ---- A fragment: rows g / g+8 of the tile, columns (t4*2, +1) and (t4*2+8, +9)
@@ -174,8 +177,8 @@ __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restric
         ub.x = gelu_pack<SCB_F16>(c[0][2], c[0][3]); ub.y = gelu_pack<SCB_F16>(c[1][2], c[1][3]);
         ub.z = gelu_pack<SCB_F16>(c[2][2], c[2][3]); ub.w = gelu_pack<SCB_F16>(c[3][2], c[3][3]);
       }
-      if (ok_a) *reinterpret_cast<uint4*>(oa + q4 * 8) = ua;
-      if (ok_b) *reinterpret_cast<uint4*>(ob + q4 * 8) = ub;
+      if (ok_a) *reinterpret_cast<uint4*>(oa + q4 * 16) = ua;
+      if (ok_b) *reinterpret_cast<uint4*>(ob + q4 * 16) = ub;
     }
   }
 }
@@ -234,7 +237,7 @@ __global__ void __launch_bounds__(256) conv0_ln_apply_kernel(const float* __rest
   uint32_t bfrag[16][2];
 #pragma unroll
   for (int nb = 0; nb < 16; ++nb) {
-    const int ch = cgrp * 128 + (g >> 1) * 32 + nb * 2 + (g & 1);
+    const int ch = cgrp * 128 + (g >> 2) * 64 + (nb >> 2) * 16 + ((g >> 1) & 1) * 8 + (nb & 3) * 2 + (g & 1);  // see conv0_apply_kernel
     const float gm = gamma ? gamma[ch] : 1.f;
     const float* wc = w + ch * kTaps;
     bfrag[nb][0] = H16<SCB_F16>::pack(wc[t4 * 2] * gm, wc[t4 * 2 + 1] * gm);
@@ -268,7 +271,8 @@ __global__ void __launch_bounds__(256) conv0_ln_apply_kernel(const float* __rest
     fstat[threadIdx.x] = make_float2(rstd, -mean * rstd);
   }
   __syncthreads();
-  uint16_t* obase = reinterpret_cast<uint16_t*>(out) + (long long)b * out_batch_stride + (long long)t0 * channels + cgrp * 128 + t4 * 32;
+  uint16_t* obase = reinterpret_cast<uint16_t*>(out) + (long long)b * out_batch_stride + (long long)t0 * channels + cgrp * 128 +
+                    (t4 >> 1) * 64 + (t4 & 1) * 8;
   for (int ft = fhalf; ft * 16 < nt; ft += 2) {
     const int f0 = ft * 16;
     // ---- A fragment: rows g / g+8 of the tile, columns (t4*2, +1) and (t4*2+8, +9)
@@ -316,8 +320,8 @@ __global__ void __launch_bounds__(256) conv0_ln_apply_kernel(const float* __rest
         ub.x = gelu_pack<SCB_F16>(c[0][2], c[0][3]); ub.y = gelu_pack<SCB_F16>(c[1][2], c[1][3]);
         ub.z = gelu_pack<SCB_F16>(c[2][2], c[2][3]); ub.w = gelu_pack<SCB_F16>(c[3][2], c[3][3]);
       }
-      if (ok_a) *reinterpret_cast<uint4*>(oa + q4 * 8) = ua;
-      if (ok_b) *reinterpret_cast<uint4*>(ob + q4 * 8) = ub;
+      if (ok_a) *reinterpret_cast<uint4*>(oa + q4 * 16) = ua;
+      if (ok_b) *reinterpret_cast<uint4*>(ob + q4 * 16) = ub;
     }
   }
 }
@@ -456,7 +460,15 @@ int conv0_groupnorm_gelu(const float* wav, long long wav_ld, int batch, int n_sa
   conv0_finalize_kernel<<<dim3((channels + 127) / 128, batch), 128, 0, st>>>(acc, w, conv_bias, gamma, beta, n_frames, channels, eps, ss);
   note_launch();
   SCB_LAUNCH_OK("conv0_finalize");
-  conv0_apply_kernel<<<dim3((n_frames + kFramesPerBlock - 1) / kFramesPerBlock, batch), 256, 0, st>>>(wav, wav_ld, w, ss, out, out_fmt,
+  static const int fpb = [] { const char* e = getenv("SCB_CONV0_FPB"); return e ? atoi(e) : 256; }();  // measured at 256 x 102400 samples: 128 -> 1.74 ms, 256 -> 1.58 ms, 512 -> 1.56 ms
+  if (fpb == 512)
+    conv0_apply_kernel<512><<<dim3((n_frames + 511) / 512, batch), 256, 0, st>>>(wav, wav_ld, w, ss, out, out_fmt,
+                                                                                n_frames, out_batch_stride, channels);
+  else if (fpb != 128)
+    conv0_apply_kernel<256><<<dim3((n_frames + 255) / 256, batch), 256, 0, st>>>(wav, wav_ld, w, ss, out, out_fmt,
+                                                                                n_frames, out_batch_stride, channels);
+  else
+  conv0_apply_kernel<128><<<dim3((n_frames + kFramesPerBlock - 1) / kFramesPerBlock, batch), 256, 0, st>>>(wav, wav_ld, w, ss, out, out_fmt,
                                                                                                      n_frames, out_batch_stride, channels);
   note_launch();
   SCB_LAUNCH_OK("conv0_apply");

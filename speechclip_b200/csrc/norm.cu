@@ -294,6 +294,135 @@ __global__ void __launch_bounds__(256) weighted_sum_fwd_kernel(const TH* __restr
   }
 }
 
+// ---- un-normalised weighted sum (the base configurations): one thread per 16-byte chunk of a row.
+// The row-per-warp kernels above keep a whole row in registers because the parameter-free LayerNorm needs its statistics; without
+// it nothing couples the columns, and the kernel is a pure 13-stream read.  What bounds it then is bytes in flight: the
+// row-per-warp form (80 registers, 24 warps per SM, 2 layers unrolled) reached 3.6 TB/s.  Here every thread owns ONE 16-byte
+// column chunk, issues kFlatUnroll independent 16-byte loads (one per layer) before it touches any of them, and keeps only
+// 4 / 8 accumulators, so ~32 warps per SM hold 128 B each in flight.
+constexpr int kFlatUnroll = 8;
+template <typename TH> __device__ __forceinline__ void decode16(const uint4& u, float (&v)[HVec<TH>::N]);
+template <> __device__ __forceinline__ void decode16<float>(const uint4& u, float (&v)[4]) {
+  v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
+}
+template <> __device__ __forceinline__ void decode16<__half>(const uint4& u, float (&v)[8]) {
+  const float2 a = H16<SCB_F16>::unpack(u.x), b = H16<SCB_F16>::unpack(u.y), c = H16<SCB_F16>::unpack(u.z), d = H16<SCB_F16>::unpack(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {  // read-once data: non-coherent path, no L1 allocation
+  uint4 u;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p));
+  return u;
+}
+
+template <typename TH>
+__global__ void __launch_bounds__(256) weighted_sum_fwd_flat_kernel(const TH* __restrict__ h, long long layer_stride,
+                                                                    const float* __restrict__ w_logits, int L,
+                                                                    float* __restrict__ out32, void* __restrict__ out16, int out16_fmt,
+                                                                    long long rows, int d, int rows_per_batch,
+                                                                    long long out16_batch_stride, long long out16_row0) {
+  constexpr int V = HVec<TH>::N;
+  __shared__ float sw[64];
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < L ? w_logits[threadIdx.x] : -INFINITY;
+    float v2 = threadIdx.x + 32 < L ? w_logits[threadIdx.x + 32] : -INFINITY;
+    const float m = warp_max(fmaxf(v, v2));
+    const float e = threadIdx.x < L ? __expf(v - m) : 0.f, e2 = threadIdx.x + 32 < L ? __expf(v2 - m) : 0.f;
+    const float s = warp_sum(e + e2);
+    sw[threadIdx.x] = e / s;
+    sw[threadIdx.x + 32] = e2 / s;
+  }
+  __syncthreads();
+  const int nvec = d / V;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * nvec) return;
+  const long long row = idx / nvec;
+  const int c = (int)(idx - row * nvec);
+  const TH* p = h + row * d + c * V;
+  float acc[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[j] = 0.f;
+  for (int l0 = 0; l0 < L; l0 += kFlatUnroll) {
+    uint4 raw[kFlatUnroll];
+#pragma unroll
+    for (int u = 0; u < kFlatUnroll; ++u)
+      if (l0 + u < L) raw[u] = ld_stream16(p + (long long)(l0 + u) * layer_stride);
+#pragma unroll
+    for (int u = 0; u < kFlatUnroll; ++u) {
+      if (l0 + u < L) {
+        float v[V];
+        decode16<TH>(raw[u], v);
+        const float wl = sw[l0 + u];
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] = fmaf(wl, v[j], acc[j]);
+      }
+    }
+  }
+  const long long bidx = row / rows_per_batch, r = row % rows_per_batch;
+#pragma unroll
+  for (int j = 0; j < V; j += 4) {
+    const float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+    if (out32) *reinterpret_cast<float4*>(out32 + row * d + c * V + j) = o;
+    if (out16) store4_16(reinterpret_cast<uint16_t*>(out16) + bidx * out16_batch_stride + (out16_row0 + r) * d + c * V + j, out16_fmt, o);
+  }
+}
+
+template <typename TH, int LMAX>
+__global__ void __launch_bounds__(256, LMAX <= 16 ? 3 : 2) weighted_sum_bwd_flat_kernel(const TH* __restrict__ h, long long layer_stride, int L,
+                                                                       const float* __restrict__ dout, long long rows, int d,
+                                                                       int rows_per_batch, long long dout_batch_stride, long long dout_row0,
+                                                                       float* __restrict__ dw_raw) {
+  constexpr int V = HVec<TH>::N;
+  __shared__ float sacc[64];
+  if (threadIdx.x < 64) sacc[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int nvec = d / V;
+  const long long total = rows * nvec;
+  float part[LMAX];
+#pragma unroll
+  for (int l = 0; l < LMAX; ++l) part[l] = 0.f;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / nvec;
+    const int c = (int)(idx - row * nvec);
+    const long long bidx = row / rows_per_batch, r = row % rows_per_batch;
+    const float* dr = dout + bidx * dout_batch_stride + (dout_row0 + r) * d + c * V;
+    float g[V];
+#pragma unroll
+    for (int j = 0; j < V; j += 4) {
+      const uint4 f = ld_stream16(dr + j);
+      g[j] = __uint_as_float(f.x); g[j + 1] = __uint_as_float(f.y); g[j + 2] = __uint_as_float(f.z); g[j + 3] = __uint_as_float(f.w);
+    }
+    const TH* p = h + row * d + c * V;
+#pragma unroll
+    for (int l0 = 0; l0 < LMAX; l0 += kFlatUnroll) {
+      uint4 raw[kFlatUnroll];
+#pragma unroll
+      for (int u = 0; u < kFlatUnroll; ++u)
+        if (l0 + u < L) raw[u] = ld_stream16(p + (long long)(l0 + u) * layer_stride);
+#pragma unroll
+      for (int u = 0; u < kFlatUnroll; ++u) {
+        if (l0 + u < L) {
+          float v[V];
+          decode16<TH>(raw[u], v);
+          float dot = 0.f;
+#pragma unroll
+          for (int j = 0; j < V; ++j) dot = fmaf(g[j], v[j], dot);
+          part[l0 + u] += dot;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int l = 0; l < LMAX; ++l) {
+    if (l < L) {
+      const float s = warp_sum(part[l]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[l], s);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < L) atomicAdd(&dw_raw[threadIdx.x], sacc[threadIdx.x]);
+}
+
 // dw_l = sum_{r,c} dout[r,c] * h_l[r,c]  (h optionally LayerNorm'ed first); then softmax backward into dlogits.
 // dout rows may live inside a larger per-batch buffer (branch input gradient): row r of batch b is at
 // dout + b*dout_batch_stride + (dout_row0 + r)*d.
@@ -473,11 +602,17 @@ int weighted_sum_fwd(const void* h, int h_dtype, long long layer_stride, const f
 #define SCB_WS_FWD(NORM, TH) \
   weighted_sum_fwd_kernel<NORM, TH><<<grid, 256, 0, st>>>(static_cast<const TH*>(h), layer_stride, w_logits, L, out32, out16, out16_fmt, \
                                                           rows, d, rows_per_batch, out16_batch_stride, out16_row0)
+  const long long chunks = rows * (d / (h_dtype == SCB_F16 ? 8 : 4));
+  const unsigned fgrid = (unsigned)((chunks + 255) / 256);
+#define SCB_WS_FLAT(TH) \
+  weighted_sum_fwd_flat_kernel<TH><<<fgrid, 256, 0, st>>>(static_cast<const TH*>(h), layer_stride, w_logits, L, out32, out16, out16_fmt, \
+                                                          rows, d, rows_per_batch, out16_batch_stride, out16_row0)
   if (h_dtype == SCB_F16) {
-    if (normalize) SCB_WS_FWD(true, __half); else SCB_WS_FWD(false, __half);
+    if (normalize) SCB_WS_FWD(true, __half); else SCB_WS_FLAT(__half);
   } else {
-    if (normalize) SCB_WS_FWD(true, float); else SCB_WS_FWD(false, float);
+    if (normalize) SCB_WS_FWD(true, float); else SCB_WS_FLAT(float);
   }
+#undef SCB_WS_FLAT
 #undef SCB_WS_FWD
   note_launch();
   SCB_LAUNCH_OK("weighted_sum_fwd");
@@ -505,11 +640,25 @@ int weighted_sum_bwd(const void* h, int h_dtype, long long layer_stride, const f
       weighted_sum_bwd_kernel<NORM, TH, 32><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const TH*>(h), layer_stride, L, dout, rows, d, \
                                                                               rows_per_batch, dout_batch_stride, dout_row0, scratch_L); \
   } while (0)
+    const long long chunks = rows * (d / (h_dtype == SCB_F16 ? 8 : 4));
+    long long fblocks = (chunks + 255) / 256;
+    const long long per_sm = L <= 16 ? 3 : 2;  // resident blocks (see the kernel's launch bounds)
+    if (fblocks > per_sm * num_sms()) fblocks = per_sm * num_sms();
+#define SCB_WS_BWD_FLAT(TH)                                                                                                        \
+  do {                                                                                                                             \
+    if (L <= 16)                                                                                                                   \
+      weighted_sum_bwd_flat_kernel<TH, 16><<<(unsigned)fblocks, 256, 0, st>>>(static_cast<const TH*>(h), layer_stride, L, dout, rows, d, \
+                                                                              rows_per_batch, dout_batch_stride, dout_row0, scratch_L); \
+    else                                                                                                                           \
+      weighted_sum_bwd_flat_kernel<TH, 32><<<(unsigned)fblocks, 256, 0, st>>>(static_cast<const TH*>(h), layer_stride, L, dout, rows, d, \
+                                                                              rows_per_batch, dout_batch_stride, dout_row0, scratch_L); \
+  } while (0)
     if (h_dtype == SCB_F16) {
-      if (normalize) SCB_WS_BWD(true, __half); else SCB_WS_BWD(false, __half);
+      if (normalize) SCB_WS_BWD(true, __half); else SCB_WS_BWD_FLAT(__half);
     } else {
-      if (normalize) SCB_WS_BWD(true, float); else SCB_WS_BWD(false, float);
+      if (normalize) SCB_WS_BWD(true, float); else SCB_WS_BWD_FLAT(float);
     }
+#undef SCB_WS_BWD_FLAT
 #undef SCB_WS_BWD
     note_launch();
     SCB_LAUNCH_OK("weighted_sum_bwd");

@@ -123,10 +123,22 @@ class TowerPipeline:
             loss = model.training_step_end(model.training_step(batch))["loss"]; loss.backward(); optimizer.step()
     """
 
-    def __init__(self, model, batches: Optional[Iterable[Dict[str, torch.Tensor]]] = None):
+    def __init__(self, model, batches: Optional[Iterable[Dict[str, torch.Tensor]]] = None, head_priority: Optional[bool] = None):
         self.model = model
         self.batches = batches
         self._n = 0
+        if head_priority is None:
+            head_priority = os.environ.get("SCB_PIPELINE_PRIORITY", "1") != "0"
+        self.head_priority = head_priority
+        self._head_stream = None
+
+    def head_stream(self, device) -> "torch.cuda.Stream":
+        """The high-priority stream the loop body runs on while the pipeline is iterated (``head_priority``): the tail's small
+        kernels are dependent on each other, so each one that queues behind a tower GEMM of the next batch adds its wait to the
+        step; with priority they take the first SMs a tower kernel frees."""
+        if self._head_stream is None:
+            self._head_stream = torch.cuda.Stream(device=device, priority=-1)
+        return self._head_stream
 
     def iterate(self, batches: Iterable[Dict[str, torch.Tensor]]) -> Iterator[Dict[str, torch.Tensor]]:
         self.batches = batches
@@ -141,6 +153,23 @@ class TowerPipeline:
     def __iter__(self) -> Iterator[Dict[str, torch.Tensor]]:
         if getattr(self.batches, "lookahead", 1) < 1:
             raise ValueError("TowerPipeline holds one batch beyond the current one: build the DevicePrefetcher with lookahead=1")
+        if not self.head_priority:
+            yield from self._iterate()
+            return
+        # The loop body (the caller's step) runs with the high-priority head stream current: the generator is suspended inside
+        # the ``with`` block, and the stream context is per thread.  On exit (exhaustion, break or exception) the caller's own
+        # stream is current again and ordered after everything the loop enqueued.
+        dev = next(self.model.parameters()).device
+        outer = torch.cuda.current_stream(dev)
+        hs = self.head_stream(dev)
+        hs.wait_stream(outer)
+        try:
+            with torch.cuda.stream(hs):
+                yield from self._iterate()
+        finally:
+            outer.wait_stream(hs)
+
+    def _iterate(self) -> Iterator[Dict[str, torch.Tensor]]:
         it = iter(self.batches)
         try:
             nxt = self._launch(next(it))
