@@ -616,19 +616,23 @@ class KWClip_GeneralTransformer(KWClipBase):
         return {"cascaded_audio_feat": cascaded_audio_feat, "parallel_audio_feat": parallel_audio_feat, "vq_results": vq_results,
                 "keywords": keywords}
 
-    def precompute_towers(self, batch: dict, slot: int = 0) -> dict:
+    def precompute_towers(self, batch: dict, slot: int = 0, overlap: bool = True) -> dict:
         """Launch the two FROZEN towers for ``batch`` on the tower streams and return at once: ``{"audio": handle, "image_raw":
         tensor, "events": (audio_done, image_done)}``.  Passing the result as ``batch["_scb_towers"]`` makes ``forward`` skip the
         towers and wait for the events instead.  Every shipped configuration freezes both towers, so their outputs for batch
         i + 1 do not depend on the optimizer step of batch i: ``speechclip_b200.runtime.TowerPipeline`` uses this to run them under
-        the (latency-bound) head / loss / backward / all-reduce / Adam tail of the previous batch."""
+        the (latency-bound) head / loss / backward / all-reduce / Adam tail of the previous batch.  ``overlap=False`` runs both
+        towers on the current stream instead (per-kernel timing)."""
         image = batch["image"]
         dev = image.device
+        self.clip.update_device(self.device)
+        if not overlap:
+            frozen = self.audio_encoder.encode_frozen(batch["wav"], batch["wav_len"], slot=slot)
+            return {"audio": frozen, "image_raw": self.forward_image(image), "events": ()}
         cur = torch.cuda.current_stream(dev)
         sa, si = _side_stream(dev, "audio"), _side_stream(dev, "image")
         sa.wait_stream(cur)   # the inputs are ready (and earlier users of this slot's buffers are done) once `cur` gets here
         si.wait_stream(cur)
-        self.clip.update_device(self.device)
         with torch.cuda.stream(si):
             image_raw = self.forward_image(image)
             ev_i = torch.cuda.Event()

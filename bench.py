@@ -304,7 +304,12 @@ def run_own(args):
     overlap, kwclip_mod.OVERLAP_TOWERS = kwclip_mod.OVERLAP_TOWERS, False
     ops.PROFILE = []
     for _ in range(prof_steps):
-        step(resident)
+        if pipe is not None:   # same tower buffers as the timed steps (slot 1), both towers on this stream
+            b = dict(resident)
+            b["_scb_towers"] = model.precompute_towers(resident, slot=1, overlap=False)
+            step(b)
+        else:
+            step(resident)
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
     kwclip_mod.OVERLAP_TOWERS = overlap
@@ -441,6 +446,7 @@ def run_own(args):
                 "d2h_bytes_per_step": 4, "h2d_gb_per_s_measured": h2d_gbs, "numa_node_bound": numa_node, "passes_ms_per_step": [t[0] for t in passes],
                 "reported": "median pass", "fastest_pass_ms_per_step": min(t[0] for t in passes), "diagnostics": e2e_diag,
                 "loss_read": "every step's loss is copied to pinned host memory and read by the host one step late (after the next step is enqueued)"},
+        "hbm_peak_reserved_gb": torch.cuda.max_memory_reserved(dev) / 1e9,
         "gpu_launches": int(launches), "host_enqueue_ms_per_step": sorted(host_times)[len(host_times) // 2],
         "host_enqueue_ms_per_step_timed": host_ms,
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (scb_gemm)", "achieved": achieved, "peak": pk["tflops"],

@@ -160,6 +160,11 @@ class TowerPipeline:
         # the ``with`` block, and the stream context is per thread.  On exit (exhaustion, break or exception) the caller's own
         # stream is current again and ordered after everything the loop enqueued.
         dev = next(self.model.parameters()).device
+        # the parameters' AccumulateGrad nodes live on the stream of their first backward; autograd orders the streams itself and
+        # warns about the mismatch on every step otherwise
+        quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if quiet is not None:
+            quiet(False)
         outer = torch.cuda.current_stream(dev)
         hs = self.head_stream(dev)
         hs.wait_stream(outer)
