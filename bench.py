@@ -15,6 +15,7 @@ its CPU implementation of the path is the torch fp32 oracle (oracle/, a restatem
 modules): a bounded sample (16 pairs per step) of the same training step on the host cores.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -256,6 +257,14 @@ def run_own(args):
             torch.cuda.synchronize()
 
     def timed(fn, steps):
+        gc.collect()
+        gc.disable()   # a generation-2 collection inside a 100-400 ms timed region is a visible hiccup at 5-20 ms per step
+        try:
+            return _timed(fn, steps)
+        finally:
+            gc.enable()
+
+    def _timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
