@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SCB_ABI_VERSION 3
+#define SCB_ABI_VERSION 4
 
 enum { SCB_OK = 0, SCB_EINVAL = -1, SCB_ECUDA = -2, SCB_EUNSUPPORTED = -3 };
 enum { SCB_F32 = 0, SCB_F16 = 1, SCB_BF16 = 2 };
@@ -77,9 +77,14 @@ typedef struct scb_gemm_args {
   float alpha;
   int64_t residual_ld;           /* 0: residual shares out's ldc / batch stride (then the two below are ignored) */
   int64_t residual_batch_stride; /* may be 0 with residual_ld != 0: one [m_per_batch][n] table broadcast over the batch */
+  void* workspace;               /* optional: scb_gemm_workspace_bytes() of device memory, ZEROED once by the caller and then left to
+                                    the library, private to the stream the call runs on.  With it, a GEMM whose last wave of tiles
+                                    would leave most SMs idle splits those tiles along K over all SMs (stream-K tail); NULL: never */
+  int64_t workspace_bytes;
 } scb_gemm_args;
 
 int scb_gemm(const scb_gemm_args* args, void* stream);
+int64_t scb_gemm_workspace_bytes(void);
 
 /* ------------------------------------------------------------------------------------------------
  * fp32 SIMT contraction for the few hundred rows of the trainable head (CLS row of the parallel branch and

@@ -89,6 +89,8 @@ int scb_gemm(const scb_gemm_args* args, void* stream) {
   return scb::gemm(*args, ST);
 }
 
+int64_t scb_gemm_workspace_bytes(void) { return scb::gemm_workspace_bytes(); }
+
 int scb_sgemm(const float* a, int64_t a_rs, int64_t a_cs, const float* b, int64_t b_rs, int64_t b_cs, float* c, int64_t ldc, int32_t M,
               int32_t N, int32_t K, float alpha, float beta, void* stream) {
   return scb::sgemm(a, a_rs, a_cs, b, b_rs, b_cs, c, ldc, M, N, K, alpha, beta, ST);

@@ -7,6 +7,7 @@
 //
 // The two TMEM accumulator buffers let the epilogue of tile i overlap the MMAs of tile i+1.
 // See include/speechclip_b200.h (scb_gemm) for the operand model (plain / strided-conv / grouped tap walk).
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -35,6 +36,14 @@ __host__ __device__ constexpr bool tma_out(bool pair, int BN, int ACT, int RES, 
   return BN == 256 && ACT >= 0 && ((RES == 3 && ODT == SCB_F16) || (pair && ODT == SCB_F32 && RES == SCB_F16));
 }
 
+// stream-K workspace (scb_gemm_args.workspace): arrival counters, then one [2][128 x 256] fp32 slot per CTA pair
+constexpr int kSkFlagBytes = 4096;
+inline bool stream_k_applies(long long tiles, int pairs, int k_blocks) {
+  const long long rem = tiles % pairs;
+  // worth it when the last wave is at most 80 % full, and every pair's share of it is at least 2 k-blocks
+  return rem > 0 && rem * 5 <= (long long)pairs * 4 && rem * k_blocks >= 2LL * pairs;
+}
+
 struct GemmParams {
   int batch, m_tiles_per_batch, n_tiles, groups, num_tiles;
   int m_per_batch, n, k_blocks;
@@ -53,6 +62,11 @@ struct GemmParams {
   long long ldc, out_batch_stride;
   long long res_ld, res_batch_stride;
   int out_group_cols;
+  // stream-K tail of the CTA-pair kernel (sk_rem == 0: plain tile loop): every pair first takes sk_full whole tiles, then the
+  // sk_rem tiles of the last, partial wave are cut along K into one contiguous range of k-blocks per pair
+  int sk_full, sk_rem;
+  float* sk_part;  // [pairs][2 CTAs][128 x 256] fp32 partial accumulators of the ranges that do not start a tile
+  int* sk_flags;   // [sk_rem][2 CTAs] arrival counters (zero between launches: the owner resets them)
 };
 
 struct TileCoord {
@@ -562,7 +576,131 @@ __device__ __forceinline__ TileCoord decode_tile2(const GemmParams& p, int tile,
   return t;
 }
 
-template <int ACT, int RES, int ODT>
+// ---- stream-K tail.  A GEMM whose tile count is not a multiple of the number of CTA pairs leaves most SMs idle in its last
+// wave (HuBERT out-proj / fc2 at 32 utterances per GPU: 120 tiles on 74 pairs = 1.6 waves; CLIP ViT-B/32 fc2 at 256 images:
+// 150 tiles = 2.03 waves).  Here the tiles of that last wave are cut along K instead: pair w gets the k-block units
+// [w * UR / W, (w + 1) * UR / W) of the UR = sk_rem * k_blocks units, i.e. a piece of one tile and possibly the head of the
+// next.  The pair whose range STARTS a tile owns it: the others dump their fp32 accumulators to a workspace slot and bump
+// the tile's counter; the owner adds the partial sums into its TMEM accumulator (tcgen05.ld / add / tcgen05.st) and then runs
+// the ordinary epilogue unchanged.  All pairs reach their ranges at the same time (after their whole tiles) and all are
+// resident, so the owner's wait is short and cannot deadlock.
+template <bool SK>
+__device__ __forceinline__ bool sk_item(const GemmParams& p, int worker, int W, int i, int& tile, int& kb0, int& kb1) {
+  kb0 = 0;
+  kb1 = p.k_blocks;
+  if (!SK) {
+    tile = worker + i * W;
+    return tile < p.num_tiles;
+  }
+  if (i < p.sk_full) {
+    tile = worker + i * W;
+    return true;
+  }
+  const int UR = p.sk_rem * p.k_blocks;
+  const int u0 = (int)((long long)worker * UR / W), u1 = (int)((long long)(worker + 1) * UR / W);
+  if (u1 <= u0) return false;
+  const int r = u0 / p.k_blocks;
+  if (i == p.sk_full) {
+    tile = p.sk_full * W + r;
+    kb0 = u0 - r * p.k_blocks;
+    kb1 = min(p.k_blocks, kb0 + (u1 - u0));
+    return true;
+  }
+  if (i == p.sk_full + 1 && u1 > (r + 1) * p.k_blocks) {
+    tile = p.sk_full * W + r + 1;
+    kb1 = u1 - (r + 1) * p.k_blocks;
+    return true;
+  }
+  return false;
+}
+// pairs other than the owner that hold a piece of remainder tile r
+__device__ __forceinline__ int sk_partners(const GemmParams& p, int worker, int W, int r) {
+  const int UR = p.sk_rem * p.k_blocks;
+  const long long u_last = (long long)(r + 1) * p.k_blocks - 1;
+  return (int)(((u_last + 1) * W - 1) / UR) - worker;
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EpiCfg<256>::WARPS * 32) : "memory"); }
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Slot layout: [epilogue warp][16-column chunk][16-byte unit][lane] float4 — every warp store / load is 512 contiguous bytes.
+__device__ __forceinline__ void sk_dump(float* slot, int* flag, uint32_t tmem_base, int acc, uint32_t acc_phase, uint64_t* tfull_bar,
+                                        uint32_t tempty_addr, int warp, int lane) {
+  constexpr int BN = 256, COLS = EpiCfg<BN>::COLS;
+  const int q = warp & 3, part = (warp - 4) >> 2;
+  mbar_wait(tfull_bar, acc_phase);
+  tc_fence_after();
+  float4* dst = reinterpret_cast<float4*>(slot) + (size_t)(warp - 4) * (COLS / 16) * 4 * 32 + lane;
+#pragma unroll
+  for (int c = 0; c < COLS / 16; ++c) {
+    uint32_t v[16];
+    tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + part * COLS + c * 16), v);
+    tmem_ld_wait();
+    if (c == COLS / 16 - 1) {  // accumulator fully read by this warp: hand the buffer back to the MMA warp
+      tc_fence_before();
+      if (lane == 0) mbar_arrive_cluster(tempty_addr);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      __stcg(dst + (c * 4 + k) * 32, make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]), __uint_as_float(v[4 * k + 2]),
+                                                 __uint_as_float(v[4 * k + 3])));
+  }
+  epi_bar_sync();  // CTA-scope order of every warp's stores before the gpu-scope release below (cumulative)
+  if (warp == 4 && lane == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(flag) : "memory");
+}
+// slots: the workspace slot of the first partner (pairs worker + 1 ...), slot_stride floats apart
+__device__ __forceinline__ void sk_reduce(const float* slots, size_t slot_stride, int partners, int* flag, uint32_t tmem_base, int acc,
+                                          uint32_t acc_phase, uint64_t* tfull_bar, int warp, int lane) {
+  constexpr int BN = 256, COLS = EpiCfg<BN>::COLS;
+  const int q = warp & 3, part = (warp - 4) >> 2;
+  mbar_wait(tfull_bar, acc_phase);
+  tc_fence_after();
+  if (lane == 0) {
+    while (ld_acquire_gpu(flag) < partners) __nanosleep(64);
+  }
+  __syncwarp();
+  const float4* src = reinterpret_cast<const float4*>(slots) + (size_t)(warp - 4) * (COLS / 16) * 4 * 32 + lane;
+  // two 32-column halves; the partial sums of a half (8 x 16 bytes per lane per partner) are all requested before any is used
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    float4 s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = __ldcg(src + (h * 8 + i) * 32);
+    for (int pw = 1; pw < partners; ++pw) {
+      const float4* s4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + (size_t)pw * slot_stride);
+      float4 t[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t[i] = __ldcg(s4 + (h * 8 + i) * 32);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i].x += t[i].x; s[i].y += t[i].y; s[i].z += t[i].z; s[i].w += t[i].w;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + part * COLS + (h * 2 + c) * 16);
+      uint32_t v[16];
+      tmem_ld_32x16(taddr, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 a = s[c * 4 + k];
+        v[4 * k] = __float_as_uint(__uint_as_float(v[4 * k]) + a.x);
+        v[4 * k + 1] = __float_as_uint(__uint_as_float(v[4 * k + 1]) + a.y);
+        v[4 * k + 2] = __float_as_uint(__uint_as_float(v[4 * k + 2]) + a.z);
+        v[4 * k + 3] = __float_as_uint(__uint_as_float(v[4 * k + 3]) + a.w);
+      }
+      tmem_st_32x16(taddr, v);
+    }
+  }
+  tmem_st_wait();
+  epi_bar_sync();  // every epilogue warp is past its wait: the counter can go back to zero for the next launch
+  if (warp == 4 && lane == 0) *reinterpret_cast<volatile int*>(flag) = 0;
+}
+
+template <int ACT, int RES, int ODT, bool SK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<BN2>::THREADS, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
@@ -617,10 +755,11 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ------------------------------------------------------------------ TMA producer (both CTAs)
     int stage_i = 0;
     uint32_t phase = 0;
-    for (int tile = pair; tile < p.num_tiles; tile += num_pairs) {
+    int tile, kb0, kb1;
+    for (int it = 0; sk_item<SK>(p, pair, num_pairs, it, tile, kb0, kb1); ++it) {
       const TileCoord t = decode_tile2(p, tile, (int)rank);
       const int a_c0 = p.a_col0 + t.g * p.a_group_cols;
-      for (int kb = 0; kb < p.k_blocks; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty[stage_i], phase ^ 1u);
         const uint32_t full_leader = mapa_u32(smem_u32(&full[stage_i]), 0);
         if (leader) mbar_expect_tx(&full[stage_i], 2u * (uint32_t)(A_BYTES + B_BYTES));
@@ -642,19 +781,20 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = pair; tile < p.num_tiles; tile += num_pairs) {
+    int tile, kb0, kb1;
+    for (int it = 0; sk_item<SK>(p, pair, num_pairs, it, tile, kb0, kb1); ++it) {
       mbar_wait(&tempty[acc], acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN2);
-      for (int kb = 0; kb < p.k_blocks; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full[stage_i], phase);
         tc_fence_after();
         const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(sA + stage_i * A_BYTES));
         const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(sB + stage_i * B_BYTES));
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
-          if (tf32) tc_mma_tf32_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
-          else tc_mma_f16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          if (tf32) tc_mma_tf32_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)(((kb - kb0) | k) != 0));
+          else tc_mma_f16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)(((kb - kb0) | k) != 0));
         }
         tc_commit_2sm(&empty[stage_i], 3);
         if (++stage_i == STAGES) {
@@ -670,8 +810,23 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ------------------------------------------------------------------ epilogue (both CTAs; drains report to the leader)
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = pair; tile < p.num_tiles; tile += num_pairs) {
+    constexpr size_t kSlot = (size_t)BM * BN2;  // floats per CTA slot; a pair's two slots are adjacent
+    int tile, kb0, kb1;
+    for (int it = 0; sk_item<SK>(p, pair, num_pairs, it, tile, kb0, kb1); ++it) {
       const TileCoord t = decode_tile2(p, tile, (int)rank);
+      if (SK && kb0 != 0) {  // a range that does not start its tile: partial sums to the workspace, the owner finishes the tile
+        const int r = tile - p.sk_full * num_pairs;
+        sk_dump(p.sk_part + ((size_t)pair * 2 + rank) * kSlot, p.sk_flags + r * 2 + (int)rank, tmem_base, acc, acc_phase, &tfull[acc],
+                mapa_u32(smem_u32(&tempty[acc]), 0), warp, lane);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+        continue;
+      }
+      if (SK && kb1 != p.k_blocks) {  // owner of a tile whose tail other pairs computed
+        const int r = tile - p.sk_full * num_pairs;
+        sk_reduce(p.sk_part + ((size_t)(pair + 1) * 2 + rank) * kSlot, 2 * kSlot, sk_partners(p, pair, num_pairs, r),
+                  p.sk_flags + r * 2 + (int)rank, tmem_base, acc, acc_phase, &tfull[acc], warp, lane);
+      }
       if constexpr (TMAO && ODT == SCB_F32) epilogue_tile_tma_res<RES>(p, &tmO, t, tmem_base, acc, acc_phase, &tfull[acc], mapa_u32(smem_u32(&tempty[acc]), 0), epi, warp, lane);
       else if constexpr (TMAO) epilogue_tile_tma<ACT>(p, &tmO, t, tmem_base, acc, acc_phase, &tfull[acc], mapa_u32(smem_u32(&tempty[acc]), 0), epi, warp, lane);
       else epilogue_tile<BN2, ACT, RES, ODT>(p, t, tmem_base, acc, acc_phase, &tfull[acc], mapa_u32(smem_u32(&tempty[acc]), 0), stage, warp, lane);
@@ -689,23 +844,28 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
-template <int ACT, int RES, int ODT>
-int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p, cudaStream_t stream) {
+template <int ACT, int RES, int ODT, bool SK>
+int launch2_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p, cudaStream_t stream) {
   constexpr bool TMAO = tma_out(true, BN2, ACT, RES, ODT);
   constexpr int smem_bytes = stages2(TMAO) * (BM * BK * 2 + (BN2 / 2) * BK * 2) + 1024 + 256 +
                              (TMAO ? EpiCfg<BN2>::TMA_BYTES : EpiCfg<BN2>::PATCH_BYTES);
   static_assert(smem_bytes <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
   static bool configured = false;
   if (!configured) {
-    SCB_CUDA(cudaFuncSetAttribute(gemm2_tcgen05_kernel<ACT, RES, ODT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    SCB_CUDA(cudaFuncSetAttribute(gemm2_tcgen05_kernel<ACT, RES, ODT, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = true;
   }
   int pairs = num_sms() / 2;
-  if (p.num_tiles < pairs) pairs = p.num_tiles;
-  SCB_CUDA(launch_pdl(gemm2_tcgen05_kernel<ACT, RES, ODT>, dim3((unsigned)(2 * pairs)), EpiCfg<BN2>::THREADS, smem_bytes, stream, tmA, tmB, tmO, p));
+  if (p.num_tiles < pairs && !SK) pairs = p.num_tiles;
+  SCB_CUDA(launch_pdl(gemm2_tcgen05_kernel<ACT, RES, ODT, SK>, dim3((unsigned)(2 * pairs)), EpiCfg<BN2>::THREADS, smem_bytes, stream, tmA, tmB, tmO, p));
   note_launch();
   SCB_LAUNCH_OK("gemm2_tcgen05");
   return SCB_OK;
+}
+// the stream-K variant is a separate instantiation: its dump / reduce paths cost the plain kernel neither registers nor branches
+template <int ACT, int RES, int ODT>
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p, cudaStream_t stream) {
+  return p.sk_rem ? launch2_impl<ACT, RES, ODT, true>(tmA, tmB, tmO, p, stream) : launch2_impl<ACT, RES, ODT, false>(tmA, tmB, tmO, p, stream);
 }
 
 template <int BN, int STAGES, int ACT = -1, int RES = -1, int ODT = -1>
@@ -726,6 +886,8 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
 }
 
 }  // namespace
+
+long long gemm_workspace_bytes() { return kSkFlagBytes + (long long)(num_sms() / 2) * 2 * BM * 256 * (long long)sizeof(float); }
 
 int gemm(const scb_gemm_args& a, cudaStream_t stream) {
   SCB_CHECK(a.a && a.b && a.out, SCB_EINVAL, "scb_gemm: null operand");
@@ -760,6 +922,8 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
   // 256-row super tiles pad 17 %)
   const bool two_ok = two_env != 0 && a.n > 128 && a.m_per_batch >= 256 && (a.tap_row_shift == 0 || a.m_per_batch >= 2048);
   const int bn_max = a.n > 128 ? 256 : (a.n > 64 ? 128 : 64);
+  static const int sk_env = [] { const char* e = getenv("SCB_GEMM_STREAMK"); return e ? atoi(e) : 1; }();
+  const bool sk_ok = sk_env != 0 && a.workspace != nullptr && a.workspace_bytes >= gemm_workspace_bytes();
   int bn = bn_max;
   bool two = false;
   {
@@ -772,13 +936,17 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
       if (cand == 3 && !two_ok) continue;
       const long long tiles = (cand == 3 ? mt2 : mt1) * ((a.n + cbn - 1) / cbn);
       const int slots = cand == 3 ? sms / 2 : sms;
-      const long long waves = (tiles + slots - 1) / slots;
-      const double active = (double)(tiles < slots ? tiles : slots) * (cand == 3 ? 2 : 1);
+      double waves = (double)((tiles + slots - 1) / slots);
+      double active = (double)(tiles < slots ? tiles : slots) * (cand == 3 ? 2 : 1);
+      if (cand == 3 && sk_ok && stream_k_applies(tiles, slots, kb)) {  // the last wave is cut along K over all pairs
+        waves = (double)(tiles / slots) + (double)(tiles % slots) / slots + 0.35;  // + dump / reduce of the split tiles
+        active = sms;
+      }
       const double bw = fmin(64.0, 8500.0 / active);                                   // bytes per clock per CTA
       const double bytes = (cand == 3 ? (BM + 128) : (BM + cbn)) * 128.0;             // per CTA per k-block
       const double mma = cbn * 2.0;                                                    // 128 x BN x 64 MACs at 4096 MAC / clk
       // (64-wide tiles measured ~1.6x slower per k-block than their byte count predicts)
-      const double t = 2000.0 + (double)waves * (kb * fmax(mma, (cbn == 64 ? 1.6 : 1.0) * bytes / bw) + 600.0) + cbn * 8.0;  // fill + main loops + last epilogue
+      const double t = 2000.0 + waves * (kb * fmax(mma, (cbn == 64 ? 1.6 : 1.0) * bytes / bw) + 600.0) + cbn * 8.0;  // fill + main loops + last epilogue
       if (t < best) {
         best = t;
         bn = cbn;
@@ -803,6 +971,17 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
   p.tap_row_shift = a.tap_row_shift;
   p.a_col0 = a.a_col0;
   p.a_group_cols = a.a_group_cols;
+  if (two && sk_ok && stream_k_applies(p.num_tiles, num_sms() / 2, p.k_blocks)) {
+    const int W = num_sms() / 2;
+    p.sk_full = p.num_tiles / W;
+    p.sk_rem = p.num_tiles % W;
+    p.sk_flags = static_cast<int*>(a.workspace);
+    p.sk_part = reinterpret_cast<float*>(static_cast<uint8_t*>(a.workspace) + kSkFlagBytes);
+  }
+  static const int dbg_env = [] { const char* e = getenv("SCB_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
+  if (dbg_env)
+    fprintf(stderr, "scb_gemm m=%d x%d n=%d k=%d: bn=%d pair=%d tiles=%d stream-k full=%d rem=%d\n", a.m_per_batch, a.batch, a.n, a.k, bn,
+            (int)two, p.num_tiles, p.sk_full, p.sk_rem);
   p.umma_n = two ? 128 : ((a.n < bn ? a.n : bn) + 15) / 16 * 16;  // rows of the B box (cta_group::2: half of the 256-wide tile per CTA)
   p.slab = (!two && eb == 2 && bn == 64 && a.kb_per_tap == 1 && a.tap_row_shift == 1 && p.k_blocks + BM - 1 <= 256) ? 1 : 0;
   p.slab_sub_bytes = p.umma_n * BK * 2;  // 48 x 128 B = 6 KB (base) / 8 KB (large): multiples of the 1024-byte swizzle atom

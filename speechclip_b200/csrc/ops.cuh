@@ -5,6 +5,7 @@
 namespace scb {
 // gemm_tcgen05.cu
 int gemm(const scb_gemm_args& a, cudaStream_t stream);
+long long gemm_workspace_bytes();
 // loss.cu
 int sgemm(const float* a, long long a_rs, long long a_cs, const float* b, long long b_rs, long long b_cs, float* c, long long ldc, int M, int N,
           int K, float alpha, float beta, cudaStream_t st);

@@ -53,6 +53,7 @@ class Workspace:
 HIDDEN16 = os.environ.get("SCB_HIDDEN_FP32", "0") != "1"   # post-LN towers: fp16 hidden states / residual stream (see HubertPlan._forward)
 LAYER_CHUNKS = int(os.environ.get("SCB_LAYER_CHUNKS", "1"))   # batch slices for the transformer layer stack (L2 residency)
 GRAPHS = os.environ.get("SCB_CUDA_GRAPHS", "1") != "0"   # replay the frozen towers as CUDA graphs (launch-bound at small batch)
+STREAM_K = os.environ.get("SCB_GEMM_STREAMK", "0") == "1"   # pass the stream-K workspace to the layer GEMMs (see EncoderLayerPlan.forward)
 MAX_GRAPHS = 4                                            # per plan; further input shapes run eagerly
 
 
@@ -154,26 +155,33 @@ class EncoderLayerPlan:
         ctx = ws.view(tag + "ctx", (B, T, d), H)
         ffn = ws.view(tag + "ffn", (M, self.ffn), H)
         a16 = ws.view(tag + "a16", (M, d), H)
+        # Stream-K scratch of the four GEMMs (zeroed at allocation, then owned by the library; one per launching stream, because
+        # the two towers share a workspace and run concurrently).  OFF by default: measured on B200 (tools/streamk_bench.py,
+        # profiles/r2_streamk_bench.txt) the split tiles' extra dump + reduce pass costs more than the idle tail of the last wave
+        # on every shape of this model (HuBERT fc2 at 32 utterances: 48 -> 61 us; no change at 256).
+        sk = None
+        if STREAM_K:
+            sk = ws.get(f"gemm_sk_{torch.cuda.current_stream().cuda_stream}", ops.gemm_workspace_bytes(), torch.uint8, zero=True)
         if self.pre_ln:
             ops.layernorm(x32, *self.ln1, y16=a16, rows=M, d=d, eps=self.eps)
             src16 = a16
         else:
             src16 = x16
-        ops.gemm(src16, self.wqkv, bias=self.bqkv, out=qkv.view(M, 3 * d))
+        ops.gemm(src16, self.wqkv, bias=self.bqkv, out=qkv.view(M, 3 * d), scratch=sk)
         ops.attention(qkv[:, :, 0:d], qkv[:, :, d:2 * d], qkv[:, :, 2 * d:3 * d], ctx, self.heads, hd ** -0.5, kv_len, causal)
         if self.pre_ln:
             xa = ws.view(tag + "xa", (M, d), torch.float32)
-            ops.gemm(ctx.view(M, d), self.wo, bias=self.bo, residual=x32, out=xa)
+            ops.gemm(ctx.view(M, d), self.wo, bias=self.bo, residual=x32, out=xa, scratch=sk)
             ops.layernorm(xa, *self.ln2, y16=a16, rows=M, d=d, eps=self.eps)
-            ops.gemm(a16, self.w1, bias=self.b1, act=self.act, out=ffn)
-            ops.gemm(ffn, self.w2, bias=self.b2, residual=xa, out=out32)
+            ops.gemm(a16, self.w1, bias=self.b1, act=self.act, out=ffn, scratch=sk)
+            ops.gemm(ffn, self.w2, bias=self.b2, residual=xa, out=out32, scratch=sk)
             return None
         y = ws.view(tag + "y", (M, d), torch.float32)
         x1 = ws.view(tag + "x1", (M, d), torch.float32) if x32 is not None else None
-        ops.gemm(ctx.view(M, d), self.wo, bias=self.bo, residual=x32 if x32 is not None else x16, out=y)
+        ops.gemm(ctx.view(M, d), self.wo, bias=self.bo, residual=x32 if x32 is not None else x16, out=y, scratch=sk)
         ops.layernorm(y, *self.ln1, y32=x1, y16=a16, rows=M, d=d, eps=self.eps)
-        ops.gemm(a16, self.w1, bias=self.b1, act=self.act, out=ffn)
-        ops.gemm(ffn, self.w2, bias=self.b2, residual=x1 if x1 is not None else a16, out=y)
+        ops.gemm(a16, self.w1, bias=self.b1, act=self.act, out=ffn, scratch=sk)
+        ops.gemm(ffn, self.w2, bias=self.b2, residual=x1 if x1 is not None else a16, out=y, scratch=sk)
         o16 = out16 if out16 is not None else (ws.view(tag + "o16", (M, d), H) if want_x16 else None)
         ops.layernorm(y, *self.ln2, y32=out32, y16=o16, rows=M, d=d, eps=self.eps)
         return o16

@@ -79,6 +79,7 @@ class GemmArgs(ctypes.Structure):
         ("residual_dtype", ctypes.c_int32), ("act", ctypes.c_int32),
         ("alpha", ctypes.c_float),
         ("residual_ld", ctypes.c_int64), ("residual_batch_stride", ctypes.c_int64),
+        ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_int64),
     ]
 
 
@@ -93,6 +94,8 @@ def _declare(lib):
     lib.scb_launch_count.restype = i64
     lib.scb_conv0_scratch_bytes.restype = i64
     lib.scb_conv0_scratch_bytes.argtypes = [i32]
+    lib.scb_gemm_workspace_bytes.restype = i64
+    lib.scb_gemm_workspace_bytes.argtypes = []
     lib.scb_infonce_scratch_bytes.restype = i64
     lib.scb_infonce_scratch_bytes.argtypes = [i32]
     sig = {
@@ -157,7 +160,7 @@ def _declare(lib):
         fn.restype = i32
 
 
-EXPORTS = ["scb_abi_version", "scb_last_error", "scb_launch_count", "scb_conv0_scratch_bytes", "scb_infonce_scratch_bytes",
+EXPORTS = ["scb_abi_version", "scb_last_error", "scb_launch_count", "scb_conv0_scratch_bytes", "scb_gemm_workspace_bytes", "scb_infonce_scratch_bytes",
            "scb_gemm", "scb_sgemm", "scb_attention_fwd", "scb_cls_attention_fwd", "scb_cls_attention_bwd", "scb_frame_lengths",
            "scb_lengths_to_i32", "scb_wav_prepare", "scb_conv0_groupnorm_gelu", "scb_conv0_layernorm_gelu", "scb_posconv_pack", "scb_patchify",
            "scb_broadcast_row", "scb_cast_rows", "scb_transpose", "scb_layernorm_fwd", "scb_layernorm_bwd", "scb_l2norm_fwd",

@@ -58,8 +58,9 @@ def gemm_raw(*, a: torch.Tensor, a_inner: int, a_rows: int, a_row_stride: int, a
              out2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
              residual: Optional[torch.Tensor] = None, residual_ld: int = 0, residual_batch_stride: int = 0,
              act: int = ACT_NONE, alpha: float = 1.0, a_offset: int = 0, out_offset: int = 0, residual_offset: int = 0,
-             algo_k: Optional[int] = None):
+             algo_k: Optional[int] = None, scratch: Optional[torch.Tensor] = None):
     """Full operand model of scb_gemm (plain / strided-conv / grouped tap walk); offsets are in elements.
+    scratch: `gemm_workspace_bytes()` of zero-initialised device memory private to the launching stream (stream-K tail).
     algo_k: the ALGORITHMIC contraction length when k carries zero padding (pos-conv groups padded 48 -> 64 channels)."""
     global _FLOPS, _SHAPE
     if PROFILE is not None:
@@ -89,13 +90,26 @@ def gemm_raw(*, a: torch.Tensor, a_inner: int, a_rows: int, a_row_stride: int, a
         g.residual_dtype = _DT[residual.dtype]
         g.residual_ld, g.residual_batch_stride = residual_ld, residual_batch_stride
     g.act, g.alpha = act, alpha
+    if scratch is not None:
+        g.workspace, g.workspace_bytes = scratch.data_ptr(), scratch.numel() * scratch.element_size()
     _call("scb_gemm", ctypes.byref(g))
     return out
 
 
+_GEMM_WS_BYTES = None
+
+
+def gemm_workspace_bytes() -> int:
+    global _GEMM_WS_BYTES
+    if _GEMM_WS_BYTES is None:
+        _GEMM_WS_BYTES = int(_l.load().scb_gemm_workspace_bytes())
+    return _GEMM_WS_BYTES
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
          residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-         out_dtype: torch.dtype = torch.float16, out2: Optional[torch.Tensor] = None, alpha: float = 1.0) -> torch.Tensor:
+         out_dtype: torch.dtype = torch.float16, out2: Optional[torch.Tensor] = None, alpha: float = 1.0,
+         scratch: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,N] = act(alpha * a[M,K] @ w[N,K]^T + bias) + residual   (a, w 16-bit; fp32 accumulate on tcgen05)."""
     assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1] and a.stride(1) == 1 and w.stride(1) == 1
     M, K = a.shape
@@ -110,7 +124,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         assert residual.shape == out.shape and residual.stride(1) == 1
         res_ld = residual.stride(0)
     return gemm_raw(a=a, a_inner=K, a_rows=M, a_row_stride=a.stride(0), m_per_batch=M, w=w, n=N, k=K, b_row_stride=w.stride(0),
-                    out=out, ldc=out.stride(0), out2=out2, bias=bias, residual=residual, residual_ld=res_ld, act=act, alpha=alpha)
+                    out=out, ldc=out.stride(0), out2=out2, bias=bias, residual=residual, residual_ld=res_ld, act=act, alpha=alpha,
+                    scratch=scratch)
 
 
 def sgemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, alpha: float = 1.0, beta: float = 0.0):

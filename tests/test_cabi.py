@@ -27,7 +27,7 @@ def test_library_builds_and_exports_header_symbols():
 
 def test_abi_version_and_error_plumbing():
     so = lib.load()
-    assert so.scb_abi_version() == 3
+    assert so.scb_abi_version() == 4
     assert so.scb_launch_count() >= 0
     # argument validation happens before any CUDA call: a NULL args struct is rejected with a message
     assert so.scb_gemm(None, None) == -1

@@ -144,3 +144,38 @@ def test_gemm_tma_store_residual_epilogue(res_dtype, M, N, K, bias):
         ops.gemm(a, w, bias=b, residual=buf, out=buf, alpha=0.5)
         torch.cuda.synchronize()
         assert (buf - ref).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("M,N,K,act,out_dtype,res_dtype", [
+    (10208, 768, 3072, 0, torch.float32, torch.float16),   # HuBERT fc2 at 32 utterances: 120 tile pairs on 74 SM pairs
+    (10208, 768, 768, 0, torch.float32, torch.float16),    # out-proj
+    (10208, 3072, 768, 1, torch.float16, None),            # fc1 (6.49 waves), GELU + TMA store
+    (1600, 768, 3072, 0, torch.float32, torch.float32),    # CLIP ViT-B/32 fc2 at 32 images: 21 tile pairs -> every tile cut in ~3.5
+    (1600, 3072, 768, 2, torch.float16, None),
+    (12800, 768, 3072, 0, torch.float32, torch.float32),   # ViT fc2 at 256 images: 150 tile pairs = 2.03 waves
+    (1000, 520, 4096, 0, torch.float32, None),             # ragged M / N edges inside split tiles, generic epilogue
+])
+def test_gemm_stream_k_tail(M, N, K, act, out_dtype, res_dtype):
+    """With a workspace the CTA-pair kernel cuts the tiles of its last, partial wave along K over all SM pairs; partial sums
+    meet in the owner's TMEM accumulator.  Same result as without (up to fp32 summation order), repeated launches through
+    the same workspace stay correct (the arrival counters are reset by the owners), and the workspace tail is not overrun."""
+    from speechclip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).half()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).half()
+    b = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g).to(res_dtype) if res_dtype else None
+    nb = ops.gemm_workspace_bytes()
+    scratch = torch.zeros(nb + 4096, device="cuda", dtype=torch.uint8)
+    scratch[nb:] = 0x5A
+    ref = _ref(a, w, b, act, res, 0.5)
+    plain = ops.gemm(a, w, bias=b, act=act, residual=res, out_dtype=out_dtype, alpha=0.5)
+    tol = 2e-3 if out_dtype == torch.float32 else 8e-3
+    for _ in range(3):
+        out = torch.full((M, N), 9.0, device="cuda", dtype=out_dtype)
+        ops.gemm(a, w, bias=b, act=act, residual=res, out=out, alpha=0.5, scratch=scratch[:nb])
+        torch.cuda.synchronize()
+        assert (out.float() - ref).abs().max().item() < tol
+        assert (out.float() - plain.float()).abs().max().item() < (1e-4 if out_dtype == torch.float32 else 4e-3)
+        assert (scratch[:4096] == 0).all()      # counters back to zero
+    assert (scratch[nb:] == 0x5A).all()
