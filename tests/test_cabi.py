@@ -41,5 +41,5 @@ def test_gemm_args_struct_matches_header_layout():
     n_fields = len(re.findall(r"\b(?:a|a_inner|a_rows|a_row_stride|a_batch_stride|batch|m_per_batch|kb_per_tap|tap_row_shift|a_col0|"
                               r"a_group_cols|b|b_row_stride|b_group_stride|n|k|groups|out|out_dtype|out_group_cols|ldc|"
                               r"out_batch_stride|out2|out2_dtype|ab_format|bias|residual|residual_dtype|act|alpha|residual_ld|"
-                              r"residual_batch_stride)\s*[;,]", body))
-    assert n_fields == len(lib.GemmArgs._fields_) == 32
+                              r"residual_batch_stride|workspace|workspace_bytes)\s*[;,]", body))
+    assert n_fields == len(lib.GemmArgs._fields_) == 34
