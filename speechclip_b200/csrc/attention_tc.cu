@@ -8,18 +8,23 @@
 // (columns [0, H) and [H, 2H)); O lives in columns [320, 384):
 //   MMA thread       S_h = Q K_h^T        tcgen05.mma 128 x H x 64                          -> s_full[h]
 //   16 softmax warps two passes over their H/4-column slice of S_h straight from TMEM (tcgen05.ld): row max (exchanged between the
-//                    4 warps of a lane quarter), then exp2, 16-bit P into the K-major 128B-swizzled shared-memory operand and
-//                    row sums                                                                  -> s_free[h], p_full[h]
+//                    4 warps of a lane quarter), then exp2 (scale / offset on packed fma.f32x2) and 16-bit P into the K-major
+//                    128B-swizzled shared-memory operand                                       -> s_free[h], p_full[h]
 //   MMA thread       O (+)= P_h V_h        tcgen05.mma 128 x 64 x H, V as the MN-major B operand (no transposed copy of V)
+//                    ... as ONE 128 x 80 x 16 MMA per key step: the B operand's second 64-column atom (descriptor LBO) is a tile
+//                    of ones, so columns [64, 80) of the accumulator are the ROW SUMS of exactly the 16-bit P that multiplies
+//                    V — the softmax warps neither add up their exponentials nor exchange partial sums (2 of their ~5
+//                    instructions per element), and P is read from shared memory once
 // so that while the softmax warps work on one half the tensor pipe computes S of the other half / of the next query tile and the
 // P V of the previous half: the softmax warps never wait for an MMA in steady state, and the kernel runs at the rate of its
 // exponentials (MUFU) instead of the sum of all phases (round 1: one 320-column S, every phase serial, 17 % tensor pipe).
 // The two halves share one running row maximum: half 1 keeps the maximum of half 0 unless its own maximum is more than 2^8 above
-// it (P <= 256 is harmless in 16 bits; softmax is shift-invariant), in which case — rare — the warps rescale O and the partial
-// row sum in place (tcgen05.ld / st) before P V of half 1 is issued.
+// it (P <= 256 is harmless in 16 bits; softmax is shift-invariant), in which case — rare — the warps rescale O and the row
+// sums in place (tcgen05.ld / st) before P V of half 1 is issued.
 // O of a tile is drained (divided by the row sum, packed, stored) inside the NEXT tile, also across items.  Query quarters
 // (32 rows) that lie entirely beyond Tq skip all softmax work (T = 319: 2 of the 12 quarters of an item).
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "ops.cuh"
@@ -27,12 +32,18 @@
 namespace scb {
 #ifdef SCB_ATTN_TRACE
 __device__ long long g_attn_trace[64 * 16];
+__device__ long long g_attn_trace_w[32 * 16 * 4];   // [tile][softmax warp][s_full passed / p_full arrive, per half]
 #define ATTN_TRACE(cond, tile, slot) do { if ((cond) && blockIdx.x == 0 && (tile) < 64 && (tile) >= 0) g_attn_trace[(tile) * 16 + (slot)] = clock64(); } while (0)
+#define ATTN_TRACE_W(tile, w, slot) do { if (blockIdx.x == 0 && (tile) < 32 && (threadIdx.x & 31) == 0) g_attn_trace_w[((tile) * 16 + (w)) * 4 + (slot)] = clock64(); } while (0)
 extern "C" int scb_debug_attn_trace(long long* host_out) {
   return (int)cudaMemcpyFromSymbol(host_out, g_attn_trace, sizeof(g_attn_trace));
 }
+extern "C" int scb_debug_attn_trace_w(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_attn_trace_w, sizeof(g_attn_trace_w));
+}
 #else
 #define ATTN_TRACE(cond, tile, slot) do { } while (0)
+#define ATTN_TRACE_W(tile, w, slot) do { } while (0)
 #endif
 namespace {
 
@@ -41,16 +52,25 @@ constexpr int BQ = 128;
 constexpr int MAX_NK = 320;
 constexpr int MAX_QT = 3;                       // query tiles resident per item (Tq <= 384)
 constexpr int O_COL = 320;                      // TMEM column of the O accumulator
+constexpr int L_COL = O_COL + HD;               // TMEM columns [384, 400): row sums of P (every column holds the same sum)
+constexpr int ONES_BYTES = 64 * 128;            // second MN atom of the P V B operand: 64 key rows x 128 B of ones (all elements equal, so
+                                                // the swizzle does not matter); reached from every V block through the descriptor's LBO
 constexpr int kSoftmaxWarps = 16;                // 4 per TMEM lane quarter, each owning H/4 key columns of a half
-constexpr int kCtrlWarps = 2;                    // warp 0: TMA producer (+ TMEM alloc), warp 1: MMA issuer; then the softmax warps
-constexpr int kThreads = (kCtrlWarps + kSoftmaxWarps) * 32;
+// Warp roles.  A warp's scheduler is warp % 4 and so is the TMEM lane quarter it may read, so the 4 softmax warps of a row quarter
+// share one scheduler with each other and with whatever control warp has the same index mod 4.  Measured (per-warp trace): the
+// quarter that shares its scheduler with the MMA-issuing warp runs ~800 clocks per tile (11 %) behind the others — the 28
+// tcgen05.mma / commit dispatches and barrier polls of a tile are not free for their scheduler — and the slowest quarter sets the
+// pace (P V waits for all 16 warps).  The control warps therefore sit on schedulers 2 and 3: the quarters 2 and 3 have no rows in
+// the last, partial query tile of an item (T = 319: 63 rows), i.e. a third less softmax work than quarters 0 and 1.
+constexpr int kMmaWarp = 18, kProducerWarp = 19;   // warps 16 and 17 are idle fillers (exit at once)
+constexpr int kThreads = 20 * 32;   // (registers are allocated per 4 warps: 18 warps get the same 96-register cap as 20)
 constexpr int K_BYTES = MAX_NK * 128;           // 40 KB
 constexpr int V_BYTES = MAX_NK * 128;           // 40 KB (5 key blocks of 64 rows x 128 B)
 constexpr int Q_BYTES = MAX_QT * BQ * 128;      // 48 KB
 constexpr int P_BYTES = (MAX_NK / 64) * BQ * 128;  // 80 KB (5 k-blocks of [128 x 64]; half h owns the keys [h H, h H + H))
-constexpr int RED_FLOATS = 3 * 4 * BQ;          // row max of half 0 / half 1, row sums: [4 column parts][128 rows] each
-constexpr int COLD_BYTES = kSoftmaxWarps * 32 * 16;   // per softmax thread: the pending tile's (item, tile, 1 / row sum)
-constexpr int SMEM_BYTES = K_BYTES + V_BYTES + Q_BYTES + P_BYTES + RED_FLOATS * 4 + COLD_BYTES + 256 + 1024;  // 256: mbarriers + TMEM slot
+constexpr int RED_FLOATS = 2 * 4 * BQ;          // row max of half 0 / half 1: [4 column parts][128 rows] each
+constexpr int COLD_BYTES = kSoftmaxWarps * 32 * 8;    // per softmax thread: the pending tile's output row pointer (bit 63: quarter is live)
+constexpr int SMEM_BYTES = K_BYTES + V_BYTES + Q_BYTES + P_BYTES + ONES_BYTES + RED_FLOATS * 4 + COLD_BYTES + 256 + 1024;  // 256: mbarriers + TMEM slot
 constexpr float kRescaleLog2 = 8.f;             // half 1 keeps half 0's row maximum unless its own is > 2^8 above it
 
 struct AttnTcParams {
@@ -87,7 +107,13 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 // kind::f16 instruction descriptor with an MN-major B operand (bit 16)
-__device__ __forceinline__ uint32_t idesc_pv(int fmt) { return umma_idesc_f16(BQ, HD, fmt) | (1u << 16); }
+// (N = 64 head dims + 16 columns of row sums)
+__device__ __forceinline__ uint32_t idesc_pv(int fmt) { return umma_idesc_f16(BQ, HD + 16, fmt) | (1u << 16); }
+// MN-major SWIZZLE_128B operand whose MN extent exceeds one 64-element atom: LBO = byte distance to the next atom along MN
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = umma_desc_kmajor_sw128(smem_addr) & ~((uint64_t)0x3FFF << 16);
+  return d | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
 
 // NCH = NK / 64 (1..5): compile-time so that every S slice has a static register footprint
 template <bool BF16, int NCH>
@@ -104,9 +130,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sV = sK + K_BYTES;
   uint8_t* sQ = sV + V_BYTES;
   uint8_t* sP = sQ + Q_BYTES;
-  float* red_max = reinterpret_cast<float*>(sP + P_BYTES);  // [half][4 column parts][128 rows]
-  float* red_sum = red_max + 2 * 4 * BQ;                    // [4 column parts][128 rows]
-  int4* cold = reinterpret_cast<int4*>(red_sum + 4 * BQ);   // [softmax thread]
+  uint8_t* sOnes = sP + P_BYTES;                             // 1024-aligned (every region above is a multiple of 1 KB)
+  float* red_max = reinterpret_cast<float*>(sOnes + ONES_BYTES);  // [half][4 column parts][128 rows]
+  uint2* cold = reinterpret_cast<uint2*>(red_max + 2 * 4 * BQ);   // [softmax thread]
   uint64_t* bars = reinterpret_cast<uint64_t*>(cold + kSoftmaxWarps * 32);
   uint64_t* kq_full = bars + 0;     // K and every Q tile of the item have landed
   uint64_t* kq_empty = bars + 1;    // every S MMA of the item has retired: K and Q may be overwritten
@@ -120,12 +146,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == kMmaWarp && lane == 0) {
     mbar_init(kq_full, 1);
     mbar_init(kq_empty, 1);
     mbar_init(v_full, 1);
@@ -139,7 +165,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(o_empty, kSoftmaxWarps);
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  if (warp == kProducerWarp) tmem_alloc<512>(tmem_slot);
+  for (int i = threadIdx.x; i < ONES_BYTES / 4; i += kThreads) reinterpret_cast<uint32_t*>(sOnes)[i] = BF16 ? 0x3F803F80u : 0x3C003C00u;
+  fence_proxy_async();  // the tensor core reads the tile through the async proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -148,7 +176,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   griddep_launch_dependents();
   const int n_items = p.batch * p.heads;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     // ------------------------------------------------------------------ producer
     // K and Q of the NEXT item are loaded as soon as the last S of the current item has retired (kq_empty), i.e. while its last
     // query tile is still in the softmax / P V phases; V follows once the last P V has retired (item_empty).
@@ -165,7 +193,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int kb = 0; kb < NCH; ++kb) tma_load_3d(sV + kb * 64 * 128, &tmV, v_full, h * HD, kb * 64, b);
       ph ^= 1u;
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == kMmaWarp && lane == 0) {
     // ------------------------------------------------------------------ MMA issuer
     const int fmt = BF16 ? 1 : 0;
     const uint32_t idesc_s = umma_idesc_f16(BQ, H, fmt);
@@ -181,13 +209,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     };
     // O (+)= P_h V_h: H / 16 k-steps of 16 keys; key kk lives in block kk / 64 of P (K-major, 32 B per step inside the 128-byte
     // row) and of V (MN-major: 16 rows per step)
-    auto issue_pv = [&](int h) __attribute__((always_inline)) {
-#pragma unroll 1
+    // (fully unrolled with a compile-time half: every descriptor is base + constant.  The issuing thread shares its scheduler with
+    // four busy softmax warps, so each dependent integer instruction in front of an MMA costs several issue rounds: with the
+    // descriptors recomputed per step the 10 MMAs of a half took ~1900 clocks to ISSUE — 190 per MMA against ~40 of tensor time.)
+    const uint64_t p_desc0 = umma_desc_kmajor_sw128(smem_u32(sP));
+    const uint32_t v_base = smem_u32(sV), ones_base = smem_u32(sOnes);
+    auto issue_pv = [&](auto hc) __attribute__((always_inline)) {
+      constexpr int h = decltype(hc)::value;
+#pragma unroll
       for (int j = 0; j < H / 16; ++j) {
-        const int kk = h * H + j * 16;
-        const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(sP + (kk >> 6) * (BQ * 128))) + (uint64_t)(((kk & 63) * 2) >> 4);
-        const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(sV + (kk >> 6) * (64 * 128))) + (uint64_t)(((kk & 63) >> 4) * ((16 * 128) >> 4));
-        tc_mma_f16(tmem_base + O_COL, a_desc, b_desc, idesc_o, (uint32_t)((h | j) != 0));
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int kk = h * H + j * 16;   // compile-time after unrolling
+        const uint64_t a_desc = p_desc0 + (uint64_t)((((kk >> 6) * (BQ * 128)) + ((kk & 63) * 2)) >> 4);
+        const uint32_t v_blk = v_base + (uint32_t)((kk >> 6) * (64 * 128));
+        const uint64_t b_desc = umma_desc_mnmajor_sw128(v_blk, ones_base - v_blk) + (uint64_t)(((kk & 63) >> 4) * ((16 * 128) >> 4));
+        tc_mma_f16(tmem_base + O_COL, a_desc, b_desc, idesc_o, (uint32_t)((h | j) != 0));   // columns 64..79: row sums of the same P
       }
       tc_commit(pv_done + h);
     };
@@ -210,7 +247,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (qt == 0) wait_bar(v_full, ph_item);
         wait_bar(o_empty, pt ^ 1u);   // O of the previous tile has been read out of TMEM
         tc_fence_after();
-        issue_pv(0);
+        ATTN_TRACE(true, trace_tile, 15);
+        issue_pv(std::integral_constant<int, 0>{});
         ATTN_TRACE(true, trace_tile, 10);
         if (next) {
           wait_bar(s_free + 0, pt);
@@ -222,7 +260,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // ---- half 1
         wait_bar(p_full + 1, pt);
         tc_fence_after();
-        issue_pv(1);
+        issue_pv(std::integral_constant<int, 1>{});
         ATTN_TRACE(true, trace_tile, 12);
         if (!same_item) tc_commit(item_empty);
         if (next) {
@@ -237,9 +275,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       ph_item ^= 1u;
     }
-  } else if (warp >= kCtrlWarps) {
+  } else if (warp < kSoftmaxWarps) {
     // ------------------------------------------------------------------ softmax + output
-    const int q = warp & 3, part = (warp - kCtrlWarps) >> 2;  // TMEM lane quarter; which quarter of a half's key columns
+    const int q = warp & 3, part = warp >> 2;  // TMEM lane quarter; which quarter of a half's key columns
     const int r = q * 32 + lane;                                // row of the query tile owned by this lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const float c2 = p.scale_log2;
@@ -248,28 +286,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint32_t pt = 0;
     int trace_tile = 0;
     (void)trace_tile;
-    const bool tr = (warp == kCtrlWarps + 2 || warp == kCtrlWarps + 3) && lane == 0;   // (q = 0, part = 0) and (q = 1, part = 0)
-    const int trace_off = warp == kCtrlWarps + 3 ? 32 : 0;
+    const bool tr = (warp == 0 || warp == 1) && lane == 0;   // (q = 0, part = 0) and (q = 1, part = 0)
+    const int trace_off = warp == 1 ? 32 : 0;
     (void)trace_off;
     (void)tr;
     // the tile whose O is still to be drained: always the previous tile of this CTA, possibly of the previous item.  Its (item,
     // tile, 1 / row sum) live in SHARED memory, not in registers: the softmax loop is at the register limit, and what the
     // compiler spills goes to the stack, whose L1 is almost entirely carved out for shared memory here (an L2 round trip in
     // front of a barrier wait); a 16-byte LDS per tile is cheap and predictable.
-    int4* my_cold = cold + (threadIdx.x - kCtrlWarps * 32);
+    uint2* my_cold = cold + threadIdx.x;
     bool have_pend = false;
     // O / rowsum of the previous query tile -> global (its last P V was issued when the previous tile's P_1 was complete)
     auto drain_o = [&]() __attribute__((always_inline)) {
       wait_bar(pv_done + 1, pt ^ 1u);
       tc_fence_after();
       ATTN_TRACE(tr, trace_tile + trace_off, 4);
-      const int4 pc = *my_cold;   // (output row pointer lo, hi, 1 / row sum, tile is live for this quarter)
-      uint16_t* const pend_dst = reinterpret_cast<uint16_t*>(((unsigned long long)(uint32_t)pc.y << 32) | (uint32_t)pc.x);
-      const float pend_inv = __int_as_float(pc.z);
-      const bool pend_live = pc.w != 0;
-      uint32_t ov[16];
+      const uint2 pc = *my_cold;   // output row pointer (lo, hi); bit 63: the tile is live for this quarter
+      uint16_t* const pend_dst = reinterpret_cast<uint16_t*>(((unsigned long long)(pc.y & 0x7FFFFFFFu) << 32) | pc.x);
+      const bool pend_live = (pc.y >> 31) != 0;
+      uint32_t ov[16], lv[8];
       if (pend_live) {
         tmem_ld_32x16(lane_addr + (uint32_t)(O_COL + part * 16), ov);
+        tmem_ld_32x8(lane_addr + (uint32_t)L_COL, lv);
         tmem_ld_wait();
       }
       ATTN_TRACE(tr, trace_tile + trace_off, 14);
@@ -277,6 +315,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
       if (pend_live && pend_dst != nullptr) {
+        const float sum = __uint_as_float(lv[0]);
+        const float pend_inv = sum > 0.f ? 1.f / sum : 0.f;   // no visible key: zeros, like the masked softmax of the reference's padding rows
         uint16_t* dst = pend_dst;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
@@ -295,36 +335,48 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int row_g = qt * BQ + r;      // query index
         const bool live = qt * BQ + q * 32 < p.Tq;  // warp-uniform (and uniform over the 4 warps of this lane quarter)
         const int key_hi = p.causal ? min(kvl, row_g + 1) : kvl;  // keys [0, key_hi) are visible to this row
-        float m_run = -INFINITY, l_run = 0.f;   // running row maximum (raw score units) / this warp's partial row sum
+        int k_all = key_hi, k_any = key_hi;   // warp-uniform: keys below k_all are visible to every row of the warp, keys from k_any on to none
+        if (p.causal) {
+          k_all = __reduce_min_sync(0xffffffffu, key_hi);
+          k_any = __reduce_max_sync(0xffffffffu, key_hi);
+        }
+        float m_run = -INFINITY;   // running row maximum (raw score units)
         ATTN_TRACE(tr, trace_tile + trace_off, 7);
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           wait_bar(s_full + hf, pt);
           tc_fence_after();
           ATTN_TRACE(tr, trace_tile + trace_off, hf * 5 + 0);
+          ATTN_TRACE_W(trace_tile, warp, hf * 2);
           const int col0 = hf * H + part * CW;   // first key column of this warp's slice (= TMEM column of S)
           if (live) {
             // ---- pass 1: row max of this half straight from TMEM (nothing is kept: holding the slice in registers from here to
             //      the exp pass pushes the loop over the register limit, and the spills / rematerialisation cost more than the
             //      second TMEM read), masking only on chunks that straddle key_hi; exchanged between the 4 warps of the quarter
+            // (requesting the whole slice — 5 chunks, 40 registers — before one wait spills: 231 -> 400 us.  With the shared-memory
+            //  carve-out at its maximum a spilled byte costs an L2 round trip.)
             float mx = -INFINITY;
 #pragma unroll
             for (int c0 = 0; c0 < NCK; c0 += 2) {
-              uint32_t v[2][8];
-              tmem_ld_32x8(lane_addr + (uint32_t)(col0 + c0 * 8), v[0]);
-              if (c0 + 1 < NCK) tmem_ld_32x8(lane_addr + (uint32_t)(col0 + c0 * 8 + 8), v[1]);
-              tmem_ld_wait();
+              if (col0 + c0 * 8 < k_any) {   // (uniform) at least one row sees a key of this pair of chunks
+                uint32_t v[2][8];
+                tmem_ld_32x8(lane_addr + (uint32_t)(col0 + c0 * 8), v[0]);
+                if (c0 + 1 < NCK) tmem_ld_32x8(lane_addr + (uint32_t)(col0 + c0 * 8 + 8), v[1]);
+                tmem_ld_wait();
 #pragma unroll
-              for (int cc = 0; cc < 2; ++cc) {
-                if (c0 + cc < NCK) {
-                  const int key0 = col0 + (c0 + cc) * 8;
-                  if (__all_sync(0xffffffffu, key0 + 8 <= key_hi)) {
+                for (int cc = 0; cc < 2; ++cc) {
+                  if (c0 + cc < NCK) {
+                    const int key0 = col0 + (c0 + cc) * 8;
+                    if (key0 + 8 <= k_all) {
+                      const float a = fmaxf(fmaxf(__uint_as_float(v[cc][0]), __uint_as_float(v[cc][1])), __uint_as_float(v[cc][2]));
+                      const float b = fmaxf(fmaxf(__uint_as_float(v[cc][3]), __uint_as_float(v[cc][4])), __uint_as_float(v[cc][5]));
+                      mx = fmaxf(fmaxf(mx, a), b);
+                      mx = fmaxf(fmaxf(mx, __uint_as_float(v[cc][6])), __uint_as_float(v[cc][7]));   // 4 three-input FMNMX3 per 8 scores
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) mx = fmaxf(mx, __uint_as_float(v[cc][i]));
-                  } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                      if (key0 + i < key_hi) mx = fmaxf(mx, __uint_as_float(v[cc][i]));
+                      for (int i = 0; i < 8; ++i)
+                        if (key0 + i < key_hi) mx = fmaxf(mx, __uint_as_float(v[cc][i]));
+                    }
                   }
                 }
               }
@@ -353,15 +405,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
                 for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
                 tmem_st_32x16(lane_addr + (uint32_t)(O_COL + part * 16), ov);
+                if (part == 0) {   // the row sums of half 0 live in TMEM too
+                  tmem_ld_32x16(lane_addr + (uint32_t)L_COL, ov);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+                  tmem_st_32x16(lane_addr + (uint32_t)L_COL, ov);
+                }
                 tmem_st_wait();
                 tc_fence_before();
-                l_run *= alpha;
                 if (need) m_run = mx;
               }
             }
             // ---- pass 2: p = 2^((s - m) * scale), row sum, P -> shared memory (K-major, 128B-swizzled A operand of P V).  A row
             //      of P is 5 blocks of 8 16-byte units; this warp's chunk c is unit u0 + c of the row.
             const float m_off = (m_run == -INFINITY) ? 0.f : -m_run * c2;
+            const uint64_t c22 = pk2(c2, c2), mo2 = pk2(m_off, m_off);
             const int u0 = col0 >> 3;
 #pragma unroll
             for (int c0 = 0; c0 < NCK; c0 += 2) {
@@ -373,19 +432,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               for (int cc = 0; cc < 2; ++cc) {
                 if (c0 + cc < NCK) {
                   const int key0 = col0 + (c0 + cc) * 8;
-                  float pv[8];
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(v[cc][i]), c2, m_off));
-                  if (!__all_sync(0xffffffffu, key0 + 8 <= key_hi)) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                      if (key0 + i >= key_hi) pv[i] = 0.f;
-                  }
                   uint32_t pk[4];
+                  if (key0 + 8 <= k_all) {   // (uniform) every row sees all 8 keys: 4 packed FMAs, 8 exponentials, 4 packs
 #pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    l_run += pv[2 * i] + pv[2 * i + 1];
-                    pk[i] = H16<BF16 ? SCB_BF16 : SCB_F16>::pack(pv[2 * i], pv[2 * i + 1]);
+                    for (int i = 0; i < 4; ++i) {
+                      float a, b;
+                      upk2(fma2(pk2(__uint_as_float(v[cc][2 * i]), __uint_as_float(v[cc][2 * i + 1])), c22, mo2), a, b);
+                      pk[i] = H16<BF16 ? SCB_BF16 : SCB_F16>::pack(ex2_approx(a), ex2_approx(b));
+                    }
+                  } else if (key0 >= k_any) {
+                    pk[0] = pk[1] = pk[2] = pk[3] = 0u;
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                      const float a = key0 + 2 * i < key_hi ? ex2_approx(fmaf(__uint_as_float(v[cc][2 * i]), c2, m_off)) : 0.f;
+                      const float b = key0 + 2 * i + 1 < key_hi ? ex2_approx(fmaf(__uint_as_float(v[cc][2 * i + 1]), c2, m_off)) : 0.f;
+                      pk[i] = H16<BF16 ? SCB_BF16 : SCB_F16>::pack(a, b);
+                    }
                   }
                   const int u = u0 + c0 + cc;
                   *reinterpret_cast<uint4*>(p_row + ((u >> 3) << 14) + (((u & 7) ^ rx) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -400,6 +463,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               mbar_arrive(p_full + hf);
             }
             ATTN_TRACE(tr, trace_tile + trace_off, hf * 5 + 3);
+            ATTN_TRACE_W(trace_tile, warp, hf * 2 + 1);
           } else {
             // rows beyond Tq: nothing to compute (the MMA rows they would feed are never read); keep the barrier protocol going
             if (hf == 0 && have_pend) drain_o();
@@ -411,19 +475,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
           }
         }
-        float inv = 0.f;
-        if (live) {
-          red_sum[part * BQ + r] = l_run;
-          named_bar_sync(1 + q, 128);
-          const float sum = (red_sum[r] + red_sum[BQ + r]) + (red_sum[2 * BQ + r] + red_sum[3 * BQ + r]);
-          inv = sum > 0.f ? 1.f / sum : 0.f;
-        }
         ATTN_TRACE(tr, trace_tile + trace_off, 9);
         ++trace_tile;
         {
           const unsigned long long dst = row_g < p.Tq ? (unsigned long long)(p.o + (long long)(item / p.heads) * p.o_bs + (long long)row_g * p.o_ld +
                                                                              (item % p.heads) * HD + part * 16) : 0ull;
-          *my_cold = make_int4((int)(uint32_t)dst, (int)(uint32_t)(dst >> 32), __float_as_int(inv), live ? 1 : 0);
+          *my_cold = make_uint2((uint32_t)dst, (uint32_t)(dst >> 32) | (live ? 0x80000000u : 0u));
         }
         have_pend = true;
         pt ^= 1u;
@@ -434,7 +491,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
