@@ -176,7 +176,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   griddep_launch_dependents();
   const int n_items = p.batch * p.heads;
 
-  if (warp == kProducerWarp && lane == 0) {
+  if (warp == kProducerWarp && elect_one_sync()) {
     // ------------------------------------------------------------------ producer
     // K and Q of the NEXT item are loaded as soon as the last S of the current item has retired (kq_empty), i.e. while its last
     // query tile is still in the softmax / P V phases; V follows once the last P V has retired (item_empty).
@@ -193,7 +193,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int kb = 0; kb < NCH; ++kb) tma_load_3d(sV + kb * 64 * 128, &tmV, v_full, h * HD, kb * 64, b);
       ph ^= 1u;
     }
-  } else if (warp == kMmaWarp && lane == 0) {
+  } else if (warp == kMmaWarp && elect_one_sync()) {
     // ------------------------------------------------------------------ MMA issuer
     const int fmt = BF16 ? 1 : 0;
     const uint32_t idesc_s = umma_idesc_f16(BQ, H, fmt);

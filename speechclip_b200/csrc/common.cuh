@@ -466,6 +466,14 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
   return d;
 }
+// One lane of a fully converged warp (elect.sync): the compiler then knows the code it guards runs on a single thread and issues
+// tcgen05.mma / commit directly, instead of wrapping each of them in an "elect / issue / any lane left?" loop as it does under
+// `lane == 0` (5 extra instructions per MMA on the issuing thread).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // kind::f16 instruction descriptor: fp32 accumulator, A/B both K-major, format 0 = f16 / 1 = bf16.
 // (kind::tf32 uses the same layout with format 2 = tf32.)
 __device__ __forceinline__ uint32_t umma_idesc_f16(int m, int n, int fmt) {

@@ -44,6 +44,19 @@ inline bool stream_k_applies(long long tiles, int pairs, int k_blocks) {
   return rem > 0 && rem * 5 <= (long long)pairs * 4 && rem * k_blocks >= 2LL * pairs;
 }
 
+// The MMA-issuing thread runs a long chain of dependent scalar instructions between tcgen05.mma issues; measured on the attention
+// kernel, every instruction in front of an MMA costs ~6-10 clocks, and on the 128 x 48 pos-conv tiles (96 clocks of tensor time
+// per tap) rebuilding two 64-bit descriptors per tap made the issue thread the bottleneck (~425 clocks per tap).  The shared-
+// memory descriptors therefore live as a 32-bit low word (address field + LBO) that is advanced by constants, and a constant
+// high word (SBO, version, swizzle).  Shared addresses are < 256 KB, so the 14-bit address field never carries.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc_join(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
+
 struct GemmParams {
   int batch, m_tiles_per_batch, n_tiles, groups, num_tiles;
   int m_per_batch, n, k_blocks;
@@ -415,7 +428,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   griddep_wait();
   griddep_launch_dependents();  // a following row kernel (LayerNorm) may become resident beside this CTA and wait for its data
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one_sync()) {
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
@@ -460,7 +473,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && elect_one_sync()) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = umma_idesc_f16(BM, p.umma_n, p.ab_fmt);
     const bool tf32 = p.ab_fmt == 2;
@@ -481,18 +494,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // The 128B swizzle XORs the 16-byte chunk index with ABSOLUTE shared-address bits [7:9] (in TMA and in the MMA's
         // operand fetch alike), so a row-shifted window of a 1024-aligned slab needs no descriptor base offset (measured:
         // base offset (kb & 7) gives wrong results, 0 is bit-identical to reloading every tap).
-        const uint32_t slab_addr = smem_u32(sA + sl * SLAB_BYTES);
-        const uint32_t bs_addr = smem_u32(sA + 2 * SLAB_BYTES);
+        uint32_t a_lo = desc_lo(smem_u32(sA + sl * SLAB_BYTES));   // + 8 (one 128-byte row) per tap
+        const uint32_t b_lo0 = desc_lo(smem_u32(sA + 2 * SLAB_BYTES));
+        const uint32_t sub4 = (uint32_t)p.slab_sub_bytes >> 4;
+        uint32_t accf = 0;
         for (int kb0 = 0; kb0 < p.k_blocks; kb0 += kSlabTaps) {
           const int ntap = min(kSlabTaps, p.k_blocks - kb0);
+          uint32_t b_lo = b_lo0 + (uint32_t)(stage * kSlabTaps) * sub4;
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          for (int tp = 0; tp < ntap; ++tp) {
-            const uint64_t a_desc = umma_desc_kmajor_sw128(slab_addr + (uint32_t)(kb0 + tp) * 128u);
-            const uint64_t b_desc = umma_desc_kmajor_sw128(bs_addr + (uint32_t)(stage * kSlabTaps + tp) * (uint32_t)p.slab_sub_bytes);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              tc_mma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)((kb0 | tp | k) != 0));
+          for (int tp = 0; tp < kSlabTaps; ++tp) {
+            if (tp < ntap) {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                tc_mma_f16(d_tmem, desc_join(a_lo + (uint32_t)(2 * k), kDescHi), desc_join(b_lo + (uint32_t)(2 * k), kDescHi), idesc, accf);
+                accf = 1;
+              }
+              a_lo += 8;
+              b_lo += sub4;
+            }
           }
           tc_commit(&empty[stage]);
           if (++stage == p.slab_stages) {
@@ -501,21 +522,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
-      for (int kb = 0; kb < (p.slab ? 0 : p.k_blocks); ++kb) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(sA + stage * A_BYTES));
-        const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(sB + stage * B_BYTES));
+      {
+        const uint32_t a_lo0 = desc_lo(smem_u32(sA)), b_lo0 = desc_lo(smem_u32(sB));
+        uint32_t accf = 0;
+        for (int kb = 0; kb < (p.slab ? 0 : p.k_blocks); ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_lo = a_lo0 + (uint32_t)stage * (uint32_t)(A_BYTES >> 4), b_lo = b_lo0 + (uint32_t)stage * (uint32_t)(B_BYTES >> 4);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 elements (32 B) inside the 128 B swizzle row: +2 in the (addr >> 4) field
-          if (tf32) tc_mma_tf32(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
-          else tc_mma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
-        }
-        tc_commit(&empty[stage]);
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1u;
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements (32 B) inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            if (tf32) tc_mma_tf32(d_tmem, desc_join(a_lo + (uint32_t)(2 * k), kDescHi), desc_join(b_lo + (uint32_t)(2 * k), kDescHi), idesc, accf);
+            else tc_mma_f16(d_tmem, desc_join(a_lo + (uint32_t)(2 * k), kDescHi), desc_join(b_lo + (uint32_t)(2 * k), kDescHi), idesc, accf);
+            accf = 1;
+          }
+          tc_commit(&empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
       }
       if (p.slab) {
@@ -751,7 +776,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   griddep_wait();  // programmatic dependent launch: global memory is only touched below
   griddep_launch_dependents();
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one_sync()) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
     int stage_i = 0;
     uint32_t phase = 0;
@@ -773,10 +798,11 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
       }
     }
-  } else if (warp == 1 && lane == 0 && leader) {
+  } else if (warp == 1 && leader && elect_one_sync()) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     const uint32_t idesc = umma_idesc_f16(256, BN2, p.ab_fmt);
     const bool tf32 = p.ab_fmt == 2;
+    const uint32_t a_lo0 = desc_lo(smem_u32(sA)), b_lo0 = desc_lo(smem_u32(sB));
     int stage_i = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -786,15 +812,16 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_wait(&tempty[acc], acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN2);
+      uint32_t accf = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full[stage_i], phase);
         tc_fence_after();
-        const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(sA + stage_i * A_BYTES));
-        const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(sB + stage_i * B_BYTES));
+        const uint32_t a_lo = a_lo0 + (uint32_t)stage_i * (uint32_t)(A_BYTES >> 4), b_lo = b_lo0 + (uint32_t)stage_i * (uint32_t)(B_BYTES >> 4);
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
-          if (tf32) tc_mma_tf32_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)(((kb - kb0) | k) != 0));
-          else tc_mma_f16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)(((kb - kb0) | k) != 0));
+          if (tf32) tc_mma_tf32_2sm(d_tmem, desc_join(a_lo + (uint32_t)(2 * k), kDescHi), desc_join(b_lo + (uint32_t)(2 * k), kDescHi), idesc, accf);
+          else tc_mma_f16_2sm(d_tmem, desc_join(a_lo + (uint32_t)(2 * k), kDescHi), desc_join(b_lo + (uint32_t)(2 * k), kDescHi), idesc, accf);
+          accf = 1;
         }
         tc_commit_2sm(&empty[stage_i], 3);
         if (++stage_i == STAGES) {
