@@ -451,8 +451,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int ntap = min(kSlabTaps, p.k_blocks - kb0);
           mbar_wait(&empty[stage], phase ^ 1u);
           mbar_expect_tx(&full[stage], (uint32_t)(ntap * p.slab_sub_bytes));
-          for (int tp = 0; tp < ntap; ++tp)
-            tma_load_3d(sBs + stage * (kSlabTaps * p.slab_sub_bytes) + tp * p.slab_sub_bytes, &tmB, &full[stage], (kb0 + tp) * p.bk, t.n0, t.g);
+          uint8_t* dst = sBs + stage * (kSlabTaps * p.slab_sub_bytes);
+          int b_col = kb0 * p.bk;
+          for (int tp = 0; tp < ntap; ++tp, dst += p.slab_sub_bytes, b_col += p.bk) tma_load_3d(dst, &tmB, &full[stage], b_col, t.n0, t.g);
           if (++stage == p.slab_stages) {
             stage = 0;
             phase ^= 1u;
@@ -460,13 +461,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         continue;
       }
+      // (coordinates advance incrementally: an integer division per k-block on this single thread costs more than the TMA issue)
+      int a_col = a_c0, a_row = t.m0, b_col = 0, kin = 0;
       for (int kb = 0; kb < p.k_blocks; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1u);
         mbar_expect_tx(&full[stage], p.tx_bytes);
-        const int tap = kb / p.kb_per_tap;
-        const int kin = kb - tap * p.kb_per_tap;
-        tma_load_3d(sA + stage * A_BYTES, &tmA, &full[stage], a_c0 + kin * p.bk, t.m0 + tap * p.tap_row_shift, t.b);
-        tma_load_3d(sB + stage * B_BYTES, &tmB, &full[stage], kb * p.bk, t.n0, t.g);
+        tma_load_3d(sA + stage * A_BYTES, &tmA, &full[stage], a_col, a_row, t.b);
+        tma_load_3d(sB + stage * B_BYTES, &tmB, &full[stage], b_col, t.n0, t.g);
+        b_col += p.bk;
+        a_col += p.bk;
+        if (++kin == p.kb_per_tap) {   // next tap: back to the group's first column, tap_row_shift rows further
+          kin = 0;
+          a_col = a_c0;
+          a_row += p.tap_row_shift;
+        }
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1u;
@@ -780,18 +788,27 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ------------------------------------------------------------------ TMA producer (both CTAs)
     int stage_i = 0;
     uint32_t phase = 0;
+    const uint32_t full_leader0 = mapa_u32(smem_u32(&full[0]), 0);   // the leader's full[] barriers, 8 bytes apart
     int tile, kb0, kb1;
     for (int it = 0; sk_item<SK>(p, pair, num_pairs, it, tile, kb0, kb1); ++it) {
       const TileCoord t = decode_tile2(p, tile, (int)rank);
       const int a_c0 = p.a_col0 + t.g * p.a_group_cols;
+      int kin = kb0 % p.kb_per_tap;
+      int a_row = t.m0 + (kb0 / p.kb_per_tap) * p.tap_row_shift, a_col = a_c0 + kin * p.bk, b_col = kb0 * p.bk;
+      const int b_row = t.n0 + (int)rank * (BN2 / 2);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty[stage_i], phase ^ 1u);
-        const uint32_t full_leader = mapa_u32(smem_u32(&full[stage_i]), 0);
+        const uint32_t full_leader = full_leader0 + (uint32_t)stage_i * 8u;
         if (leader) mbar_expect_tx(&full[stage_i], 2u * (uint32_t)(A_BYTES + B_BYTES));
-        const int tap = kb / p.kb_per_tap;
-        const int kin = kb - tap * p.kb_per_tap;
-        tma_load_3d_2sm(sA + stage_i * A_BYTES, &tmA, full_leader, a_c0 + kin * p.bk, t.m0 + tap * p.tap_row_shift, t.b);
-        tma_load_3d_2sm(sB + stage_i * B_BYTES, &tmB, full_leader, kb * p.bk, t.n0 + (int)rank * (BN2 / 2), t.g);
+        tma_load_3d_2sm(sA + stage_i * A_BYTES, &tmA, full_leader, a_col, a_row, t.b);
+        tma_load_3d_2sm(sB + stage_i * B_BYTES, &tmB, full_leader, b_col, b_row, t.g);
+        b_col += p.bk;
+        a_col += p.bk;
+        if (++kin == p.kb_per_tap) {
+          kin = 0;
+          a_col = a_c0;
+          a_row += p.tap_row_shift;
+        }
         if (++stage_i == STAGES) {
           stage_i = 0;
           phase ^= 1u;
