@@ -199,12 +199,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t idesc_s = umma_idesc_f16(BQ, H, fmt);
     const uint32_t idesc_o = idesc_pv(fmt);
     // S_h of query tile qt: 4 k-steps of 16 over the head dimension
-    auto issue_s = [&](int qt, int h) __attribute__((always_inline)) {
-      const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(sQ + qt * BQ * 128));
-      const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(sK + h * H * 128));
+    // (descriptor low words — address field + LBO — are precomputed; the high word is a constant: see gemm_tcgen05.cu)
+    constexpr uint32_t kHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
+    auto join = [](uint32_t lo, uint32_t hi) __attribute__((always_inline)) {
+      uint64_t d;
+      asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+      return d;
+    };
+    const uint32_t q_lo0 = ((smem_u32(sQ) >> 4) & 0x3FFFu) | (1u << 16), k_lo0 = ((smem_u32(sK) >> 4) & 0x3FFFu) | (1u << 16);
+    auto issue_s = [&](int qt, auto hc) __attribute__((always_inline)) {
+      constexpr int h = decltype(hc)::value;
+      const uint32_t a_lo = q_lo0 + (uint32_t)qt * (uint32_t)((BQ * 128) >> 4);
+      const uint32_t b_lo = k_lo0 + (uint32_t)((h * H * 128) >> 4);
 #pragma unroll
       for (int k = 0; k < HD / 16; ++k)
-        tc_mma_f16(tmem_base + (uint32_t)(h * H), a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc_s, (uint32_t)(k != 0));
+        tc_mma_f16(tmem_base + (uint32_t)(h * H), join(a_lo + (uint32_t)(2 * k), kHi), join(b_lo + (uint32_t)(2 * k), kHi), idesc_s, (uint32_t)(k != 0));
       tc_commit(s_full + h);
     };
     // O (+)= P_h V_h: H / 16 k-steps of 16 keys; key kk lives in block kk / 64 of P (K-major, 32 B per step inside the 128-byte
@@ -212,19 +221,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // (fully unrolled with a compile-time half: every descriptor is base + constant.  The issuing thread shares its scheduler with
     // four busy softmax warps, so each dependent integer instruction in front of an MMA costs several issue rounds: with the
     // descriptors recomputed per step the 10 MMAs of a half took ~1900 clocks to ISSUE — 190 per MMA against ~40 of tensor time.)
-    const uint64_t p_desc0 = umma_desc_kmajor_sw128(smem_u32(sP));
-    const uint32_t v_base = smem_u32(sV), ones_base = smem_u32(sOnes);
+    const uint32_t p_lo0 = ((smem_u32(sP) >> 4) & 0x3FFFu) | (1u << 16);
+    // V block kb, key step s: address field (sV + kb * 8 KB + s * 2 KB) >> 4, LBO field (sOnes - (sV + kb * 8 KB)) >> 4: both are the
+    // block-0 value plus / minus compile-time constants, so the low word is ONE add per MMA
+    const uint32_t v_lo0 = ((smem_u32(sV) >> 4) & 0x3FFFu) | ((((smem_u32(sOnes) - smem_u32(sV)) >> 4) & 0x3FFFu) << 16);
     auto issue_pv = [&](auto hc) __attribute__((always_inline)) {
       constexpr int h = decltype(hc)::value;
 #pragma unroll
       for (int j = 0; j < H / 16; ++j) {
-        constexpr int dummy = 0;
-        (void)dummy;
         const int kk = h * H + j * 16;   // compile-time after unrolling
-        const uint64_t a_desc = p_desc0 + (uint64_t)((((kk >> 6) * (BQ * 128)) + ((kk & 63) * 2)) >> 4);
-        const uint32_t v_blk = v_base + (uint32_t)((kk >> 6) * (64 * 128));
-        const uint64_t b_desc = umma_desc_mnmajor_sw128(v_blk, ones_base - v_blk) + (uint64_t)(((kk & 63) >> 4) * ((16 * 128) >> 4));
-        tc_mma_f16(tmem_base + O_COL, a_desc, b_desc, idesc_o, (uint32_t)((h | j) != 0));   // columns 64..79: row sums of the same P
+        const int blk = kk >> 6, step = (kk & 63) >> 4;
+        const uint32_t a_lo = p_lo0 + (uint32_t)(((blk * (BQ * 128)) + ((kk & 63) * 2)) >> 4);
+        const uint32_t b_lo = v_lo0 + (uint32_t)(((blk * (64 * 128)) + step * (16 * 128)) >> 4) - ((uint32_t)((blk * (64 * 128)) >> 4) << 16);
+        tc_mma_f16(tmem_base + O_COL, join(a_lo, kHi), join(b_lo, kHi), idesc_o, (uint32_t)((h | j) != 0));   // columns 64..79: row sums of the same P
       }
       tc_commit(pv_done + h);
     };
@@ -233,8 +242,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     (void)trace_tile;
     wait_bar(kq_full, ph_item);
     tc_fence_after();
-    issue_s(0, 0);
-    issue_s(0, 1);
+    issue_s(0, std::integral_constant<int, 0>{});
+    issue_s(0, std::integral_constant<int, 1>{});
     if (p.n_qt == 1) tc_commit(kq_empty);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const bool has_next = item + (int)gridDim.x < n_items;
@@ -254,7 +263,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           wait_bar(s_free + 0, pt);
           if (!same_item) wait_bar(kq_full, ph_item ^ 1u);
           tc_fence_after();
-          issue_s(nqt, 0);
+          issue_s(nqt, std::integral_constant<int, 0>{});
         }
         ATTN_TRACE(true, trace_tile, 11);
         // ---- half 1
@@ -266,7 +275,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (next) {
           wait_bar(s_free + 1, pt);
           tc_fence_after();
-          issue_s(nqt, 1);
+          issue_s(nqt, std::integral_constant<int, 1>{});
           if (same_item ? (qt + 2 == p.n_qt) : (p.n_qt == 1)) tc_commit(kq_empty);  // the item's last S: K / Q are free once it retires
         }
         ATTN_TRACE(true, trace_tile, 13);
