@@ -64,7 +64,12 @@ struct GemmParams {
   int umma_n;
   int bk;  // elements per k-block: 64 (16-bit) or 32 (tf32)
   int slab;       // 1: one-tap-per-k-block walk with row shift 1 (positional conv): A is loaded ONCE per tile as a 256-row slab
-  int slab_stages, slab_sub_bytes;  // slab mode: B ring of slab_stages stages, each kSlabTaps sub-tiles of slab_sub_bytes
+  int slab_stages, slab_sub_bytes;  // slab mode: B ring of slab_stages stages, each slab_taps sub-tiles of slab_sub_bytes
+  // slab mode, several M tiles per work item (pos-conv: T = 319 is 3 tiles): the slab holds slab_mt * 128 + taps - 1 rows, loaded as
+  // slab_parts boxes of slab_box_rows rows; every tap's weight sub-tile then feeds slab_mt x 4 MMAs instead of 4 — the weights
+  // of a group (786 KB at 48 x 8192) are streamed from L2 once per utterance instead of once per 128 frames
+  int slab_mt, slab_taps, slab_parts, slab_box_rows, slab_bytes;
+  int tile_m;  // rows of M covered by one tile index of the single-CTA kernel (BM, or BM * slab_mt)
   uint32_t tx_bytes;
   void* out;
   void* out2;
@@ -95,7 +100,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) 
   rest /= p.m_tiles_per_batch;
   t.b = rest % p.batch;
   t.g = rest / p.batch;
-  t.m0 = mt * BM;
+  t.m0 = mt * p.tile_m;
   t.n0 = nt * BN;
   return t;
 }
@@ -120,9 +125,11 @@ __device__ __forceinline__ void store4(void* base, int dtype, long long off, con
 // residual loads of a chunk are issued before the TMEM load (out may alias residual, so the compiler cannot hoist them).
 // ACT / RES / ODT >= 0 pin the activation, the residual dtype (3 = no residual) and the output dtype at compile time (and imply
 // out2 == NULL) for the shapes that dominate the step; -1 keeps the runtime switch.
+// tmem_col0: first TMEM column of the tile's accumulator; release: this is the last tile read from the accumulator buffer (the
+// buffer holds several tiles in the multi-tile slab mode), so the warp hands it back after its last load.
 template <int BN, int ACT, int RES, int ODT>
-__device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoord& t, uint32_t tmem_base, int acc, uint32_t acc_phase,
-                                              uint64_t* tfull_bar, uint32_t tempty_addr, float* stage, int warp, int lane) {
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoord& t, uint32_t tmem_base, int tmem_col0, uint32_t acc_phase,
+                                              uint64_t* tfull_bar, uint32_t tempty_addr, float* stage, int warp, int lane, bool release = true) {
   constexpr int COLS = EpiCfg<BN>::COLS;
   const int q = warp & 3;            // TMEM lane quarter this warp may touch
   const int part = (warp - 4) >> 2;  // which slice of the tile's columns
@@ -143,7 +150,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
       if (col_base < p.n && m_base < p.m_per_batch) nchunks = min(COLS / 16, (p.n - col_base + 15) / 16);
       mbar_wait(tfull_bar, acc_phase);
       tc_fence_after();
-      if (nchunks == 0) {
+      if (nchunks == 0 && release) {
         tc_fence_before();
         if (lane == 0) mbar_arrive_cluster(tempty_addr);
       }
@@ -172,9 +179,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
           }
         }
         uint32_t v[16];
-        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + part * COLS + ch * 16), v);
+        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tmem_col0 + part * COLS + ch * 16), v);
         tmem_ld_wait();
-        if (ch == nchunks - 1) {  // accumulator fully read by this warp: hand the buffer back to the MMA warp
+        if (ch == nchunks - 1 && release) {  // accumulator fully read by this warp: hand the buffer back to the MMA warp
           tc_fence_before();
           if (lane == 0) mbar_arrive_cluster(tempty_addr);
         }
@@ -418,7 +425,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
+  const bool wide_tmem = BN == 64 && p.slab_mt > 1;   // 2 buffers x 256 columns
+  if (warp == 2) {
+    if (wide_tmem) tmem_alloc<512>(tmem_slot);
+    else tmem_alloc<2 * BN>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -439,19 +450,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int a_c0 = p.a_col0 + t.g * p.a_group_cols;
       if (p.slab) {  // rows m0 .. m0+255 of this group's 64 columns: every tap's A tile is a row-shifted window of it
         mbar_wait(&sempty[sl], sl_phase ^ 1u);
-        mbar_expect_tx(&sfull[sl], (uint32_t)SLAB_BYTES);
-        tma_load_3d(sA + sl * SLAB_BYTES, &tmA, &sfull[sl], a_c0, t.m0, t.b);
+        mbar_expect_tx(&sfull[sl], (uint32_t)p.slab_bytes);
+        for (int part = 0; part < p.slab_parts; ++part)
+          tma_load_3d(sA + sl * p.slab_bytes + part * (p.slab_box_rows * 128), &tmA, &sfull[sl], a_c0, t.m0 + part * p.slab_box_rows, t.b);
         sl ^= 1;
         if (sl == 0) sl_phase ^= 1u;
       }
       if (p.slab) {
         // B ring for the slab walk: kSlabTaps consecutive taps per stage, carved out of [sA + 2 slabs, end of the B ring)
-        uint8_t* sBs = sA + 2 * SLAB_BYTES;
-        for (int kb0 = 0; kb0 < p.k_blocks; kb0 += kSlabTaps) {
-          const int ntap = min(kSlabTaps, p.k_blocks - kb0);
+        uint8_t* sBs = sA + 2 * p.slab_bytes;
+        for (int kb0 = 0; kb0 < p.k_blocks; kb0 += p.slab_taps) {
+          const int ntap = min(p.slab_taps, p.k_blocks - kb0);
           mbar_wait(&empty[stage], phase ^ 1u);
           mbar_expect_tx(&full[stage], (uint32_t)(ntap * p.slab_sub_bytes));
-          uint8_t* dst = sBs + stage * (kSlabTaps * p.slab_sub_bytes);
+          uint8_t* dst = sBs + stage * (p.slab_taps * p.slab_sub_bytes);
           int b_col = kb0 * p.bk;
           for (int tp = 0; tp < ntap; ++tp, dst += p.slab_sub_bytes, b_col += p.bk) tma_load_3d(dst, &tmB, &full[stage], b_col, t.n0, t.g);
           if (++stage == p.slab_stages) {
@@ -494,7 +506,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       mbar_wait(&tempty[acc], acc_phase ^ 1u);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * (wide_tmem ? 256 : BN));
       if (p.slab) {
         mbar_wait(&sfull[sl], sl_phase);
         tc_fence_after();
@@ -502,23 +514,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // The 128B swizzle XORs the 16-byte chunk index with ABSOLUTE shared-address bits [7:9] (in TMA and in the MMA's
         // operand fetch alike), so a row-shifted window of a 1024-aligned slab needs no descriptor base offset (measured:
         // base offset (kb & 7) gives wrong results, 0 is bit-identical to reloading every tap).
-        uint32_t a_lo = desc_lo(smem_u32(sA + sl * SLAB_BYTES));   // + 8 (one 128-byte row) per tap
-        const uint32_t b_lo0 = desc_lo(smem_u32(sA + 2 * SLAB_BYTES));
+        uint32_t a_lo = desc_lo(smem_u32(sA + sl * p.slab_bytes));   // + 8 (one 128-byte row) per tap; + 1024 per M tile
+        const uint32_t b_lo0 = desc_lo(smem_u32(sA + 2 * p.slab_bytes));
         const uint32_t sub4 = (uint32_t)p.slab_sub_bytes >> 4;
-        uint32_t accf = 0;
-        for (int kb0 = 0; kb0 < p.k_blocks; kb0 += kSlabTaps) {
-          const int ntap = min(kSlabTaps, p.k_blocks - kb0);
-          uint32_t b_lo = b_lo0 + (uint32_t)(stage * kSlabTaps) * sub4;
+        uint32_t accf = 0;   // 0 during the first tap (every tile's first MMA overwrites its accumulator)
+        for (int kb0 = 0; kb0 < p.k_blocks; kb0 += p.slab_taps) {
+          const int ntap = min(p.slab_taps, p.k_blocks - kb0);
+          uint32_t b_lo = b_lo0 + (uint32_t)(stage * p.slab_taps) * sub4;
           mbar_wait(&full[stage], phase);
           tc_fence_after();
 #pragma unroll
           for (int tp = 0; tp < kSlabTaps; ++tp) {
             if (tp < ntap) {
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
-                tc_mma_f16(d_tmem, desc_join(a_lo + (uint32_t)(2 * k), kDescHi), desc_join(b_lo + (uint32_t)(2 * k), kDescHi), idesc, accf);
-                accf = 1;
+              for (int mt = 0; mt < 3; ++mt) {
+                if (mt < p.slab_mt) {
+#pragma unroll
+                  for (int k = 0; k < BK / 16; ++k)
+                    tc_mma_f16(d_tmem + (uint32_t)(mt * BN), desc_join(a_lo + (uint32_t)(mt * 1024 + 2 * k), kDescHi),
+                               desc_join(b_lo + (uint32_t)(2 * k), kDescHi), idesc, k == 0 ? accf : 1u);
+                }
               }
+              accf = 1;
               a_lo += 8;
               b_lo += sub4;
             }
@@ -568,7 +585,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const TileCoord t = decode_tile<BN>(p, tile);
       if constexpr (TMAO && ODT == SCB_F32) epilogue_tile_tma_res<RES>(p, &tmO, t, tmem_base, acc, acc_phase, &tfull[acc], smem_u32(&tempty[acc]), epi, warp, lane);
       else if constexpr (TMAO) epilogue_tile_tma<ACT>(p, &tmO, t, tmem_base, acc, acc_phase, &tfull[acc], smem_u32(&tempty[acc]), epi, warp, lane);
-      else epilogue_tile<BN, ACT, RES, ODT>(p, t, tmem_base, acc, acc_phase, &tfull[acc], smem_u32(&tempty[acc]), stage, warp, lane);
+      else if (BN == 64 && p.slab_mt > 1) {   // several M tiles per accumulator buffer (256 columns per buffer, 64 per tile)
+        for (int mt = 0; mt < p.slab_mt; ++mt) {
+          TileCoord tt = t;
+          tt.m0 = t.m0 + mt * BM;
+          epilogue_tile<BN, ACT, RES, ODT>(p, tt, tmem_base, acc * 256 + mt * BN, acc_phase, &tfull[acc], smem_u32(&tempty[acc]), stage, warp, lane,
+                                           mt == p.slab_mt - 1);
+        }
+      } else epilogue_tile<BN, ACT, RES, ODT>(p, t, tmem_base, acc * BN, acc_phase, &tfull[acc], smem_u32(&tempty[acc]), stage, warp, lane);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -579,7 +603,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<2 * BN>(tmem_base);
+    if (wide_tmem) tmem_dealloc<512>(tmem_base);
+    else tmem_dealloc<2 * BN>(tmem_base);
   }
 }
 
@@ -873,7 +898,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
       if constexpr (TMAO && ODT == SCB_F32) epilogue_tile_tma_res<RES>(p, &tmO, t, tmem_base, acc, acc_phase, &tfull[acc], mapa_u32(smem_u32(&tempty[acc]), 0), epi, warp, lane);
       else if constexpr (TMAO) epilogue_tile_tma<ACT>(p, &tmO, t, tmem_base, acc, acc_phase, &tfull[acc], mapa_u32(smem_u32(&tempty[acc]), 0), epi, warp, lane);
-      else epilogue_tile<BN2, ACT, RES, ODT>(p, t, tmem_base, acc, acc_phase, &tfull[acc], mapa_u32(smem_u32(&tempty[acc]), 0), stage, warp, lane);
+      else epilogue_tile<BN2, ACT, RES, ODT>(p, t, tmem_base, acc * BN2, acc_phase, &tfull[acc], mapa_u32(smem_u32(&tempty[acc]), 0), stage, warp, lane);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -1030,8 +1055,30 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
   p.slab = (!two && eb == 2 && bn == 64 && a.kb_per_tap == 1 && a.tap_row_shift == 1 && p.k_blocks + BM - 1 <= 256) ? 1 : 0;
   p.slab_sub_bytes = p.umma_n * BK * 2;  // 48 x 128 B = 6 KB (base) / 8 KB (large): multiples of the 1024-byte swizzle atom
   if (p.slab && p.slab_sub_bytes % 1024 != 0) p.slab = 0;
-  p.slab_stages = 8;
-  while (p.slab && p.slab_stages * kSlabTaps * p.slab_sub_bytes > 8 * (BM * BK * 2 + 64 * BK * 2) - 2 * 256 * BK * 2) --p.slab_stages;
+  p.tile_m = BM;
+  p.slab_mt = 1;
+  p.slab_taps = kSlabTaps;
+  p.slab_parts = 1;
+  p.slab_box_rows = 256;
+  static const int mt_env = [] { const char* e = getenv("SCB_GEMM_SLAB_MT"); return e ? atoi(e) : 3; }();
+  if (p.slab && p.m_tiles_per_batch >= 2 && p.m_tiles_per_batch <= mt_env && p.m_tiles_per_batch <= 3) {
+    // every M tile of a batch entry in one work item: slab of mt * 128 + taps - 1 rows in two boxes
+    p.slab_mt = p.m_tiles_per_batch;
+    const int rows = p.slab_mt * BM + p.k_blocks - 1;
+    p.slab_parts = 2;
+    p.slab_box_rows = ((rows + 1) / 2 + 7) / 8 * 8;
+    p.tile_m = BM * p.slab_mt;
+    p.m_tiles_per_batch = 1;
+    p.num_tiles = p.groups * p.batch * p.n_tiles;
+  }
+  p.slab_bytes = p.slab_parts * p.slab_box_rows * BK * 2;
+  {
+    const int ring = 8 * (BM * BK * 2 + 64 * BK * 2);   // the BN = 64 kernel's A + B rings (8 stages)
+    const int region = ring - 2 * p.slab_bytes;          // what the two slabs leave for the weight sub-tiles
+    if (p.slab && region < 3 * kSlabTaps * p.slab_sub_bytes) p.slab_taps = 2;   // fewer taps per stage rather than a 2-deep ring
+    p.slab_stages = 8;
+    while (p.slab && p.slab_stages > 1 && p.slab_stages * p.slab_taps * p.slab_sub_bytes > region) --p.slab_stages;
+  }
   p.tx_bytes = (uint32_t)(BM * BK * 2 + p.umma_n * BK * 2);
   p.out = a.out;
   p.out2 = a.out2;
@@ -1056,7 +1103,7 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
     const uint64_t bstride = a.a_batch_stride ? (uint64_t)a.a_batch_stride : rows * (uint64_t)a.a_row_stride;
     const uint64_t dims[3] = {(uint64_t)a.a_inner, rows, (uint64_t)a.batch};
     const uint64_t strides[2] = {(uint64_t)a.a_row_stride * eb, bstride * eb};
-    const uint32_t box[3] = {(uint32_t)p.bk, (uint32_t)(p.slab ? 256 : BM), 1};
+    const uint32_t box[3] = {(uint32_t)p.bk, (uint32_t)(p.slab ? p.slab_box_rows : BM), 1};
     int e = make_tmap(&tmA, a.a, eb, 3, dims, strides, box, 1);
     if (e) return e;
   }
