@@ -514,7 +514,10 @@ _SIDE_STREAMS: dict = {}
 def _side_stream(device, which: str = "image") -> "torch.cuda.Stream":
     key = (str(device), which)
     if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+        # The speech tower is the long pole of a step: its stream outranks the image tower's, so that the image tower's short
+        # kernels fill SMs the speech kernels leave idle instead of queueing in front of them (SCB_TOWER_PRIORITY=0: equal).
+        prio = -1 if (which == "audio" and os.environ.get("SCB_TOWER_PRIORITY", "1") != "0") else 0
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device, priority=prio)
     return _SIDE_STREAMS[key]
 
 
