@@ -310,9 +310,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       wait_bar(pv_done + 1, pt ^ 1u);
       tc_fence_after();
       ATTN_TRACE(tr, trace_tile + trace_off, 4);
-      const uint2 pc = *my_cold;   // output row pointer (lo, hi); bit 63: the tile is live for this quarter
-      uint16_t* const pend_dst = reinterpret_cast<uint16_t*>(((unsigned long long)(pc.y & 0x7FFFFFFFu) << 32) | pc.x);
+      const uint2 pc = *my_cold;   // output pointer of the quarter's first row (48 bits), valid rows (bits 56..61), live (bit 63)
+      uint16_t* const qbase = reinterpret_cast<uint16_t*>(((unsigned long long)(pc.y & 0x00FFFFFFu) << 32) | pc.x);
       const bool pend_live = (pc.y >> 31) != 0;
+      const int pend_rows = (int)((pc.y >> 24) & 63u);
       uint32_t ov[16], lv[8];
       if (pend_live) {
         tmem_ld_32x16(lane_addr + (uint32_t)(O_COL + part * 16), ov);
@@ -323,10 +324,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
-      if (pend_live && pend_dst != nullptr) {
+      if (pend_live) {
+        // Row-per-lane stores would touch 32 different 32-byte sectors per warp instruction (measured: the drain of a full tile
+        // took ~1300 clocks, ~400 when only two quarters were live — LSU wavefronts).  The quarter's 32 x 128 B go through a
+        // swizzled staging tile instead: the last P block, which the finished P V no longer reads and which this quarter's
+        // warps only rewrite (exp pass of half 1) behind their next named barrier; 8 lanes then write one full 128-byte row.
         const float sum = __uint_as_float(lv[0]);
         const float pend_inv = sum > 0.f ? 1.f / sum : 0.f;   // no visible key: zeros, like the masked softmax of the reference's padding rows
-        uint16_t* dst = pend_dst;
+        uint8_t* const stage = sP + 4 * (BQ * 128);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           uint4 u;
@@ -334,7 +339,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             uu[i] = H16<BF16 ? SCB_BF16 : SCB_F16>::pack(__uint_as_float(ov[t * 8 + 2 * i]) * pend_inv, __uint_as_float(ov[t * 8 + 2 * i + 1]) * pend_inv);
-          *reinterpret_cast<uint4*>(dst + t * 8) = u;
+          *reinterpret_cast<uint4*>(stage + r * 128 + (((2 * part + t) ^ rx) << 4)) = u;
+        }
+        named_bar_sync(1 + q, 128);
+        const int tq = part * 32 + lane, unit = tq & 7;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int row = k * 16 + (tq >> 3);
+          if (row < pend_rows)
+            *reinterpret_cast<uint4*>(qbase + (long long)row * p.o_ld + unit * 8) =
+                *reinterpret_cast<const uint4*>(stage + (q * 32 + row) * 128 + ((unit ^ (row & 7)) << 4));
         }
       }
     };
@@ -487,9 +501,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         ATTN_TRACE(tr, trace_tile + trace_off, 9);
         ++trace_tile;
         {
-          const unsigned long long dst = row_g < p.Tq ? (unsigned long long)(p.o + (long long)(item / p.heads) * p.o_bs + (long long)row_g * p.o_ld +
-                                                                             (item % p.heads) * HD + part * 16) : 0ull;
-          *my_cold = make_uint2((uint32_t)dst, (uint32_t)(dst >> 32) | (live ? 0x80000000u : 0u));
+          const int row0 = qt * BQ + q * 32;   // first query of this quarter
+          const unsigned long long dst = (unsigned long long)(p.o + (long long)(item / p.heads) * p.o_bs + (long long)row0 * p.o_ld + (item % p.heads) * HD);
+          const uint32_t rows = (uint32_t)max(0, min(32, p.Tq - row0));
+          *my_cold = make_uint2((uint32_t)dst, ((uint32_t)(dst >> 32) & 0x00FFFFFFu) | (rows << 24) | (live ? 0x80000000u : 0u));
         }
         have_pend = true;
         pt ^= 1u;
