@@ -435,6 +435,39 @@ __global__ void __launch_bounds__(256) transpose_kernel(const TI* __restrict__ i
   }
 }
 
+// 16-bit -> 16-bit transpose (the bf16 operands of the head's wgrad GEMMs: [B*(T+1), 2d] and [B*(T+1), d] per step) with 16-byte
+// global accesses on both sides.  A 64 x 64 tile lives in shared memory as 64 rows of 32 words (two adjacent columns per word)
+// + 1 pad word.  Load: 8 lanes read one 128-byte input row.  Store: a thread gathers word w of 8 consecutive rows, splits the
+// low / high halves into the 16-byte pieces of output rows 2w and 2w+1, and 8 lanes (8 row groups) write one full 128-byte
+// output row — the element-wise 32 x 32 version moved 64 bytes per warp instruction (0.4 ms per step, 31 % of the HBM rate).
+__global__ void __launch_bounds__(256) transpose16_kernel(const uint16_t* __restrict__ in, long long in_ld, uint16_t* __restrict__ out,
+                                                          long long out_ld, int rows, int cols) {
+  __shared__ uint32_t tile[64][33];
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int row = (t >> 3) + 32 * pass, chunk = t & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r0 + row < rows && c0 + chunk * 8 < cols) v = *reinterpret_cast<const uint4*>(in + (long long)(r0 + row) * in_ld + c0 + chunk * 8);
+    uint32_t* d = &tile[row][chunk * 4];
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  __syncthreads();
+  const int g = t & 7, w = t >> 3;   // 8 input rows r0 + 8g .. +7; input columns c0 + 2w, c0 + 2w + 1
+  uint32_t x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = tile[g * 8 + i][w];
+  uint4 lo, hi;
+  lo.x = __byte_perm(x[0], x[1], 0x5410); lo.y = __byte_perm(x[2], x[3], 0x5410); lo.z = __byte_perm(x[4], x[5], 0x5410); lo.w = __byte_perm(x[6], x[7], 0x5410);
+  hi.x = __byte_perm(x[0], x[1], 0x7632); hi.y = __byte_perm(x[2], x[3], 0x7632); hi.z = __byte_perm(x[4], x[5], 0x7632); hi.w = __byte_perm(x[6], x[7], 0x7632);
+  const int r = r0 + g * 8, c = c0 + 2 * w;
+  if (r < rows) {   // rows % 8 == 0 (checked by the launcher): a group of 8 is inside or outside
+    if (c < cols) *reinterpret_cast<uint4*>(out + (long long)c * out_ld + r) = lo;
+    if (c + 1 < cols) *reinterpret_cast<uint4*>(out + (long long)(c + 1) * out_ld + r) = hi;
+  }
+}
+
 }  // namespace
 
 int conv0_groupnorm_gelu(const float* wav, long long wav_ld, int batch, int n_samples, const float* w, const float* conv_bias,
@@ -566,6 +599,14 @@ int transpose(const void* in, int in_dtype, long long in_ld, void* out, int out_
   SCB_CHECK(in && out, SCB_EINVAL, "scb_transpose: null operand");
   if (rows == 0 || cols == 0) return SCB_OK;
   SCB_CHECK((rows + 31) / 32 <= 65535, SCB_EUNSUPPORTED, "scb_transpose: too many rows (%d)", rows);
+  if (in_dtype == out_dtype && in_dtype != SCB_F32 && rows % 8 == 0 && cols % 8 == 0 && in_ld % 8 == 0 && out_ld % 8 == 0 &&
+      ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    transpose16_kernel<<<dim3((cols + 63) / 64, (rows + 63) / 64), 256, 0, st>>>(static_cast<const uint16_t*>(in), in_ld, static_cast<uint16_t*>(out),
+                                                                                  out_ld, rows, cols);
+    note_launch();
+    SCB_LAUNCH_OK("transpose16");
+    return SCB_OK;
+  }
   if (in_dtype == SCB_F32) return transpose_out((const float*)in, in_ld, out, out_dtype, out_ld, rows, cols, st);
   if (in_dtype == SCB_F16) return transpose_out((const __half*)in, in_ld, out, out_dtype, out_ld, rows, cols, st);
   return transpose_out((const __nv_bfloat16*)in, in_ld, out, out_dtype, out_ld, rows, cols, st);

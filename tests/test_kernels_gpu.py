@@ -534,3 +534,21 @@ def test_retrieval_rank_matches_oracle_and_fixture(golden):
     top1 = torch.empty(nA, device=DEV, dtype=torch.int32)
     ops.retrieval_rank(sc, None, None, None, top1)
     assert torch.equal(top1.long(), sc.argmax(1))
+
+
+# ------------------------------------------------------------------------------------------------ transposes
+@pytest.mark.parametrize("rows,cols,out_pad", [(64, 64, 0), (4608, 1536, 256), (328, 72, 8), (81920 // 8, 768, 0), (100, 36, 0), (7, 5, 0)])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_transpose_16bit(rows, cols, out_pad, dt):
+    """dst[c, r] = src[r, c]: the vectorised 64 x 64 kernel (rows, cols, leading dimensions multiples of 8) and the generic one;
+    the output may be a column slice of a wider buffer (the wgrad operand buffers are padded to the split-K length)."""
+    from speechclip_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(rows + cols)
+    src_full = torch.randn(rows, cols + 8, device=DEV, generator=g).to(dt)
+    src = src_full[:, :cols]                      # row stride cols + 8
+    buf = torch.full((cols, rows + out_pad), 3.0, device=DEV, dtype=dt)
+    ops.transpose(src, buf[:, :rows])
+    torch.cuda.synchronize()
+    assert torch.equal(buf[:, :rows], src.t())
+    if out_pad:
+        assert (buf[:, rows:] == 3.0).all()
