@@ -30,10 +30,11 @@ template <int BN> struct EpiCfg {
 // Epilogues whose output is 16-bit with no residual (QKV, fc1, the conv stack, CLIP c_fc), and the fp32 + residual epilogues
 // of the CTA-pair kernel (out-proj, fc2), leave through TMA stores: see epilogue_tile_tma / epilogue_tile_tma_res.  They give
 // up one pipeline stage for the 64 KB of staging.
-// (fp32 output + 16-bit residual only on CTA pairs, where it measured 137 -> 127 us on the HuBERT out-proj; with an fp32
-// residual the row-per-lane residual reads cost more L1 wavefronts than the transpose patch they replace: 156 -> 182 us.)
+// (fp32 output + residual only on CTA pairs.  A 16-bit residual is read row-per-lane: 137 -> 127 us on the HuBERT out-proj.  An
+// fp32 residual read that way costs more L1 wavefronts than the transpose patch it replaces (156 -> 182 us), so it arrives by
+// TMA instead, INTO the staging tile the result leaves from: see epilogue_tile_tma_res.)
 __host__ __device__ constexpr bool tma_out(bool pair, int BN, int ACT, int RES, int ODT) {
-  return BN == 256 && ACT >= 0 && ((RES == 3 && ODT == SCB_F16) || (pair && ODT == SCB_F32 && RES == SCB_F16));
+  return BN == 256 && ACT >= 0 && ((RES == 3 && ODT == SCB_F16) || (pair && ODT == SCB_F32 && (RES == SCB_F16 || RES == SCB_F32)));
 }
 
 // stream-K workspace (scb_gemm_args.workspace): arrival counters, then one [2][128 x 256] fp32 slot per CTA pair
@@ -137,7 +138,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
   const int prow = lane >> 2, u = lane & 3;  // after the transpose: row (within a pass of 8) and 4-column unit of this lane
   const int act = ACT >= 0 ? ACT : p.act;
   const bool has_res = RES >= 0 ? (RES != 3) : (p.residual != nullptr);
-  const int res_dt = (RES >= 0 && RES != 3) ? RES : p.residual_dtype;
+  const int res_dt = (RES >= 0 && RES != 3) ? (RES & 15) : p.residual_dtype;   // (RES = 16 + dtype: the same, kept off the TMA epilogue)
   const int out_dt = ODT >= 0 ? ODT : p.out_dtype;
   void* const out2 = ODT >= 0 ? nullptr : p.out2;
   {
@@ -303,12 +304,74 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
 // (32 columns: 64 contiguous bytes of fp16 or 128 of fp32, issued before the accumulator wait), adds, writes the 32 fp32
 // columns as eight swizzled 16-byte units of a [32 rows][128 B] staging tile and one lane issues the TMA store; a warp's 64
 // columns are two such rounds through the same 4 KB tile (the second waits for the first store's shared-memory reads).
+// fp32 residual (pre-LN towers: CLIP ViT, HuBERT-large): the warp's 32 x 32 residual box is TMA-loaded into the staging tile
+// itself (same box and swizzle as the store), each lane adds its accumulator row in place (8 conflict-free 16-byte units) and
+// the tile leaves by TMA again — no per-lane global addressing on either side.  rbar / rphase: the warp's own mbarrier for
+// the residual loads and its running parity.
 template <int RES>
-__device__ __forceinline__ void epilogue_tile_tma_res(const GemmParams& p, const CUtensorMap* tmO, const TileCoord& t, uint32_t tmem_base,
-                                                      int acc, uint32_t acc_phase, uint64_t* tfull_bar, uint32_t tempty_addr,
-                                                      uint8_t* stage_all, int warp, int lane) {
+__device__ __forceinline__ void epilogue_tile_tma_res(const GemmParams& p, const CUtensorMap* tmO, const CUtensorMap* tmR, const TileCoord& t,
+                                                      uint32_t tmem_base, int acc, uint32_t acc_phase, uint64_t* tfull_bar, uint32_t tempty_addr,
+                                                      uint8_t* stage_all, uint64_t* rbar, uint32_t& rphase, int warp, int lane) {
   constexpr int BN = 256, COLS = EpiCfg<BN>::COLS;
   static_assert(COLS == 64, "two 32-column rounds per warp");
+  if constexpr (RES == SCB_F32) {
+    const int q = warp & 3;
+    const int part = (warp - 4) >> 2;
+    const int m_base = t.m0 + q * 32;
+    const int col_base = t.n0 + part * COLS;
+    uint8_t* const tile = stage_all + (warp - 4) * (32 * 128);
+    const uint32_t stg = smem_u32(tile) + (uint32_t)lane * 128u;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    const bool live = col_base < p.n && m_base < p.m_per_batch;
+    const bool has_bias = p.bias != nullptr;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (live && lane == 0) {
+        bulk_wait_read0();  // the previous store (last tile / first round) has finished reading the staging tile
+        mbar_expect_tx(rbar, 32u * 128u);
+        tma_load_3d(tile, tmR, rbar, col_base + h * 32, m_base, t.b);   // rows / columns past the edges arrive as zeros
+      }
+      if (h == 0) {
+        mbar_wait(tfull_bar, acc_phase);
+        tc_fence_after();
+      }
+      uint32_t v[32];
+      if (live) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + part * COLS + h * 32), v);
+      tmem_ld_wait();
+      if (h == 1) {  // accumulator fully read by this warp: hand the buffer back to the MMA warp
+        tc_fence_before();
+        if (lane == 0) mbar_arrive_cluster(tempty_addr);
+      }
+      if (live) {
+        mbar_wait(rbar, rphase);
+        rphase ^= 1u;
+        const uint64_t al2 = pk2(p.alpha, p.alpha);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // 4 columns -> one 16-byte unit of fp32
+          float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_bias) b0 = __ldg(reinterpret_cast<const float4*>(p.bias + min(col_base + h * 32 + k * 4, p.n - 4)));
+          const uint32_t addr = stg + (((uint32_t)k ^ sw) << 4);
+          uint32_t r0, r1, r2, r3;
+          ld_shared_v4(addr, r0, r1, r2, r3);
+          const uint64_t x0 = add2(fma2(al2, pk2(__uint_as_float(v[4 * k + 0]), __uint_as_float(v[4 * k + 1])), pk2(b0.x, b0.y)),
+                                   pk2(__uint_as_float(r0), __uint_as_float(r1)));
+          const uint64_t x1 = add2(fma2(al2, pk2(__uint_as_float(v[4 * k + 2]), __uint_as_float(v[4 * k + 3])), pk2(b0.z, b0.w)),
+                                   pk2(__uint_as_float(r2), __uint_as_float(r3)));
+          float o0, o1, o2, o3;
+          upk2(x0, o0, o1);
+          upk2(x1, o2, o3);
+          st_shared_v4(addr, __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2), __float_as_uint(o3));
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(tmO, stg, col_base + h * 32, m_base, t.b);
+          bulk_commit();
+        }
+      }
+    }
+    return;
+  }
   constexpr int RW = RES == SCB_F32 ? 8 : 4;  // 16-byte units of residual per lane per round
   const int q = warp & 3;
   const int part = (warp - 4) >> 2;
@@ -581,9 +644,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ------------------------------------------------------------------ epilogue (see epilogue_tile)
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t rphase_unused = 0;   // (the TMA-loaded fp32 residual exists on CTA pairs only)
+    (void)rphase_unused;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile<BN>(p, tile);
-      if constexpr (TMAO && ODT == SCB_F32) epilogue_tile_tma_res<RES>(p, &tmO, t, tmem_base, acc, acc_phase, &tfull[acc], smem_u32(&tempty[acc]), epi, warp, lane);
+      if constexpr (TMAO && ODT == SCB_F32) epilogue_tile_tma_res<RES>(p, &tmO, &tmO, t, tmem_base, acc, acc_phase, &tfull[acc], smem_u32(&tempty[acc]), epi, nullptr, rphase_unused, warp, lane);
       else if constexpr (TMAO) epilogue_tile_tma<ACT>(p, &tmO, t, tmem_base, acc, acc_phase, &tfull[acc], smem_u32(&tempty[acc]), epi, warp, lane);
       else if (BN == 64 && p.slab_mt > 1) {   // several M tiles per accumulator buffer (256 columns per buffer, 64 per tile)
         for (int mt = 0; mt < p.slab_mt; ++mt) {
@@ -761,7 +826,7 @@ __device__ __forceinline__ void sk_reduce(const float* slots, size_t slot_stride
 template <int ACT, int RES, int ODT, bool SK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<BN2>::THREADS, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
+                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int B_BYTES = (BN2 / 2) * BK * 2;
   constexpr bool TMAO = tma_out(true, BN2, ACT, RES, ODT);
@@ -776,8 +841,10 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* rbar = tempty + 2;   // [16] one per epilogue warp: its TMA-loaded residual box has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + EpiCfg<BN2>::WARPS);
   float* stage = reinterpret_cast<float*>(epi);
+  constexpr bool TMAR = TMAO && ODT == SCB_F32 && RES == SCB_F32;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -789,6 +856,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (TMAO) tma_prefetch_desc(&tmO);
+    if (TMAR) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -799,6 +867,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_init(&tfull[s], 1);
       mbar_init(&tempty[s], 2 * EpiCfg<BN2>::WARPS);
     }
+    for (int s = 0; s < EpiCfg<BN2>::WARPS; ++s) mbar_init(&rbar[s], 1);
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc_2sm<2 * BN2>(tmem_slot);
@@ -880,6 +949,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     int acc = 0;
     uint32_t acc_phase = 0;
     constexpr size_t kSlot = (size_t)BM * BN2;  // floats per CTA slot; a pair's two slots are adjacent
+    uint32_t rphase = 0;
     int tile, kb0, kb1;
     for (int it = 0; sk_item<SK>(p, pair, num_pairs, it, tile, kb0, kb1); ++it) {
       const TileCoord t = decode_tile2(p, tile, (int)rank);
@@ -896,7 +966,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         sk_reduce(p.sk_part + ((size_t)(pair + 1) * 2 + rank) * kSlot, 2 * kSlot, sk_partners(p, pair, num_pairs, r),
                   p.sk_flags + r * 2 + (int)rank, tmem_base, acc, acc_phase, &tfull[acc], warp, lane);
       }
-      if constexpr (TMAO && ODT == SCB_F32) epilogue_tile_tma_res<RES>(p, &tmO, t, tmem_base, acc, acc_phase, &tfull[acc], mapa_u32(smem_u32(&tempty[acc]), 0), epi, warp, lane);
+      if constexpr (TMAO && ODT == SCB_F32) epilogue_tile_tma_res<RES>(p, &tmO, &tmR, t, tmem_base, acc, acc_phase, &tfull[acc], mapa_u32(smem_u32(&tempty[acc]), 0), epi, &rbar[warp - 4], rphase, warp, lane);
       else if constexpr (TMAO) epilogue_tile_tma<ACT>(p, &tmO, t, tmem_base, acc, acc_phase, &tfull[acc], mapa_u32(smem_u32(&tempty[acc]), 0), epi, warp, lane);
       else epilogue_tile<BN2, ACT, RES, ODT>(p, t, tmem_base, acc * BN2, acc_phase, &tfull[acc], mapa_u32(smem_u32(&tempty[acc]), 0), stage, warp, lane);
       acc ^= 1;
@@ -914,9 +984,10 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 template <int ACT, int RES, int ODT, bool SK>
-int launch2_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p, cudaStream_t stream) {
+int launch2_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR, const GemmParams& p,
+                 cudaStream_t stream) {
   constexpr bool TMAO = tma_out(true, BN2, ACT, RES, ODT);
-  constexpr int smem_bytes = stages2(TMAO) * (BM * BK * 2 + (BN2 / 2) * BK * 2) + 1024 + 256 +
+  constexpr int smem_bytes = stages2(TMAO) * (BM * BK * 2 + (BN2 / 2) * BK * 2) + 1024 + 512 +
                              (TMAO ? EpiCfg<BN2>::TMA_BYTES : EpiCfg<BN2>::PATCH_BYTES);
   static_assert(smem_bytes <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
   static bool configured = false;
@@ -926,15 +997,16 @@ int launch2_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
   }
   int pairs = num_sms() / 2;
   if (p.num_tiles < pairs && !SK) pairs = p.num_tiles;
-  SCB_CUDA(launch_pdl(gemm2_tcgen05_kernel<ACT, RES, ODT, SK>, dim3((unsigned)(2 * pairs)), EpiCfg<BN2>::THREADS, smem_bytes, stream, tmA, tmB, tmO, p));
+  SCB_CUDA(launch_pdl(gemm2_tcgen05_kernel<ACT, RES, ODT, SK>, dim3((unsigned)(2 * pairs)), EpiCfg<BN2>::THREADS, smem_bytes, stream, tmA, tmB, tmO, tmR, p));
   note_launch();
   SCB_LAUNCH_OK("gemm2_tcgen05");
   return SCB_OK;
 }
 // the stream-K variant is a separate instantiation: its dump / reduce paths cost the plain kernel neither registers nor branches
 template <int ACT, int RES, int ODT>
-int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p, cudaStream_t stream) {
-  return p.sk_rem ? launch2_impl<ACT, RES, ODT, true>(tmA, tmB, tmO, p, stream) : launch2_impl<ACT, RES, ODT, false>(tmA, tmB, tmO, p, stream);
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR, const GemmParams& p,
+            cudaStream_t stream) {
+  return p.sk_rem ? launch2_impl<ACT, RES, ODT, true>(tmA, tmB, tmO, tmR, p, stream) : launch2_impl<ACT, RES, ODT, false>(tmA, tmB, tmO, tmR, p, stream);
 }
 
 template <int BN, int STAGES, int ACT = -1, int RES = -1, int ODT = -1>
@@ -1128,8 +1200,19 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
   // modes 1, 3, 4 store through TMA: [batch][rows][cols] view of the output, 32-row x 64-column boxes in the 128B swizzle
   static const int tma_env = [] { const char* e = getenv("SCB_GEMM_TMA_STORE"); return e ? atoi(e) : 1; }();
   if (mode != 0 && (a.groups != 1 || tma_env == 0)) mode = 0;   // (the generic register-store epilogue handles everything)
-  CUtensorMap tmO = tmA;
-  if (mode == 1 || mode == 3 || mode == 4 || (mode == 5 && two)) {  // 32-row boxes of 128 bytes: 64 16-bit or 32 fp32 columns
+  // fp32 residual by TMA (mode 2 on pairs) needs a residual laid out like the output: a [m_per_batch][n] table broadcast over the
+  // batch (stride 0: the patch-embedding GEMM's positional table) stays on the register-store path
+  if (mode == 2 && two && a.batch > 1 && a.residual_ld != 0 && a.residual_batch_stride == 0) mode = 0;
+  CUtensorMap tmO = tmA, tmR = tmA;
+  if (mode == 2 && two) {
+    const uint64_t dims[3] = {(uint64_t)a.n, (uint64_t)a.m_per_batch, (uint64_t)a.batch};
+    const uint64_t bstride = p.res_batch_stride ? (uint64_t)p.res_batch_stride : (uint64_t)a.m_per_batch * (uint64_t)p.res_ld;
+    const uint64_t strides[2] = {(uint64_t)p.res_ld * 4, bstride * 4};
+    const uint32_t box[3] = {32, 32, 1};
+    int e = make_tmap(&tmR, a.residual, 4, 3, dims, strides, box, 1);
+    if (e) return e;
+  }
+  if (mode == 1 || mode == 3 || mode == 4 || ((mode == 5 || mode == 2) && two)) {  // 32-row boxes of 128 bytes: 64 16-bit or 32 fp32 columns
     const int ob = a.out_dtype == SCB_F32 ? 4 : 2;
     const uint64_t dims[3] = {(uint64_t)a.n, (uint64_t)a.m_per_batch, (uint64_t)a.batch};
     const uint64_t bstride = a.out_batch_stride ? (uint64_t)a.out_batch_stride : (uint64_t)a.m_per_batch * (uint64_t)a.ldc;
@@ -1140,12 +1223,17 @@ int gemm(const scb_gemm_args& a, cudaStream_t stream) {
   }
   if (two) {
     switch (mode) {
-      case 1: return launch2<SCB_ACT_NONE, 3, SCB_F16>(tmA, tmB, tmO, p, stream);
-      case 2: return launch2<SCB_ACT_NONE, SCB_F32, SCB_F32>(tmA, tmB, tmO, p, stream);
-      case 3: return launch2<SCB_ACT_GELU_ERF, 3, SCB_F16>(tmA, tmB, tmO, p, stream);
-      case 4: return launch2<SCB_ACT_QUICK_GELU, 3, SCB_F16>(tmA, tmB, tmO, p, stream);
-      case 5: return launch2<SCB_ACT_NONE, SCB_F16, SCB_F32>(tmA, tmB, tmO, p, stream);
-      default: return launch2<-1, -1, -1>(tmA, tmB, tmO, p, stream);
+      case 1: return launch2<SCB_ACT_NONE, 3, SCB_F16>(tmA, tmB, tmO, tmR, p, stream);
+      // fp32 residual: by TMA through the staging tile for short K, where the epilogue bounds the tile (ViT out-proj 38.8 -> 32.4 us,
+      // HuBERT-large out-proj 61.5 -> 58.0); for long K the main loop bounds it and the 6th pipeline stage is worth more than
+      // the epilogue (fc2 at K = 3072 / 4096 measured 5-6 % slower on the TMA path), so those keep the register-store epilogue
+      case 2:
+        return p.k_blocks <= 24 ? launch2<SCB_ACT_NONE, SCB_F32, SCB_F32>(tmA, tmB, tmO, tmR, p, stream)
+                                : launch2<SCB_ACT_NONE, 16 + SCB_F32, SCB_F32>(tmA, tmB, tmO, tmR, p, stream);
+      case 3: return launch2<SCB_ACT_GELU_ERF, 3, SCB_F16>(tmA, tmB, tmO, tmR, p, stream);
+      case 4: return launch2<SCB_ACT_QUICK_GELU, 3, SCB_F16>(tmA, tmB, tmO, tmR, p, stream);
+      case 5: return launch2<SCB_ACT_NONE, SCB_F16, SCB_F32>(tmA, tmB, tmO, tmR, p, stream);
+      default: return launch2<-1, -1, -1>(tmA, tmB, tmO, tmR, p, stream);
     }
   }
   if (bn == 256) {
