@@ -552,3 +552,27 @@ def test_transpose_16bit(rows, cols, out_pad, dt):
     assert torch.equal(buf[:, :rows], src.t())
     if out_pad:
         assert (buf[:, rows:] == 3.0).all()
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("d,act,affine", [(512, 1, True), (512, 0, False), (264, 2, True), (64, 1, True)])
+def test_layernorm_16bit_rows_kernel(dt, d, act, affine):
+    """16-bit in, 16-bit out, many rows (the HuBERT-large conv blocks run LayerNorm + GELU in place over B x T x 512): the
+    grid-stride kernel with gamma / beta in registers and 16-byte accesses; in place and into a strided output."""
+    from speechclip_b200 import ops
+    rows = 5003
+    x = randn(rows, d, seed=d + act).to(dt)
+    g = 1 + 0.1 * randn(d, seed=2) if affine else None
+    b = 0.1 * randn(d, seed=3) if affine else None
+    ref = F.layer_norm(x.float(), (d,), g, b, 1e-5)
+    if act == 1:
+        ref = F.gelu(ref)
+    elif act == 2:
+        ref = ref * torch.sigmoid(1.702 * ref)
+    tol = 6e-3 if dt == torch.float16 else 4e-2
+    wide = torch.full((rows, d + 16), 5.0, device=DEV, dtype=dt)
+    ops.layernorm(x, g, b, y16=wide[:, :d], rows=rows, d=d, x_ld=d, y_ld=d + 16, act=act)
+    assert (wide[:, :d].float() - ref).abs().max() < tol
+    assert (wide[:, d:] == 5.0).all()
+    ops.layernorm(x, g, b, y16=x, rows=rows, d=d, act=act)   # in place
+    assert (x.float() - ref).abs().max() < tol
