@@ -217,9 +217,12 @@ def run_own(args):
         per_gpu = args.batch
     global_batch = per_gpu * world
     # CUDA-graph replay of the frozen towers: needed once the per-GPU batch is small enough for python/ctypes launch time
-    # (~10 ms per step) to bound the step; with graphs the per-kernel events cannot be taken inside the timed region, so the
-    # roofline numbers then come from one extra eager, event-instrumented step after it.
-    use_graphs = args.graphs == "on" or (args.graphs == "auto" and per_gpu < 256)
+    # (~10 ms per step) to bound the step, and used up to 256 pairs per GPU because it takes the host out of the timed region
+    # (eager enqueue measured 8-28 ms per 35 ms step on the shared boxes, 3.5 ms with graphs; same device time).  With graphs
+    # the per-kernel events cannot be taken inside the timed region, so the roofline numbers come from eager, event-
+    # instrumented steps after it.  Above 256 pairs per GPU (config 5: 512) the graphs' private buffers would not fit beside
+    # the pipeline's two tower slots.
+    use_graphs = args.graphs == "on" or (args.graphs == "auto" and per_gpu <= 256)
     engine.GRAPHS = use_graphs
 
     if args.config == "cascaded":   # BASELINE.json configs[2]: keyword VQ + CLIP text tower, 8112-entry reduced vocabulary
@@ -291,7 +294,11 @@ def run_own(args):
 
     # warm-up: every CUDA-graph signature is run eagerly once, captured on its second use and replayed from the third; the
     # pipeline alternates two tower slots, so it needs six steps before every step is a replay
-    n_warm = max(args.warmup, 6 if pipe is not None else 3)
+    n_warm = max(args.warmup, 3)
+    setup_steps = max(0, (6 if pipe is not None else 3) - n_warm)   # graph warm / capture passes that the W warm-up steps do not cover
+    if setup_steps:
+        run_steps(resident for _ in range(setup_steps))
+        barrier()
     run_steps(resident for _ in range(n_warm))
     barrier()
 
@@ -309,10 +316,13 @@ def run_own(args):
     ms_total = timed(lambda: run_steps(resident for _ in range(args.steps)), 1)
     host_ms = timed.host_ms / args.steps
     launches = lib.launch_count() + engine.graph_replayed_kernels() - n0
-    prof_steps = 1 if use_graphs else min(args.steps, 5)
+    prof_steps = 3 if use_graphs else min(args.steps, 5)
     overlap, kwclip_mod.OVERLAP_TOWERS = kwclip_mod.OVERLAP_TOWERS, False
     ops.PROFILE = []
-    for _ in range(prof_steps):
+    for i in range(prof_steps + (1 if use_graphs else 0)):
+        if use_graphs and i == 1:
+            torch.cuda.synchronize()
+            ops.PROFILE = []   # the first eager step after graph replay allocates the eager workspace: not counted
         if pipe is not None:   # same tower buffers as the timed steps (slot 1), both towers on this stream
             b = dict(resident)
             b["_scb_towers"] = model.precompute_towers(resident, slot=1, overlap=False)
@@ -450,7 +460,7 @@ def run_own(args):
                    "mode": "training step (model.train()): branch dropout p=0.1 active (Philox masks, regenerated in backward), frozen towers in eval arithmetic, trainable branch "
                            + ("2.77 M params (+ frozen CLIP text tower in the differentiated path)" if args.config == "cascaded" else "7.48 M params"),
                    "l2": "inputs (259 MB) and activations (GBs) larger than the 126 MB L2; no flush needed",
-                   "cuda_graphs": use_graphs, "tower_pipeline": pipe is not None, "tower_streams": 2 if kwclip_mod.OVERLAP_TOWERS else 1},
+                   "cuda_graphs": use_graphs, "tower_pipeline": pipe is not None, "setup_steps_before_warmup": setup_steps, "tower_streams": 2 if kwclip_mod.OVERLAP_TOWERS else 1},
         "e2e": {"value": global_batch / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "h2d_gb_per_s_measured": h2d_gbs, "numa_node_bound": numa_node, "passes_ms_per_step": [t[0] for t in passes],
                 "reported": "median pass", "fastest_pass_ms_per_step": min(t[0] for t in passes), "diagnostics": e2e_diag,
