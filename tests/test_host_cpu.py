@@ -359,3 +359,39 @@ def test_lightning_checkpoint_roundtrip(tmp_path):
     assert list(sd2) == list(sd)
     for k in sd:
         assert torch.equal(sd[k], sd2[k]), k
+
+
+def test_tower_pipeline_order_and_slots_without_a_gpu():
+    """runtime.TowerPipeline: the towers of batch i + 1 are launched BEFORE batch i is handed to the loop body, tower buffer slots
+    alternate 1 / 2, every batch carries its own handle, and a prefetcher without a look-ahead slot is refused."""
+    from speechclip_b200.runtime import TowerPipeline
+
+    log = []
+
+    class FakeModel:
+        def precompute_towers(self, batch, slot=0):
+            log.append(("launch", batch["i"], slot))
+            return {"for": batch["i"], "slot": slot}
+
+    pipe = TowerPipeline(FakeModel(), head_priority=False)
+    seen = []
+    for b in pipe.iterate({"i": i} for i in range(5)):
+        log.append(("step", b["i"]))
+        assert b["_scb_towers"]["for"] == b["i"]
+        seen.append((b["i"], b["_scb_towers"]["slot"]))
+    assert seen == [(0, 1), (1, 2), (2, 1), (3, 2), (4, 1)]
+    order = [e[:2] for e in log]
+    for i in range(4):   # launch(i + 1) precedes step(i)
+        assert order.index(("launch", i + 1)) < order.index(("step", i))
+    assert order.index(("launch", 0)) == 0 and order[-1] == ("step", 4)
+    assert list(pipe.iterate(iter(()))) == []   # empty epoch
+
+    class NoLookahead:
+        lookahead = 0
+
+        def __iter__(self):
+            return iter(())
+
+    import pytest
+    with pytest.raises(ValueError, match="lookahead=1"):
+        list(TowerPipeline(FakeModel(), head_priority=False).iterate(NoLookahead()))
